@@ -1,0 +1,278 @@
+// Shared device helpers of libfpq_b200 (constant grid tables, streaming loads/stores, the
+// 16-elements-per-lane register tile, group reductions, launch bookkeeping).
+//
+// Thread mapping of the group kernels: a group of GS contiguous elements is owned by
+// LPG = GS/16 adjacent lanes; lane l holds 16 elements as 16-byte vectors, vector j of lane l
+// covering elements [j*VEC*LPG + l*VEC, +VEC).  One warp-wide 128-bit load therefore touches
+// 32/LPG groups x (16*LPG) contiguous bytes: whole 128-byte lines for the reference's GS=128.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stddef.h>
+
+#include "../../include/fpq_b200.h"
+#include "fpq_round.cuh"
+
+namespace fpq {
+
+// ------------------------------------------------------------------------------------------
+// constant tables: the reference's grids spelled out (one private copy per translation unit)
+// ------------------------------------------------------------------------------------------
+#define E2M1_POS_ 0.5f, 1.0f, 1.5f, 2.0f, 3.0f, 4.0f, 6.0f
+#define E2M1_NEG_ -6.0f, -4.0f, -3.0f, -2.0f, -1.5f, -1.0f, -0.5f
+#define E1M2_POS_ 0.25f, 0.5f, 0.75f, 1.0f, 1.25f, 1.5f, 1.75f
+#define E1M2_NEG_ -1.75f, -1.5f, -1.25f, -1.0f, -0.75f, -0.5f, -0.25f
+#define E3M0_POS_ 0.25f, 0.5f, 1.0f, 2.0f, 4.0f, 8.0f, 16.0f
+#define E3M0_NEG_ -16.0f, -8.0f, -4.0f, -2.0f, -1.0f, -0.5f, -0.25f
+#define E2M3_POS_ 0.125f, 0.25f, 0.375f, 0.5f, 0.625f, 0.75f, 0.875f, 1.0f, 1.125f, 1.25f, 1.375f, 1.5f, 1.625f, 1.75f, 1.875f, \
+                  2.0f, 2.25f, 2.5f, 2.75f, 3.0f, 3.25f, 3.5f, 3.75f, 4.0f, 4.5f, 5.0f, 5.5f, 6.0f, 6.5f, 7.0f, 7.5f
+#define E2M3_NEG_ -7.5f, -7.0f, -6.5f, -6.0f, -5.5f, -5.0f, -4.5f, -4.0f, -3.75f, -3.5f, -3.25f, -3.0f, -2.75f, -2.5f, -2.25f, -2.0f, \
+                  -1.875f, -1.75f, -1.625f, -1.5f, -1.375f, -1.25f, -1.125f, -1.0f, -0.875f, -0.75f, -0.625f, -0.5f, -0.375f, -0.25f, -0.125f
+#define E3M2_POS_ 0.0625f, 0.125f, 0.1875f, 0.25f, 0.3125f, 0.375f, 0.4375f, 0.5f, 0.625f, 0.75f, 0.875f, 1.0f, 1.25f, 1.5f, 1.75f, \
+                  2.0f, 2.5f, 3.0f, 3.5f, 4.0f, 5.0f, 6.0f, 7.0f, 8.0f, 10.0f, 12.0f, 14.0f, 16.0f, 20.0f, 24.0f, 28.0f
+#define E3M2_NEG_ -28.0f, -24.0f, -20.0f, -16.0f, -14.0f, -12.0f, -10.0f, -8.0f, -7.0f, -6.0f, -5.0f, -4.0f, -3.5f, -3.0f, -2.5f, -2.0f, \
+                  -1.75f, -1.5f, -1.25f, -1.0f, -0.875f, -0.75f, -0.625f, -0.5f, -0.4375f, -0.375f, -0.3125f, -0.25f, -0.1875f, -0.125f, -0.0625f
+#define INT_NEG_ -32.f, -31.f, -30.f, -29.f, -28.f, -27.f, -26.f, -25.f, -24.f, -23.f, -22.f, -21.f, -20.f, -19.f, -18.f, -17.f, \
+                 -16.f, -15.f, -14.f, -13.f, -12.f, -11.f, -10.f, -9.f, -8.f, -7.f, -6.f, -5.f, -4.f, -3.f, -2.f, -1.f
+
+static __constant__ GridTable c_grids[GT_COUNT] = {
+    {15, {E2M1_NEG_, 0.0f, E2M1_POS_}},
+    {15, {E1M2_NEG_, 0.0f, E1M2_POS_}},
+    {15, {E3M0_NEG_, 0.0f, E3M0_POS_}},
+    {64, {E2M3_NEG_, 0.0f, 0.0f, E2M3_POS_}},
+    {64, {E3M2_NEG_, 0.0f, 0.0f, E3M2_POS_}},
+    {33, {INT_NEG_, 0.0f}},
+    {32, {0.0f, E2M3_POS_}},
+    {8, {E1M2_NEG_, 0.0f}},
+    {8, {0.0f, E2M1_POS_}},
+    {8, {E2M1_NEG_, 0.0f}},
+};
+
+
+// launch bookkeeping (defined in fpq_grid.cu)
+int finish_launch();
+int sm_count();
+static inline unsigned grid_for(size_t work_items, size_t items_per_block, int blocks_per_sm) {
+    size_t need = (work_items + items_per_block - 1) / items_per_block;
+    size_t cap = size_t(sm_count()) * blocks_per_sm;
+    if (need < 1) need = 1;
+    return unsigned(need < cap ? need : cap);
+}
+
+// ------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fmax_nan(float a, float b) {
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+
+__device__ __forceinline__ uint4 ldg_stream(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void stg_stream(void* p, uint4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void stg_stream(void* p, uint2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+
+__device__ __forceinline__ float h2f(uint16_t b) { return __half2float(__ushort_as_half(b)); }
+__device__ __forceinline__ uint16_t f2h(float f) { return __half_as_ushort(__float2half_rn(f)); }
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
+    __half2 h = __floats2half2_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// 16 elements per lane, as floats, whatever the storage type
+template <typename T> struct Vec16;
+template <> struct Vec16<float> {
+    static constexpr int NV = 4, VEC = 4;
+    static __device__ __forceinline__ void load(const float* base, int lane_in_group, int lpg, float (&v)[16]) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            uint4 u = ldg_stream(base + (j * lpg + lane_in_group) * VEC);
+            v[4 * j + 0] = __uint_as_float(u.x); v[4 * j + 1] = __uint_as_float(u.y);
+            v[4 * j + 2] = __uint_as_float(u.z); v[4 * j + 3] = __uint_as_float(u.w);
+        }
+    }
+    static __device__ __forceinline__ void store(float* base, int lane_in_group, int lpg, const float (&v)[16]) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            uint4 u = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+            stg_stream(base + (j * lpg + lane_in_group) * VEC, u);
+        }
+    }
+};
+template <> struct Vec16<__half> {
+    static constexpr int NV = 2, VEC = 8;
+    static __device__ __forceinline__ void load(const __half* base, int lane_in_group, int lpg, float (&v)[16]) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            uint4 u = ldg_stream(base + (j * lpg + lane_in_group) * VEC);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+                v[8 * j + 2 * k] = f.x; v[8 * j + 2 * k + 1] = f.y;
+            }
+        }
+    }
+    // element order of a lane's 16 values depends on the INPUT type's vector width; the
+    // store helpers below take the input VEC so that in/out types may differ.
+};
+
+// store 16 per-lane values (laid out for an input type with IN_VEC elements per 16-byte vector)
+template <typename OutT, int IN_VEC>
+__device__ __forceinline__ void store16(OutT* base, int lane_in_group, int lpg, const float (&v)[16]) {
+    constexpr int NV = 16 / IN_VEC;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        OutT* p = base + (j * lpg + lane_in_group) * IN_VEC;
+        if constexpr (sizeof(OutT) == 4) {
+#pragma unroll
+            for (int k = 0; k < IN_VEC; k += 4) {
+                uint4 u = make_uint4(__float_as_uint(v[IN_VEC * j + k]), __float_as_uint(v[IN_VEC * j + k + 1]),
+                                     __float_as_uint(v[IN_VEC * j + k + 2]), __float_as_uint(v[IN_VEC * j + k + 3]));
+                stg_stream(p + k, u);
+            }
+        } else {
+            if constexpr (IN_VEC == 8) {
+                uint4 u = make_uint4(pack_h2(v[8 * j], v[8 * j + 1]), pack_h2(v[8 * j + 2], v[8 * j + 3]),
+                                     pack_h2(v[8 * j + 4], v[8 * j + 5]), pack_h2(v[8 * j + 6], v[8 * j + 7]));
+                stg_stream(p, u);
+            } else {
+                uint2 u = make_uint2(pack_h2(v[4 * j], v[4 * j + 1]), pack_h2(v[4 * j + 2], v[4 * j + 3]));
+                stg_stream(p, u);
+            }
+        }
+    }
+}
+
+template <typename T> __device__ __forceinline__ float to_out(float f);
+template <> __device__ __forceinline__ float to_out<float>(float f) { return f; }
+template <> __device__ __forceinline__ float to_out<__half>(float f) { return f; }   // rounding happens in store16
+
+// reference arithmetic "in the input dtype": round to fp16 when the tensor is fp16
+template <typename InT> __device__ __forceinline__ float rnd_in(float f) {
+    if constexpr (sizeof(InT) == 2) return __half2float(__float2half_rn(f));
+    else return f;
+}
+
+template <int LPG>
+__device__ __forceinline__ float group_max_nan(float a) {
+#pragma unroll
+    for (int o = LPG / 2; o > 0; o >>= 1) a = fmax_nan(a, __shfl_xor_sync(0xffffffffu, a, o));
+    return a;
+}
+template <int LPG>
+__device__ __forceinline__ float group_max(float a) {      // NaN-ignoring (inputs already sanitised)
+#pragma unroll
+    for (int o = LPG / 2; o > 0; o >>= 1) a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+    return a;
+}
+
+template <int FMT> struct SymFmt;
+template <> struct SymFmt<FPQ_FMT_E2M1> { using HG = HG_E2M1; static constexpr int GT = GT_E2M1; };
+template <> struct SymFmt<FPQ_FMT_E1M2> { using HG = HG_E1M2; static constexpr int GT = GT_E1M2; };
+template <> struct SymFmt<FPQ_FMT_E3M0> { using HG = HG_E3M0; static constexpr int GT = GT_E3M0; };
+template <> struct SymFmt<FPQ_FMT_E2M3> { using HG = HG_E2M3; static constexpr int GT = GT_E2M3; };
+template <> struct SymFmt<FPQ_FMT_E3M2> { using HG = HG_E3M2; static constexpr int GT = GT_E3M2; };
+
+// Is the scale "regular", i.e. may the reciprocal-multiply fast path be used?
+//   fp32 tensors: 2^-100 <= s <= 2^100 (1/s and x*(1/s) stay normal)
+//   fp16 tensors: s is a normal, finite fp16 number
+template <typename InT> __device__ __forceinline__ bool scale_regular(float s) {
+    if constexpr (sizeof(InT) == 2) return s >= 6.103515625e-05f && s <= 65504.0f;
+    else return s >= 7.888609052210118e-31f && s <= 1.2676506002282294e30f;
+}
+
+// ------------------------------------------------------------------------------------------
+// One element of the symmetric path, given the group's scale s (already rounded to the input
+// dtype) and r = RN(1/s).
+//
+// fp16 tensors: the reference computes v = half(float(x)/float(s)).  For 11-bit operands
+//   x*RN(1/s) is within 2^-23 (relative) of x/s while x/s is either farther than that from
+//   every fp16 rounding boundary or not near one at all (a quotient of two 11-bit integers
+//   cannot sit closer than 1/(2^11 * 2^12) to a 12-bit midpoint without being equal to it,
+//   and it cannot be equal) -- so half(x*r) == half(x/s) for every input.  DESIGN.md, "fp16
+//   contract", has the derivation; tests/test_gpu_exhaustive.py checks all 2^16 x for a sweep
+//   of scales.
+// fp32 tensors: v = x/s in fp32.  x*r is within 2 ulp of it; the closed-form rounding reports
+//   when its argument is within 32 ulp of a decision boundary and only those elements pay for
+//   an IEEE division.
+// ------------------------------------------------------------------------------------------
+template <typename InT, class HG, int TIE>
+__device__ __forceinline__ float quant_elem_fast(float x, float s, float r) {
+    if constexpr (sizeof(InT) == 2) {
+        const float v = __half2float(__float2half_rn(x * r));
+        return round_closed<HG, TIE, false>(v);
+    } else {
+        bool near;
+        float q = round_closed_near<HG, TIE>(x * r, near);
+        if (near) q = round_closed<HG, TIE, false>(__fdiv_rn(x, s));
+        return q;
+    }
+}
+
+// the literal reference sequence for one element (irregular groups only)
+template <typename InT, int TIE>
+__device__ __forceinline__ float quant_elem_literal(float x, float s, const GridTable& g) {
+    const float v = rnd_in<InT>(__fdiv_rn(x, s));
+    return scan_rule<TIE>(v, g.v, g.k);
+}
+
+__device__ __forceinline__ float clamp3_keep_nan(float x) { return x < -3.0f ? -3.0f : (x > 3.0f ? 3.0f : x); }
+
+// ------------------------------------------------------------------------------------------
+// Fake-quantize one group held in registers (16 values per lane, LPG lanes per group), in place:
+// absmax -> scale -> round -> rescale.  Values are the INPUT-dtype values widened to fp32; the
+// result is q*s in fp32 (the caller's store rounds it to the output dtype).
+// ------------------------------------------------------------------------------------------
+template <typename InT, int FMT, int TIE, int LPG>
+__device__ __forceinline__ void sym_quant_tile(float (&v)[16]) {
+    using HG = typename SymFmt<FMT>::HG;
+    float a = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a = fmax_nan(a, fabsf(v[i]));
+    a = group_max_nan<LPG>(a);
+    const float s = rnd_in<InT>(__fdiv_rn(a, HG::VMAX));      // quant_utils.py:320
+    if (scale_regular<InT>(s)) {
+        const float r = __frcp_rn(s);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = quant_elem_fast<InT, HG, TIE>(v[i], s, r) * s;
+    } else {
+        // zero, subnormal, huge, inf or NaN scale: follow the reference literally
+        const GridTable& gt = c_grids[SymFmt<FMT>::GT];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = quant_elem_literal<InT, TIE>(v[i], s, gt) * s;
+    }
+}
+
+
+template <typename InT> __device__ __forceinline__ float load_elem(const InT* p) {
+    if constexpr (sizeof(InT) == 2) return __half2float(*p); else return *p;
+}
+template <typename OutT> __device__ __forceinline__ void store_elem(OutT* p, float f) {
+    if constexpr (sizeof(OutT) == 2) *p = __float2half_rn(f); else *p = f;
+}
+
+__device__ __forceinline__ float block_max_nan(float a, float* smem) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a = fmax_nan(a, __shfl_xor_sync(0xffffffffu, a, o));
+    const int w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) smem[w] = a;
+    __syncthreads();
+    float r = smem[0];
+    for (int i = 1; i < nw; ++i) r = fmax_nan(r, smem[i]);
+    return r;
+}
+
+
+}  // namespace fpq

@@ -1,0 +1,137 @@
+// libfpq_b200 -- quant_cuda.quant compatibility entry (row a1), the exhaustive rounding self-test, and launch bookkeeping
+// Part of the C ABI of include/fpq_b200.h; no torch types here.
+#include "fpq_common.cuh"
+
+namespace fpq {
+
+// ------------------------------------------------------------------------------------------
+// quant_cuda.quant compatibility entry: z[i] = nearest grid entry (literal scan semantics).
+// The block first checks whether the caller's grid is one of the reference's own tables; if
+// so the closed form is used (proven equal to the scan), else the literal scan over the grid
+// staged in shared memory.
+// ------------------------------------------------------------------------------------------
+template <int TIE>
+__device__ __forceinline__ float round_known(int gt, float v) {
+    // argmin rule, huge |v|: the fp32 distances |v - g_i| round to the SAME value for several
+    // entries once ulp(v) exceeds the grid spacing, and argmin then returns the first of them,
+    // not the nearest.  Only the literal loop reproduces that.  (The kernel rule never gets
+    // there: it answers +0 beyond 102400, where ulp is still 2^-7.)
+    if (TIE == TIE_ARGMIN && !(fabsf(v) < 1048576.0f)) return scan_argmin_rule(v, c_grids[gt].v, c_grids[gt].k);
+    switch (gt) {
+        case GT_E2M1: return round_any_sym<HG_E2M1, TIE>(v);
+        case GT_E1M2: return round_any_sym<HG_E1M2, TIE>(v);
+        case GT_E3M0: return round_any_sym<HG_E3M0, TIE>(v);
+        case GT_E2M3: return round_any_sym<HG_E2M3, TIE>(v);
+        case GT_E3M2: return round_any_sym<HG_E3M2, TIE>(v);
+        case GT_INT_NEG: return round_any_onesided<HG_INT32, TIE, true>(v);
+        case GT_E2M3_POS: return round_any_onesided<HG_E2M3, TIE, false>(v);
+        case GT_E1M2_NEG: return round_any_onesided<HG_E1M2, TIE, true>(v);
+        case GT_E2M1_POS: return round_any_onesided<HG_E2M1, TIE, false>(v);
+        default: return round_any_onesided<HG_E2M1, TIE, true>(v);   // GT_E2M1_NEG
+    }
+}
+
+template <int TIE>
+__global__ void __launch_bounds__(256) quant_grid_kernel(const float* __restrict__ x, const float* __restrict__ grid, int k,
+                                                         size_t n, float* __restrict__ z) {
+    __shared__ float sg[256];
+    __shared__ int s_match;
+    if (threadIdx.x == 0) s_match = -1;
+    for (int i = threadIdx.x; i < k; i += blockDim.x) sg[i] = grid[i];
+    __syncthreads();
+    if (threadIdx.x < GT_COUNT) {
+        const GridTable& t = c_grids[threadIdx.x];
+        bool same = (t.k == k);
+        for (int i = 0; same && i < k; ++i) same = (__float_as_uint(t.v[i]) == __float_as_uint(sg[i]));
+        if (same) s_match = threadIdx.x;     // tables are pairwise distinct: at most one writer
+    }
+    __syncthreads();
+    const int match = s_match;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(z)) & 15) == 0;
+    const size_t tid = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t nthreads = size_t(gridDim.x) * blockDim.x;
+    const size_t n4 = aligned ? n / 4 : 0;
+    for (size_t i = tid; i < n4; i += nthreads) {
+        uint4 u = ldg_stream(x + 4 * i);
+        float f[4] = {__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w)};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f[j] = match >= 0 ? round_known<TIE>(match, f[j]) : scan_rule<TIE>(f[j], sg, k);
+        stg_stream(z + 4 * i, make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])));
+    }
+    for (size_t i = 4 * n4 + tid; i < n; i += nthreads) {
+        const float f = x[i];
+        z[i] = match >= 0 ? round_known<TIE>(match, f) : scan_rule<TIE>(f, sg, k);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// exhaustive self-test: closed form vs literal scan for all 2^32 inputs
+// ------------------------------------------------------------------------------------------
+template <int TIE>
+__global__ void selftest_rounding_kernel(int gt, unsigned long long* result) {
+    const GridTable& t = c_grids[gt];
+    unsigned long long bad = 0, first = ~0ull;
+    for (unsigned long long b = size_t(blockIdx.x) * blockDim.x + threadIdx.x; b < (1ull << 32); b += size_t(gridDim.x) * blockDim.x) {
+        const float v = __uint_as_float(uint32_t(b));
+        const float want = scan_rule<TIE>(v, t.v, t.k);
+        const float got = round_known<TIE>(gt, v);
+        if (__float_as_uint(want) != __float_as_uint(got)) { ++bad; if (b < first) first = b; }
+    }
+    if (bad) { atomicAdd(result, bad); atomicMin(result + 1, first); }
+}
+
+
+static thread_local cudaError_t t_last_err = cudaSuccess;
+static thread_local uint64_t t_launches = 0;
+
+int finish_launch() {
+    cudaError_t e = cudaGetLastError();
+    ++t_launches;
+    if (e != cudaSuccess) { t_last_err = e; return FPQ_ERR_CUDA; }
+    return FPQ_OK;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace fpq
+
+using namespace fpq;
+
+extern "C" const char* fpq_version(void) { return "fpq_b200 0.1 (sm_100a)"; }
+extern "C" const char* fpq_last_cuda_error(void) { return cudaGetErrorString(t_last_err); }
+extern "C" uint64_t fpq_launch_count(void) { return t_launches; }
+
+extern "C" int fpq_quant_grid(const float* x, const float* grid, int k, size_t n, float* z, int tie_mode, void* stream) {
+    if (k < 1 || k > 256 || (n && (!x || !z)) || !grid) return FPQ_ERR_ARG;
+    if (n == 0) return FPQ_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid_dim = grid_for(n, 256 * 4, 64);
+    if (tie_mode == FPQ_TIE_KERNEL) quant_grid_kernel<TIE_KERNEL><<<grid_dim, 256, 0, st>>>(x, grid, k, n, z);
+    else if (tie_mode == FPQ_TIE_ARGMIN) quant_grid_kernel<TIE_ARGMIN><<<grid_dim, 256, 0, st>>>(x, grid, k, n, z);
+    else return FPQ_ERR_ARG;
+    return finish_launch();
+}
+
+extern "C" int fpq_selftest_rounding(int format, int tie_mode, unsigned long long* result, void* stream) {
+    int gt;
+    if (format >= 0 && format < FPQ_NUM_SYM_FORMATS) gt = format;
+    else if (format >= 16 && format < 16 + (GT_COUNT - GT_INT_NEG)) gt = GT_INT_NEG + (format - 16);
+    else return FPQ_ERR_ARG;
+    if (!result) return FPQ_ERR_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaMemsetAsync(result, 0, sizeof(unsigned long long), st);
+    cudaMemsetAsync(result + 1, 0xff, sizeof(unsigned long long), st);
+    const unsigned grid = unsigned(sm_count()) * 8;
+    if (tie_mode == FPQ_TIE_KERNEL) selftest_rounding_kernel<TIE_KERNEL><<<grid, 256, 0, st>>>(gt, result);
+    else if (tie_mode == FPQ_TIE_ARGMIN) selftest_rounding_kernel<TIE_ARGMIN><<<grid, 256, 0, st>>>(gt, result);
+    else return FPQ_ERR_ARG;
+    return finish_launch();
+}

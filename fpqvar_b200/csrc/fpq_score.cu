@@ -1,0 +1,179 @@
+// libfpq_b200 -- batched format scoring (reference row a10 of SURVEY.md section 8).
+// The search scripts quantize the same tensor once per candidate format and reduce
+// mean((x - x_q)^2) each time (search/search_fp4_format.py:340-374,472-476,840-893;
+// search/search_fp6_format.py:547-554).  Here x is read ONCE: each 128-group sits in the
+// registers of 8 lanes, every candidate is applied to the register tile, and the per-candidate
+// squared error is accumulated in fp32 per lane, fp64 per block, one atomicAdd(double) per
+// block and candidate.
+#include "fpq_common.cuh"
+
+namespace fpq {
+
+constexpr int MAX_CAND = 8;
+struct Candidates { int n; int fmt[MAX_CAND]; };
+
+template <int SPLIT> struct SplitFmtS;
+template <> struct SplitFmtS<FPQ_SPLIT_E1M2NEG_E2M1POS> { using NEG = HG_E1M2; using POS = HG_E2M1; static constexpr int GT_N = GT_E1M2_NEG, GT_P = GT_E2M1_POS; };
+template <> struct SplitFmtS<FPQ_SPLIT_INTNEG_E2M3POS> { using NEG = HG_INT32; using POS = HG_E2M3; static constexpr int GT_N = GT_INT_NEG, GT_P = GT_E2M3_POS; };
+template <> struct SplitFmtS<FPQ_SPLIT_AFPQ_E2M1> { using NEG = HG_E2M1; using POS = HG_E2M1; static constexpr int GT_N = GT_E2M1_NEG, GT_P = GT_E2M1_POS; };
+
+// squared error of one symmetric candidate over the lane's 16 values
+template <typename InT, int FMT, int TIE>
+__device__ __forceinline__ float sse_sym(const float (&v)[16], float a) {
+    using HG = typename SymFmt<FMT>::HG;
+    const float s = rnd_in<InT>(__fdiv_rn(a, HG::VMAX));
+    float acc = 0.0f;
+    if (scale_regular<InT>(s)) {
+        const float r = __frcp_rn(s);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            // output dtype of the reference quantizers: the input dtype for the *_cuda functions
+            // (kernel rule), fp32 for the argmin ones
+            float o = quant_elem_fast<InT, HG, TIE>(v[i], s, r) * s;
+            if (TIE == TIE_KERNEL) o = rnd_in<InT>(o);
+            const float d = v[i] - o;
+            acc = fmaf(d, d, acc);
+        }
+    } else {
+        const GridTable& gt = c_grids[SymFmt<FMT>::GT];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            float o = quant_elem_literal<InT, TIE>(v[i], s, gt) * s;
+            if (TIE == TIE_KERNEL) o = rnd_in<InT>(o);
+            const float d = v[i] - o;
+            acc = fmaf(d, d, acc);
+        }
+    }
+    return acc;
+}
+
+template <typename InT, int SPLIT, int TIE>
+__device__ __forceinline__ float sse_split(const float (&v)[16], float an, float ap) {
+    using SF = SplitFmtS<SPLIT>;
+    const float sn = rnd_in<InT>(__fdiv_rn(an, SF::NEG::VMAX));
+    const float sp = rnd_in<InT>(__fdiv_rn(ap, SF::POS::VMAX));
+    const bool n_ok = scale_regular<InT>(sn) || (TIE == TIE_KERNEL && sn == 0.0f);
+    const bool p_ok = scale_regular<InT>(sp) || sp == 0.0f;
+    float acc = 0.0f;
+    if (n_ok && p_ok) {
+        const float rn = sn == 0.0f ? 0.0f : __frcp_rn(sn);
+        const float rp = sp == 0.0f ? 0.0f : __frcp_rn(sp);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float x = v[i];
+            float o;
+            if (x > 0.0f) o = quant_elem_fast<InT, typename SF::POS, TIE>(x, sp, rp) * sp;
+            else o = quant_elem_fast<InT, typename SF::NEG, TIE>((x <= 0.0f) ? x : 0.0f, sn, rn) * sn;
+            if (TIE == TIE_KERNEL) o = rnd_in<InT>(o);
+            const float d = x - o;
+            acc = fmaf(d, d, acc);
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float x = v[i];
+            const float xn = (x <= 0.0f) ? x : 0.0f, xp = (x > 0.0f) ? x : 0.0f;
+            const float qn = scan_rule<TIE>(rnd_in<InT>(__fdiv_rn(xn, sn)), c_grids[SF::GT_N].v, c_grids[SF::GT_N].k);
+            const float qp = scan_rule<TIE>(rnd_in<InT>(__fdiv_rn(xp, sp)), c_grids[SF::GT_P].v, c_grids[SF::GT_P].k);
+            float o = TIE == TIE_KERNEL ? rnd_in<InT>(__fadd_rn(__fmul_rn(qn, sn), __fmul_rn(qp, sp)))
+                                        : __fmul_rn(__fadd_rn(qn, qp), (x <= 0.0f) ? sn : sp);
+            const float d = x - o;
+            acc = fmaf(d, d, acc);
+        }
+    }
+    return acc;
+}
+
+template <typename InT, int TIE>
+__global__ void __launch_bounds__(256) score_formats_kernel(const InT* __restrict__ x, size_t n_groups, Candidates cand,
+                                                            double* __restrict__ sse) {
+    constexpr int LPG = 8, GS = 128;
+    __shared__ double s_acc[MAX_CAND];
+    if (threadIdx.x < MAX_CAND) s_acc[threadIdx.x] = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int lig = lane % LPG;
+    const size_t warp_global = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
+    double acc[MAX_CAND];
+#pragma unroll
+    for (int c = 0; c < MAX_CAND; ++c) acc[c] = 0.0;
+
+    for (size_t gbase = warp_global * 4; gbase < n_groups; gbase += n_warps * 4) {
+        const size_t g = gbase + lane / LPG;
+        float v[16];
+        if (g < n_groups) {
+            Vec16<InT>::load(x + g * GS, lig, LPG, v);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+        }
+        float a = 0.0f, an = 0.0f, ap = 0.0f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            a = fmax_nan(a, fabsf(v[i]));
+            an = fmaxf(an, (v[i] <= 0.0f) ? -v[i] : 0.0f);
+            ap = fmaxf(ap, (v[i] > 0.0f) ? v[i] : 0.0f);
+        }
+        a = group_max_nan<LPG>(a);
+        an = group_max<LPG>(an);
+        ap = group_max<LPG>(ap);
+#pragma unroll
+        for (int c = 0; c < MAX_CAND; ++c) {
+            if (c < cand.n) {
+                float e;
+                switch (cand.fmt[c]) {
+                    case FPQ_FMT_E2M1: e = sse_sym<InT, FPQ_FMT_E2M1, TIE>(v, a); break;
+                    case FPQ_FMT_E1M2: e = sse_sym<InT, FPQ_FMT_E1M2, TIE>(v, a); break;
+                    case FPQ_FMT_E3M0: e = sse_sym<InT, FPQ_FMT_E3M0, TIE>(v, a); break;
+                    case FPQ_FMT_E2M3: e = sse_sym<InT, FPQ_FMT_E2M3, TIE>(v, a); break;
+                    case FPQ_FMT_E3M2: e = sse_sym<InT, FPQ_FMT_E3M2, TIE>(v, a); break;
+                    case 16 + FPQ_SPLIT_E1M2NEG_E2M1POS: e = sse_split<InT, FPQ_SPLIT_E1M2NEG_E2M1POS, TIE>(v, an, ap); break;
+                    case 16 + FPQ_SPLIT_INTNEG_E2M3POS: e = sse_split<InT, FPQ_SPLIT_INTNEG_E2M3POS, TIE>(v, an, ap); break;
+                    default: e = sse_split<InT, FPQ_SPLIT_AFPQ_E2M1, TIE>(v, an, ap); break;
+                }
+                acc[c] += double(e);
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < MAX_CAND; ++c) {
+        if (c < cand.n) {
+            double e = acc[c];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
+            if (lane == 0) atomicAdd(&s_acc[c], e);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < cand.n) atomicAdd(&sse[threadIdx.x], s_acc[threadIdx.x]);
+}
+
+}  // namespace fpq
+
+using namespace fpq;
+
+extern "C" int fpq_score_formats(const void* x, size_t n_rows, size_t row_len, int in_dtype, const int* formats_host, int n_formats,
+                                 int tie_mode, double* sse, void* stream) {
+    if (!formats_host || n_formats < 1 || n_formats > MAX_CAND || !sse || (n_rows && !x)) return FPQ_ERR_ARG;
+    if (row_len != 128) return FPQ_ERR_UNSUPPORTED;       // the search scripts use group_size 128 throughout
+    if (reinterpret_cast<uintptr_t>(x) & 15) return FPQ_ERR_ARG;
+    Candidates cand;
+    cand.n = n_formats;
+    for (int i = 0; i < MAX_CAND; ++i) cand.fmt[i] = 0;
+    for (int i = 0; i < n_formats; ++i) {
+        const int f = formats_host[i];
+        const bool ok = (f >= 0 && f < FPQ_NUM_SYM_FORMATS) || (f >= 16 && f < 16 + FPQ_NUM_SPLIT_FORMATS);
+        if (!ok) return FPQ_ERR_ARG;
+        cand.fmt[i] = f;
+    }
+    if (n_rows == 0) return FPQ_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = grid_for(n_rows, 32, 8);
+    if (in_dtype == FPQ_F32 && tie_mode == FPQ_TIE_KERNEL) score_formats_kernel<float, TIE_KERNEL><<<grid, 256, 0, st>>>(static_cast<const float*>(x), n_rows, cand, sse);
+    else if (in_dtype == FPQ_F32 && tie_mode == FPQ_TIE_ARGMIN) score_formats_kernel<float, TIE_ARGMIN><<<grid, 256, 0, st>>>(static_cast<const float*>(x), n_rows, cand, sse);
+    else if (in_dtype == FPQ_F16 && tie_mode == FPQ_TIE_KERNEL) score_formats_kernel<__half, TIE_KERNEL><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), n_rows, cand, sse);
+    else if (in_dtype == FPQ_F16 && tie_mode == FPQ_TIE_ARGMIN) score_formats_kernel<__half, TIE_ARGMIN><<<grid, 256, 0, st>>>(static_cast<const __half*>(x), n_rows, cand, sse);
+    else return FPQ_ERR_ARG;
+    return finish_launch();
+}

@@ -1,0 +1,204 @@
+// libfpq_b200 -- sign-split fake-quant kernels (reference row a3 of SURVEY.md section 8)
+// Part of the C ABI of include/fpq_b200.h; no torch types here.
+#include "fpq_common.cuh"
+
+namespace fpq {
+
+// ------------------------------------------------------------------------------------------
+// Sign-split formats
+// ------------------------------------------------------------------------------------------
+template <int SPLIT> struct SplitFmt;
+template <> struct SplitFmt<FPQ_SPLIT_E1M2NEG_E2M1POS> { using NEG = HG_E1M2; using POS = HG_E2M1; static constexpr int GT_N = GT_E1M2_NEG, GT_P = GT_E2M1_POS; };
+template <> struct SplitFmt<FPQ_SPLIT_INTNEG_E2M3POS> { using NEG = HG_INT32; using POS = HG_E2M3; static constexpr int GT_N = GT_INT_NEG, GT_P = GT_E2M3_POS; };
+template <> struct SplitFmt<FPQ_SPLIT_AFPQ_E2M1> { using NEG = HG_E2M1; using POS = HG_E2M1; static constexpr int GT_N = GT_E2M1_NEG, GT_P = GT_E2M1_POS; };
+
+// One element, literal reference sequence (quant_utils.py:428-451 / :404-410).
+template <typename InT, typename OutT, int SPLIT, int TIE>
+__device__ __forceinline__ float signsplit_elem_literal(float x, float sn, float sp) {
+    using SF = SplitFmt<SPLIT>;
+    const float xn = (x <= 0.0f) ? x : 0.0f;
+    const float xp = (x > 0.0f) ? x : 0.0f;
+    const float vn = rnd_in<InT>(__fdiv_rn(xn, sn));
+    const float vp = rnd_in<InT>(__fdiv_rn(xp, sp));
+    const float qn = scan_rule<TIE>(vn, c_grids[SF::GT_N].v, c_grids[SF::GT_N].k);
+    const float qp = scan_rule<TIE>(vp, c_grids[SF::GT_P].v, c_grids[SF::GT_P].k);
+    if (TIE == TIE_KERNEL) return __fadd_rn(__fmul_rn(qn, sn), __fmul_rn(qp, sp));
+    return __fmul_rn(__fadd_rn(qn, qp), (x <= 0.0f) ? sn : sp);
+}
+
+// Fast element: only the side the element lives on does any work; the other side
+// contributes R(0/s)*s = +0 (s regular or zero) which leaves the sum unchanged.
+template <typename InT, int SPLIT, int TIE>
+__device__ __forceinline__ float signsplit_elem_fast(float x, float sn, float rn, float sp, float rp) {
+    using SF = SplitFmt<SPLIT>;
+    if (x > 0.0f) return quant_elem_fast<InT, typename SF::POS, TIE>(x, sp, rp) * sp;
+    // x <= 0, or NaN (NaN fails both where() tests and is replaced by 0 on both sides; under the
+    // argmin rule its scale is where(x<=0, sn, sp) = sp, but the product is +0 either way)
+    const float xn = (x <= 0.0f) ? x : 0.0f;
+    return quant_elem_fast<InT, typename SF::NEG, TIE>(xn, sn, rn) * sn;
+}
+
+// May a group take the fast path?  A zero scale means "no element on that side": the
+// reference then computes 0/0 = NaN for every element of that half.  Under the kernel rule
+// NaN rounds to +0 and the half contributes nothing (fast path with r = 0).  Under the argmin
+// rule NaN rounds to grid[0]: harmless for the positive grid (grid[0] = 0) but the negative
+// grid's grid[0] = -VMAX shifts every positive element, so sn == 0 goes the literal way.
+template <typename InT, int TIE> __device__ __forceinline__ bool split_fast_ok(float sn, float sp) {
+    const bool n_ok = scale_regular<InT>(sn) || (TIE == TIE_KERNEL && sn == 0.0f);
+    const bool p_ok = scale_regular<InT>(sp) || sp == 0.0f;
+    return n_ok && p_ok;
+}
+
+template <typename InT, typename OutT, int SPLIT, int TIE, int LPG>
+__global__ void __launch_bounds__(256) signsplit_group_kernel(const InT* __restrict__ x, OutT* __restrict__ out,
+                                                              size_t n_groups, unsigned* __restrict__ nan_flag) {
+    using SF = SplitFmt<SPLIT>;
+    constexpr int GS = 16 * LPG;
+    constexpr int IN_VEC = 16 / sizeof(InT);
+    constexpr int GROUPS_PER_WARP = 32 / LPG;
+    const int lane = threadIdx.x & 31;
+    const int lig = lane % LPG;
+    const size_t warp_global = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
+
+    for (size_t gbase = warp_global * GROUPS_PER_WARP; gbase < n_groups; gbase += n_warps * GROUPS_PER_WARP) {
+        const size_t g = gbase + lane / LPG;
+        const bool valid = g < n_groups;
+        float v[16];
+        if (valid) {
+            Vec16<InT>::load(x + g * GS, lig, LPG, v);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+        }
+        // max|x_neg| and max|x_pos|; NaN elements count as 0 on both sides (where() semantics)
+        float an = 0.0f, ap = 0.0f;
+        bool has_nan = false;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            an = fmaxf(an, (v[i] <= 0.0f) ? -v[i] : 0.0f);
+            ap = fmaxf(ap, (v[i] > 0.0f) ? v[i] : 0.0f);
+            has_nan |= (v[i] != v[i]);
+        }
+        an = group_max<LPG>(an);
+        ap = group_max<LPG>(ap);
+        if (nan_flag != nullptr && has_nan) atomicOr(nan_flag, 1u);
+        const float sn = rnd_in<InT>(__fdiv_rn(an, SF::NEG::VMAX));
+        const float sp = rnd_in<InT>(__fdiv_rn(ap, SF::POS::VMAX));
+        if (split_fast_ok<InT, TIE>(sn, sp)) {
+            const float rn = sn == 0.0f ? 0.0f : __frcp_rn(sn);
+            const float rp = sp == 0.0f ? 0.0f : __frcp_rn(sp);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = signsplit_elem_fast<InT, SPLIT, TIE>(v[i], sn, rn, sp, rp);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = signsplit_elem_literal<InT, OutT, SPLIT, TIE>(v[i], sn, sp);
+        }
+        if (valid) store16<OutT, IN_VEC>(out + g * GS, lig, LPG, v);
+    }
+}
+
+template <typename InT, typename OutT, int SPLIT, int TIE>
+__global__ void __launch_bounds__(256) signsplit_row_kernel(const InT* __restrict__ x, OutT* __restrict__ out,
+                                                            size_t n_rows, size_t row_len, unsigned* __restrict__ nan_flag) {
+    using SF = SplitFmt<SPLIT>;
+    __shared__ float red[32];
+    for (size_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        const InT* xr = x + row * row_len;
+        OutT* orow = out + row * row_len;
+        float an = 0.0f, ap = 0.0f;
+        bool has_nan = false;
+        for (size_t i = threadIdx.x; i < row_len; i += blockDim.x) {
+            const float f = load_elem(xr + i);
+            an = fmaxf(an, (f <= 0.0f) ? -f : 0.0f);
+            ap = fmaxf(ap, (f > 0.0f) ? f : 0.0f);
+            has_nan |= (f != f);
+        }
+        an = block_max_nan(an, red);
+        ap = block_max_nan(ap, red);
+        if (nan_flag != nullptr && has_nan) atomicOr(nan_flag, 1u);
+        const float sn = rnd_in<InT>(__fdiv_rn(an, SF::NEG::VMAX));
+        const float sp = rnd_in<InT>(__fdiv_rn(ap, SF::POS::VMAX));
+        const bool fast = split_fast_ok<InT, TIE>(sn, sp);
+        const float rn = (fast && sn != 0.0f) ? __frcp_rn(sn) : 0.0f;
+        const float rp = (fast && sp != 0.0f) ? __frcp_rn(sp) : 0.0f;
+        for (size_t i = threadIdx.x; i < row_len; i += blockDim.x) {
+            const float f = load_elem(xr + i);
+            const float o = fast ? signsplit_elem_fast<InT, SPLIT, TIE>(f, sn, rn, sp, rp)
+                                 : signsplit_elem_literal<InT, OutT, SPLIT, TIE>(f, sn, sp);
+            store_elem(orow + i, o);
+        }
+    }
+}
+
+// qu.py:421-422 with a NaN in the tensor: clamp(x, -NaN, NaN) makes every element NaN, both
+// where() halves become 0, every scale 0, every quotient 0/0 -> q = 0 (kernel rule) or
+// grid[0] (argmin rule), and the output is (+0)*0 + (+0)*0 = +0, resp. (g0n + g0p) * 0 = -0.
+template <typename OutT>
+__global__ void poison_fill_kernel(OutT* __restrict__ out, size_t n, const unsigned* __restrict__ nan_flag, float fill) {
+    if (*nan_flag == 0u) return;
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) store_elem(out + i, fill);
+}
+
+template <typename InT, typename OutT, int SPLIT, int TIE>
+static int launch_split(const void* x, void* out, size_t n_rows, size_t row_len, unsigned* flag, cudaStream_t st) {
+    const InT* xi = static_cast<const InT*>(x);
+    OutT* oo = static_cast<OutT*>(out);
+    const bool pow2_group = (row_len == 128 || row_len == 64) &&
+                            ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if (pow2_group) {
+        const int lpg = int(row_len / 16);
+        const size_t groups_per_block = (256 / 32) * (32 / lpg);
+        const unsigned grid = grid_for(n_rows, groups_per_block, 64);
+        if (lpg == 8) signsplit_group_kernel<InT, OutT, SPLIT, TIE, 8><<<grid, 256, 0, st>>>(xi, oo, n_rows, flag);
+        else signsplit_group_kernel<InT, OutT, SPLIT, TIE, 4><<<grid, 256, 0, st>>>(xi, oo, n_rows, flag);
+    } else {
+        const unsigned grid = grid_for(n_rows, 1, 16);
+        signsplit_row_kernel<InT, OutT, SPLIT, TIE><<<grid, 256, 0, st>>>(xi, oo, n_rows, row_len, flag);
+    }
+    int rc = finish_launch();
+    if (rc != FPQ_OK || flag == nullptr) return rc;
+    // all-NaN tensor after the reference's clamp: kernel rule -> +0 everywhere; argmin rule ->
+    // (grid_neg[0] + grid_pos[0]) * 0 = -0 everywhere
+    const float fill = TIE == TIE_KERNEL ? 0.0f : -0.0f;
+    const size_t n = n_rows * row_len;
+    poison_fill_kernel<OutT><<<grid_for(n, 256 * 8, 8), 256, 0, st>>>(oo, n, flag, fill);
+    return finish_launch();
+}
+
+template <typename InT, typename OutT, int TIE>
+static int dispatch_split_fmt(int split, const void* x, void* out, size_t n_rows, size_t row_len, unsigned* flag, cudaStream_t st) {
+    switch (split) {
+        case FPQ_SPLIT_E1M2NEG_E2M1POS: return launch_split<InT, OutT, FPQ_SPLIT_E1M2NEG_E2M1POS, TIE>(x, out, n_rows, row_len, flag, st);
+        case FPQ_SPLIT_INTNEG_E2M3POS: return launch_split<InT, OutT, FPQ_SPLIT_INTNEG_E2M3POS, TIE>(x, out, n_rows, row_len, flag, st);
+        case FPQ_SPLIT_AFPQ_E2M1: return launch_split<InT, OutT, FPQ_SPLIT_AFPQ_E2M1, TIE>(x, out, n_rows, row_len, flag, st);
+        default: return FPQ_ERR_ARG;
+    }
+}
+
+template <int TIE>
+static int dispatch_split_types(int in_dtype, int out_dtype, int split, const void* x, void* out, size_t n_rows, size_t row_len,
+                                unsigned* flag, cudaStream_t st) {
+    if (in_dtype == FPQ_F32 && out_dtype == FPQ_F32) return dispatch_split_fmt<float, float, TIE>(split, x, out, n_rows, row_len, flag, st);
+    if (in_dtype == FPQ_F16 && out_dtype == FPQ_F16) return dispatch_split_fmt<__half, __half, TIE>(split, x, out, n_rows, row_len, flag, st);
+    if (in_dtype == FPQ_F16 && out_dtype == FPQ_F32) return dispatch_split_fmt<__half, float, TIE>(split, x, out, n_rows, row_len, flag, st);
+    if (in_dtype == FPQ_F32 && out_dtype == FPQ_F16) return dispatch_split_fmt<float, __half, TIE>(split, x, out, n_rows, row_len, flag, st);
+    return FPQ_ERR_ARG;
+}
+
+}  // namespace fpq
+
+using namespace fpq;
+
+extern "C" int fpq_fake_quant_signsplit(const void* x, void* out, size_t n_rows, size_t row_len, int in_dtype, int out_dtype,
+                                        int split_format, int tie_mode, unsigned flags, void* workspace, void* stream) {
+    if (row_len == 0 || (n_rows && (!x || !out)) || x == out) return FPQ_ERR_ARG;
+    if (flags & ~FPQ_FLAG_GLOBAL_CLIP) return FPQ_ERR_ARG;
+    if ((flags & FPQ_FLAG_GLOBAL_CLIP) && !workspace) return FPQ_ERR_ARG;
+    if (n_rows == 0) return FPQ_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    unsigned* flag = (flags & FPQ_FLAG_GLOBAL_CLIP) ? static_cast<unsigned*>(workspace) : nullptr;
+    if (tie_mode == FPQ_TIE_KERNEL) return dispatch_split_types<TIE_KERNEL>(in_dtype, out_dtype, split_format, x, out, n_rows, row_len, flag, st);
+    if (tie_mode == FPQ_TIE_ARGMIN) return dispatch_split_types<TIE_ARGMIN>(in_dtype, out_dtype, split_format, x, out, n_rows, row_len, flag, st);
+    return FPQ_ERR_ARG;
+}

@@ -1,0 +1,185 @@
+"""Tensor-level operators over the C ABI (include/fpq_b200.h).
+
+Host-side plumbing only: argument checks, output allocation, the current CUDA stream.  All
+arithmetic happens in the sm_100a kernels of fpqvar_b200/csrc.  CPU tensors are rejected --
+there is no fallback path.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib as L
+
+_DT = {torch.float32: L.FPQ_F32, torch.float16: L.FPQ_F16}
+
+
+def _require_cuda(x: torch.Tensor, what: str) -> None:
+    if not isinstance(x, torch.Tensor) or not x.is_cuda:
+        raise L.FpqError(f"{what}: expected a CUDA tensor (fpqvar_b200 has no CPU fallback); got "
+                         f"{getattr(x, 'device', type(x))}")
+
+
+def _dt(x: torch.Tensor, what: str) -> int:
+    try:
+        return _DT[x.dtype]
+    except KeyError:
+        raise L.FpqError(f"{what}: dtype {x.dtype} is not supported (float16 / float32 only)") from None
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _rows(x: torch.Tensor, row_len: Optional[int]) -> tuple[int, int]:
+    if row_len is None:
+        row_len = x.shape[-1] if x.dim() > 0 else 1
+    n = x.numel()
+    if row_len <= 0 or n % row_len != 0:
+        raise L.FpqError(f"numel {n} is not a multiple of the group/row length {row_len}")
+    return n // row_len, row_len
+
+
+def fake_quant(x: torch.Tensor, fmt: str, row_len: Optional[int] = 128, tie: str = "kernel", clamp3: bool = False,
+               out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Symmetric fake-quant (fpq_fake_quant). ``row_len=None``: the last dim shares one scale
+    (per_token / per_channel).  Output dtype: the input's for tie="kernel" (the ``*_cuda``
+    reference functions), float32 for tie="argmin" (quant_utils.py:308 promotes)."""
+    _require_cuda(x, "fake_quant")
+    x = x.contiguous()
+    if out_dtype is None:
+        out_dtype = x.dtype if tie == "kernel" else torch.float32
+    out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    n_rows, rl = _rows(x, row_len)
+    with torch.cuda.device_of(x):
+        rc = L.lib().fpq_fake_quant(x.data_ptr(), out.data_ptr(), n_rows, rl, _dt(x, "fake_quant"), _dt(out, "fake_quant"),
+                                    L.FMT[fmt], L.TIE[tie], L.FLAG_CLAMP3 if clamp3 else 0, _stream())
+    L.check(rc, "fpq_fake_quant")
+    return out
+
+
+def fake_quant_signsplit(x: torch.Tensor, split_fmt: str, row_len: Optional[int] = 128, tie: str = "kernel",
+                         global_clip: bool = False, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Sign-split fake-quant (fpq_fake_quant_signsplit).  ``global_clip=True`` reproduces the
+    reference's whole-tensor ``clamp(x, -|x|max, |x|max)`` (quant_utils.py:421-422), which only
+    matters when the tensor holds a NaN (then the whole output is zero)."""
+    _require_cuda(x, "fake_quant_signsplit")
+    x = x.contiguous()
+    if out_dtype is None:
+        out_dtype = x.dtype if tie == "kernel" else torch.float32
+    out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+    n_rows, rl = _rows(x, row_len)
+    ws = torch.zeros(1, dtype=torch.int32, device=x.device) if global_clip else None
+    with torch.cuda.device_of(x):
+        rc = L.lib().fpq_fake_quant_signsplit(x.data_ptr(), out.data_ptr(), n_rows, rl, _dt(x, "signsplit"), _dt(out, "signsplit"),
+                                              L.SPLIT[split_fmt], L.TIE[tie], L.FLAG_GLOBAL_CLIP if global_clip else 0,
+                                              ws.data_ptr() if ws is not None else None, _stream())
+    L.check(rc, "fpq_fake_quant_signsplit")
+    return out
+
+
+def quant_grid(x: torch.Tensor, grid: torch.Tensor, tie: str = "kernel") -> torch.Tensor:
+    """Nearest grid value, reference scan semantics (fpq_quant_grid). fp32 in, fp32 out."""
+    _require_cuda(x, "quant_grid")
+    _require_cuda(grid, "quant_grid(grid)")
+    if x.dtype != torch.float32 or grid.dtype != torch.float32:
+        raise L.FpqError("quant_grid: x and grid must be float32")
+    x = x.contiguous()
+    grid = grid.contiguous()
+    z = torch.empty_like(x)
+    with torch.cuda.device_of(x):
+        rc = L.lib().fpq_quant_grid(x.data_ptr(), grid.data_ptr(), grid.numel(), x.numel(), z.data_ptr(), L.TIE[tie], _stream())
+    L.check(rc, "fpq_quant_grid")
+    return z
+
+
+def pack_sign_bits(signs) -> "ctypes.Array":
+    """+-1 vector of length 128 -> the 4 x uint32 mask the kernels take (bit set = +1)."""
+    vals = [float(v) for v in (signs.tolist() if hasattr(signs, "tolist") else signs)]
+    if len(vals) != 128 or any(v not in (1.0, -1.0) for v in vals):
+        raise L.FpqError("sign vector must hold 128 entries of +-1")
+    words = [0, 0, 0, 0]
+    for i, v in enumerate(vals):
+        if v > 0:
+            words[i >> 5] |= 1 << (i & 31)
+    return (ctypes.c_uint32 * 4)(*words)
+
+
+def transform_rotate_quant(x: torch.Tensor, smooth: Optional[torch.Tensor], sign_bits, fmt: Optional[str],
+                           return_rotated: bool = False):
+    """Fused ``(x * smooth) @ Q_block128`` -> fp16 -> per-group fake quant (fpq_transform_rotate_quant).
+    x: fp32 [..., C]; returns fp16 of the same shape (and the pre-quantization rotated fp16
+    tensor when ``return_rotated``).  ``fmt=None`` skips the quantizer."""
+    _require_cuda(x, "transform_rotate_quant")
+    if x.dtype != torch.float32:
+        raise L.FpqError("transform_rotate_quant: x must be float32 (the adaLN-modulated LayerNorm output)")
+    x = x.contiguous()
+    c = x.shape[-1]
+    if smooth is not None:
+        _require_cuda(smooth, "transform_rotate_quant(smooth)")
+        smooth = smooth.detach().to(torch.float32).contiguous()
+        if smooth.numel() != c:
+            raise L.FpqError(f"smooth has {smooth.numel()} entries, expected {c}")
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    rot = torch.empty_like(out) if return_rotated else None
+    n_rows = x.numel() // c if c else 0
+    with torch.cuda.device_of(x):
+        rc = L.lib().fpq_transform_rotate_quant(x.data_ptr(), smooth.data_ptr() if smooth is not None else None, sign_bits,
+                                                out.data_ptr(), rot.data_ptr() if rot is not None else None, n_rows, c,
+                                                -1 if fmt is None else L.FMT[fmt], _stream())
+    L.check(rc, "fpq_transform_rotate_quant")
+    return (out, rot) if return_rotated else out
+
+
+def transform_rotate_weight(w: torch.Tensor, smooth: Optional[torch.Tensor], sign_bits, inplace: bool = False) -> torch.Tensor:
+    """``(W / smooth).double() @ Q_block128`` -> fp32 (fpq_transform_rotate_weight)."""
+    _require_cuda(w, "transform_rotate_weight")
+    if w.dtype != torch.float32 or w.dim() != 2:
+        raise L.FpqError("transform_rotate_weight: w must be a 2-D float32 tensor")
+    if not w.is_contiguous():
+        if inplace:
+            raise L.FpqError("transform_rotate_weight: in-place needs a contiguous tensor")
+        w = w.contiguous()
+    if smooth is not None:
+        smooth = smooth.detach().to(torch.float32).contiguous()
+    out = w if inplace else torch.empty_like(w)
+    with torch.cuda.device_of(w):
+        rc = L.lib().fpq_transform_rotate_weight(w.data_ptr(), smooth.data_ptr() if smooth is not None else None, sign_bits,
+                                                 out.data_ptr(), w.shape[0], w.shape[1], _stream())
+    L.check(rc, "fpq_transform_rotate_weight")
+    return out
+
+
+def _fmt_code(name: str) -> int:
+    return L.FMT[name] if name in L.FMT else 16 + L.SPLIT[name]
+
+
+def score_formats(x: torch.Tensor, formats: Sequence[str], tie: str = "kernel", sse: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Sum of squared quantization errors per candidate format, x read once (fpq_score_formats).
+    Returns / accumulates into a float64 tensor of len(formats)."""
+    _require_cuda(x, "score_formats")
+    x = x.contiguous()
+    if sse is None:
+        sse = torch.zeros(len(formats), dtype=torch.float64, device=x.device)
+    codes = (ctypes.c_int * len(formats))(*[_fmt_code(f) for f in formats])
+    n_rows, rl = _rows(x, 128)
+    with torch.cuda.device_of(x):
+        rc = L.lib().fpq_score_formats(x.data_ptr(), n_rows, rl, _dt(x, "score_formats"), codes, len(formats), L.TIE[tie],
+                                       sse.data_ptr(), _stream())
+    L.check(rc, "fpq_score_formats")
+    return sse
+
+
+def selftest_rounding(fmt_code: int, tie: str) -> tuple[int, int]:
+    """(mismatch count, first mismatching fp32 bit pattern) of closed form vs scan over all 2^32 inputs."""
+    res = torch.zeros(2, dtype=torch.int64, device="cuda")
+    rc = L.lib().fpq_selftest_rounding(fmt_code, L.TIE[tie], res.data_ptr(), _stream())
+    L.check(rc, "fpq_selftest_rounding")
+    r = res.cpu()
+    return int(r[0]), int(r[1]) & 0xFFFFFFFF
+
+
+def launch_count() -> int:
+    return int(L.lib().fpq_launch_count())

@@ -1,0 +1,173 @@
+/*
+ * fpq_b200.h -- C ABI of libfpq_b200.so: the B200 (sm_100a) implementation of FPQVAR's
+ * floating-point fake-quantization hot path.
+ *
+ * Conventions (every entry point):
+ *   - plain C types only; pointers are DEVICE pointers unless a name ends in `_host`;
+ *   - nothing allocates, nothing synchronises; work is enqueued on `stream`
+ *     (a cudaStream_t passed as void*; NULL = the legacy default stream);
+ *   - the return value is 0 on success or a negative FPQ_ERR_* code; launch errors are
+ *     reported as FPQ_ERR_CUDA and the CUDA error is retrievable with fpq_last_cuda_error();
+ *   - inputs are never modified (the reference's in-place `x.div_(scale)`,
+ *     models_fp_quant_transform_rotate/quant_utils.py:306, is a host-side concern).
+ *
+ * Reference interfaces replaced (paths relative to the reference repository root;
+ * "qu.py" = models_fp_quant_transform_rotate/quant_utils.py, "qu0.py" =
+ * models_fp_quant/quant_utils.py):
+ *   fpq_quant_grid            quant_cuda.quant            quant/quant.cpp:17-29, quant/quant_kernel.cu:11-62
+ *   fpq_fake_quant            fp_quant_e{1,2,3}_per_group_cuda qu.py:265-378, fp6_quant_*_per_{group,token}_cuda
+ *                             qu.py:503-574, argmin variants qu.py:237-358, quantize_to_nearest_grid qu.py:209-230
+ *   fpq_fake_quant_signsplit  fp_quant_e1m2_neg_e2m1_pos_per_group[_cuda] qu.py:381-452,
+ *                             fp6_quant_int_neg_e2m3_pos_per_{group,token}_cuda qu.py:577-646,
+ *                             fp4_afpq_per_group_cuda qu0.py:498-535
+ *   fpq_transform_rotate_quant   basic_var.py:263,266 (`.mul(s)` + `matmul(., Q)`) fused with the
+ *                             following QuantizedLinear.forward act_quant qu.py:764-769
+ *   fpq_transform_rotate_weight  learnable_transformation/transform_model_utils.py:8-28 +
+ *                             rotate_utils/rotation_utils.py:129-154
+ *   fpq_score_formats         search/search_fp4_format.py:340-374,472-476,840-893 and
+ *                             search/search_fp6_format.py:547-554 (tensor-level quantize + MSE)
+ */
+#ifndef FPQ_B200_H
+#define FPQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define FPQ_API __attribute__((visibility("default")))
+#else
+#define FPQ_API
+#endif
+
+/* ---- error codes ---------------------------------------------------------------- */
+#define FPQ_OK               0
+#define FPQ_ERR_ARG         -1   /* bad enum / size / alignment                         */
+#define FPQ_ERR_UNSUPPORTED -2   /* valid request this build has no kernel for          */
+#define FPQ_ERR_CUDA        -3   /* CUDA runtime reported an error at launch            */
+
+/* ---- element types -------------------------------------------------------------- */
+#define FPQ_F32 0
+#define FPQ_F16 1
+
+/* ---- symmetric formats (qu.py:233-235, 458-486) ---------------------------------- */
+#define FPQ_FMT_E2M1 0   /* "fp_e2"    +-{0,.5,1,1.5,2,3,4,6}             max 6    */
+#define FPQ_FMT_E1M2 1   /* "fp_e1"    +-{0,.25,...,1.75}                 max 1.75 */
+#define FPQ_FMT_E3M0 2   /* "fp_e3"    +-{0,.25,.5,1,2,4,8,16}            max 16   */
+#define FPQ_FMT_E2M3 3   /* "fp6_e2m3" 6-bit, 3 mantissa bits             max 7.5  */
+#define FPQ_FMT_E3M2 4   /* "fp6_e3m2" 6-bit, 2 mantissa bits             max 28   */
+#define FPQ_NUM_SYM_FORMATS 5
+
+/* ---- sign-split formats: separate grid and scale for x<=0 and x>0 ----------------- */
+#define FPQ_SPLIT_E1M2NEG_E2M1POS 0  /* "fp_e1m2_neg_e2m1_pos" qu.py:415-452         */
+#define FPQ_SPLIT_INTNEG_E2M3POS  1  /* "fp6_int_neg_e2m3_pos" qu.py:577-646         */
+#define FPQ_SPLIT_AFPQ_E2M1       2  /* "fp4_afpq"             qu0.py:498-535        */
+#define FPQ_NUM_SPLIT_FORMATS 3
+
+/* ---- tie rule -------------------------------------------------------------------- */
+#define FPQ_TIE_KERNEL 0  /* quant_cuda.quant: exact ties -> the LARGER grid value, NaN/inf -> +0
+                             (quant/quant_kernel.cu:25-37)                                     */
+#define FPQ_TIE_ARGMIN 1  /* torch.argmin:     exact ties -> the SMALLER grid value, NaN/inf -> grid[0]
+                             (qu.py:224-230)                                                   */
+
+/* ---- flags ----------------------------------------------------------------------- */
+#define FPQ_FLAG_CLAMP3      1u  /* torch.clamp(x,-3,3) first (qu.py:241,254,289,337,350)          */
+#define FPQ_FLAG_GLOBAL_CLIP 2u  /* sign-split only: reproduce the whole-tensor clip of qu.py:421-422
+                                    at clipping_strength 1.0, i.e. "a NaN anywhere poisons the whole
+                                    tensor"; needs `workspace` (see fpq_fake_quant_signsplit)       */
+
+FPQ_API const char *fpq_version(void);
+/* cudaGetErrorString of the last CUDA error seen by this library on the calling thread. */
+FPQ_API const char *fpq_last_cuda_error(void);
+/* How many of this library's kernels the calling thread has launched (bench.py's gpu_launches). */
+FPQ_API uint64_t fpq_launch_count(void);
+
+/*
+ * z[i] = nearest entry of grid[0..k) to x[i] (fp32, n elements), reference scan semantics;
+ * k <= 256.  tie_mode FPQ_TIE_KERNEL reproduces quant_cuda.quant exactly, including grids it
+ * has never seen (unsorted, duplicated entries); the reference's own grids take a closed-form
+ * path that is proven equal to the scan over all 2^32 inputs (fpq_selftest_rounding).
+ * The reference's second output (`idx`, never written, quant/quant_kernel.cu:49,58) is the
+ * binding's business, not this library's.
+ */
+FPQ_API int fpq_quant_grid(const float *x, const float *grid, int k, size_t n, float *z,
+                   int tie_mode, void *stream);
+
+/*
+ * Symmetric fake-quant: absmax scale -> divide -> grid rounding -> multiply back, in one pass.
+ *   x, out      : n_rows * row_len elements, contiguous; may NOT alias
+ *   row_len     : elements that share one scale: the group size for per_group (128 in the
+ *                 reference; 32..512 powers of two take the group kernel) or the last-dim
+ *                 length for per_token / per_channel (any length >= 1)
+ *   in_dtype    : FPQ_F32 | FPQ_F16;  out_dtype: FPQ_F32 | FPQ_F16
+ *                 (fp16 input reproduces the reference's fp16 scale and fp16 normalised
+ *                 value roundings bit for bit)
+ *   format      : FPQ_FMT_*;  tie_mode: FPQ_TIE_*;  flags: FPQ_FLAG_CLAMP3 or 0
+ */
+FPQ_API int fpq_fake_quant(const void *x, void *out, size_t n_rows, size_t row_len,
+                   int in_dtype, int out_dtype, int format, int tie_mode,
+                   unsigned flags, void *stream);
+
+/*
+ * Sign-split fake-quant (fc2 inputs): x<=0 and x>0 get their own grid and their own absmax
+ * scale per row; out = q_neg*s_neg + q_pos*s_pos.  Arguments as fpq_fake_quant;
+ * `split_format` is FPQ_SPLIT_*.  With FPQ_FLAG_GLOBAL_CLIP, `workspace` must point to 4
+ * zero-initialised bytes of device memory; the kernel raises it when the tensor holds a NaN
+ * and a second (tiny) launch then rewrites `out` as the reference would (all +0).  Without
+ * the flag a NaN element is treated as 0 locally (qu.py:428-429) and `workspace` is unused.
+ */
+FPQ_API int fpq_fake_quant_signsplit(const void *x, void *out, size_t n_rows, size_t row_len,
+                             int in_dtype, int out_dtype, int split_format, int tie_mode,
+                             unsigned flags, void *workspace, void *stream);
+
+/*
+ * Fused activation path of the rotated/transformed model (basic_var.py:263,266 followed by
+ * QuantizedLinear.forward qu.py:764-769):
+ *     y   = half( FWHT_128( x[., c] * smooth[c] * sign[c % 128] ) / fl32(sqrt(128)) )
+ *     out = fake_quant_group128(y, format)         (fp16 in, fp16 out, FPQ_TIE_KERNEL)
+ *   x        : fp32 [n_rows, n_cols], n_cols % 128 == 0 (adaLN-modulated LayerNorm output)
+ *   smooth   : fp32 [n_cols] GALT factor s, or NULL for 1
+ *   sign_bits: 128-bit mask, bit i of word i/32 set = +1 (the seed-42 vector of
+ *              rotate_utils/hadamard_utils.py:95-97); host memory, read at call time
+ *   out      : fp16 [n_rows, n_cols] fake-quantized
+ *   rotated  : optional fp16 [n_rows, n_cols]: the pre-quantization rotated values (NULL to skip)
+ *   format   : FPQ_FMT_* or -1 to skip quantization (then `out` receives the rotated values)
+ */
+FPQ_API int fpq_transform_rotate_quant(const float *x, const float *smooth, const uint32_t *sign_bits_host,
+                               void *out, void *rotated, size_t n_rows, size_t n_cols,
+                               int format, void *stream);
+
+/*
+ * Weight side of the same transform (transform_model_utils.py:8-28, rotation_utils.py:129-154):
+ *     w_out[r, :] = float( FWHT_128_f64( (w[r, c] / smooth[c]) * sign[c % 128] ) / fl32(sqrt(128)) )
+ * fp32 in/out, fp64 butterflies; in-place allowed (w_out == w).  smooth may be NULL.
+ */
+FPQ_API int fpq_transform_rotate_weight(const float *w, const float *smooth, const uint32_t *sign_bits_host,
+                                float *w_out, size_t n_rows, size_t n_cols, void *stream);
+
+/*
+ * Batched format scoring: for every candidate c in formats[0..n_formats) accumulate
+ *     sse[c] += sum_i (x[i] - fake_quant(x, format c)[i])^2          (fp64 accumulators)
+ * reading x ONCE.  formats[] entries: FPQ_FMT_* (0..4) or 16+FPQ_SPLIT_* for sign-split
+ * candidates; host array.  sse: n_formats doubles on the device, accumulated into (the caller
+ * zeroes them and divides by the element count for the reference's mean).
+ */
+FPQ_API int fpq_score_formats(const void *x, size_t n_rows, size_t row_len, int in_dtype,
+                      const int *formats_host, int n_formats, int tie_mode,
+                      double *sse, void *stream);
+
+/*
+ * Exhaustive self-check used by the GPU test-suite: for ALL 2^32 fp32 bit patterns compare the
+ * closed-form rounding of `format` (FPQ_FMT_* or 16+half-grid id, see fpq_kernels.cu) under
+ * `tie_mode` with the literal reference scan over the same grid.  result[0] = mismatch count,
+ * result[1] = bit pattern of the first mismatch found (device memory, 2 x uint64).
+ */
+FPQ_API int fpq_selftest_rounding(int format, int tie_mode, unsigned long long *result, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPQ_B200_H */
