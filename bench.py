@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- fake-quant hot-path throughput (BASELINE.json metric) on B200.
+
+A "step" is one pass of the hot path over one batch of synthetic input: every activation
+fake-quant call of ONE VAR generation pass (10 stages x depth blocks x 4 quantized linears,
+fpqvar_b200/var_workload.py).  Default workload = BASELINE.json configs[2], the configuration
+the metric is quoted on (VAR-d30 256x256 W4A4 fp_e2 + fc2 fp_e1m2_neg_e2m1_pos, block rotate +
+GALT transform, B=50 per GPU).  Multi-GPU: image batches are independent, so every rank runs its
+own batch (weak scaling, no data-path collective; one final gather of the timings).
+
+  value     algorithmic GB/s (input bytes read once + output bytes written once), inputs resident
+            in HBM, one CUDA-graph replay per step, CUDA events, max over ranks
+  e2e       same metric through the HOST-buffer entry (fpqvar_b200.hotpath.HostPipeline): pinned
+            H2D copy of every input and D2H copy of every output inside the timed region
+  roofline  the dominant kernel's launches of the step, timed alone with CUDA events
+  cpu_baseline   oracle/fakequant_port.c (multi-threaded C port of the reference functions) on a
+            bounded sample of the same workload, rank 0 / N=1 only
+
+`--impl reference` times that CPU port alone (the reference has no CPU-runnable build of its CUDA
+extension and its Python cannot travel to the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import statistics
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "fake_quant_throughput"
+UNIT = "GB/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="var_d30_w4a4_rot")
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--profile", action="store_true",
+                    help="for ncu: one warm-up replay + the timed steps only (no roofline graphs, no e2e, no CPU baseline)")
+    return ap.parse_args()
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.proc = None
+        self.path = f"/tmp/fpq_clocks_{os.getpid()}.csv"
+        exe = shutil.which("nvidia-smi")
+        if exe:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen([exe, "-i", str(index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=self.f, stderr=subprocess.DEVNULL)
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0])); mx.append(float(parts[1]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, parts[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU baseline / reference arm (oracle port; the ONLY place bench.py touches oracle/)
+# ----------------------------------------------------------------------------------------------
+def cpu_sample_inputs(hot, np, seed=0):
+    """Bounded sample: the four quantizer calls of ONE block (of `depth`) at every one of the 10
+    stages, i.e. 1/depth of a step."""
+    rng = np.random.default_rng(seed)
+    calls = hot.calls(blocks=[0])
+    data = []
+    for c in calls:
+        x = rng.standard_normal((c.rows, c.cols), dtype=np.float32)
+        if c.site == "fc2":
+            x = 0.5 * x * (1.0 + np.tanh(0.7978845608 * (x + 0.044715 * x ** 3)))     # GELU(tanh) skew, as the fc2 input has
+        if c.in_dtype == "f16":
+            x = x.astype(np.float16)
+        data.append(x)
+    return calls, data
+
+
+def cpu_run_sample(calls, data, smooth, P):
+    for c, x in zip(calls, data):
+        if c.op == "group":
+            P.fake_quant(x, c.fmt, 128, "kernel", out_dtype={"f32": "float32", "f16": "float16"}[c.out_dtype])
+        elif c.op == "signsplit":
+            P.fake_quant_signsplit(x, c.fmt, 128, "kernel")
+        else:
+            P.transform_rotate_quant(x, smooth, c.fmt)
+
+
+def cpu_baseline(hot, seconds, steps=None, warmup=1):
+    import numpy as np
+    from oracle import port as P       # test infrastructure, used here as the timed CPU baseline only
+    calls, data = cpu_sample_inputs(hot, np)
+    smooth = np.exp(np.random.default_rng(1).uniform(-1, 1, hot.width)).astype(np.float32)
+    nbytes = sum(c.bytes for c in calls)
+    for _ in range(warmup):
+        cpu_run_sample(calls, data, smooth, P)
+    times = []
+    t_end = time.perf_counter() + seconds
+    while (steps is None and time.perf_counter() < t_end and len(times) < 50) or (steps is not None and len(times) < steps):
+        t0 = time.perf_counter()
+        cpu_run_sample(calls, data, smooth, P)
+        times.append(time.perf_counter() - t0)
+        if steps is None and len(times) >= 2 and sum(times) > seconds:
+            break
+    mean = sum(times) / len(times)
+    return {
+        "value": nbytes / mean / 1e9, "unit": UNIT, "cores": P.num_threads(), "kind": "port",
+        "sample": f"1 of {hot.depth} blocks x all {len(hot.patch_nums)} stages of {hot.name} ({nbytes / 1e9:.2f} GB algorithmic, "
+                  f"{len(calls)} calls), {len(times)} repeats, {mean:.3f} s each; oracle/fakequant_port.c on {P.num_threads()} threads",
+    }, mean, len(times)
+
+
+def run_reference(args, hot):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base, mean, n = cpu_baseline(hot, 0.0, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32/f16", "data": "synthetic",
+        "config": {"workload": hot.name, "step": "bounded sample: " + base["sample"]},
+        "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+# B200 arm
+# ----------------------------------------------------------------------------------------------
+class Arena:
+    """A big device buffer handed out in rotating slices, so that no call re-reads bytes that could
+    still sit in the 126 MB L2 from an earlier call."""
+
+    def __init__(self, tensor):
+        self.t = tensor
+        self.nbytes = tensor.numel() * tensor.element_size()
+        self.base = tensor.data_ptr()
+        self.cur = 0
+
+    def take(self, nbytes):
+        nbytes_al = (nbytes + 255) // 256 * 256
+        if nbytes_al > self.nbytes:
+            raise RuntimeError("arena too small")
+        if self.cur + nbytes_al > self.nbytes:
+            self.cur = 0
+        p = self.base + self.cur
+        self.cur += nbytes_al
+        return p
+
+
+def main():
+    args = parse_args()
+    from fpqvar_b200.var_workload import WORKLOADS
+    hot = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, hot)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from fpqvar_b200 import _lib as L
+    from fpqvar_b200.hotpath import DeviceReplay, HostPipeline
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU baseline)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.lib()
+
+    calls = hot.calls()
+    step_bytes = sum(c.bytes for c in calls)
+    in_bytes = sum(c.in_bytes for c in calls)
+    out_bytes = sum(c.out_bytes for c in calls)
+    C = hot.width
+
+    # ---- synthetic inputs, resident in HBM --------------------------------------------------
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    GiB = 1 << 30
+    a_f32 = torch.randn(GiB // 4 * 2, generator=g, device=dev, dtype=torch.float32)               # 2 GiB N(0,1) fp32
+    a_f16 = torch.randn(GiB // 2, generator=g, device=dev, dtype=torch.float32).to(torch.float16)  # 1 GiB N(0,1) fp16
+    a_gelu = torch.nn.functional.gelu(torch.randn(GiB, generator=g, device=dev, dtype=torch.float32), approximate="tanh").to(torch.float16)  # 2 GiB
+    a_out = torch.empty(2 * GiB, dtype=torch.uint8, device=dev)
+    arenas = {"f32": Arena(a_f32), "f16": Arena(a_f16), "gelu": Arena(a_gelu), "out": Arena(a_out)}
+    gs = torch.Generator(device="cpu"); gs.manual_seed(7)
+    smooth = {site: torch.exp(torch.rand(C, generator=gs) * 2 - 1).to(dev) for site in ("mat_qkv", "fc1")} if hot.rotate_transform else {}
+    replay = DeviceReplay(dev, smooth)
+
+    def in_arena(c):
+        if c.in_dtype == "f32":
+            return arenas["f32"]
+        return arenas["gelu"] if c.site == "fc2" else arenas["f16"]
+
+    plan = [(c, in_arena(c).take(c.in_bytes), arenas["out"].take(c.out_bytes)) for c in calls]
+
+    def issue(subset, stream):
+        for c, pi, po in subset:
+            replay.launch(c, pi, po, stream)
+
+    side = torch.cuda.Stream(dev)
+
+    def capture(subset):
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            issue(subset[:8], side.cuda_stream)           # make sure lazy init happened outside capture
+            side.synchronize()
+            n0 = lib.fpq_launch_count()
+            with torch.cuda.graph(gr, stream=side):
+                issue(subset, side.cuda_stream)
+            n_launch = lib.fpq_launch_count() - n0
+        return gr, int(n_launch)
+
+    graph, launches_per_step = capture(plan)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed_replays(gr, k):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        with torch.cuda.stream(side):
+            e0.record(side)
+            for _ in range(k):
+                gr.replay()
+            e1.record(side)
+        barrier()
+        return e0.elapsed_time(e1) / 1e3
+
+    n_warm = 1 if args.profile else max(3, args.warmup)
+    for _ in range(n_warm):
+        graph.replay()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_dev = timed_replays(graph, args.steps)
+    if args.profile:
+        if sampler:
+            sampler.stop()
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "steps": args.steps, "launches_per_step": launches_per_step,
+                              "value_under_profiler_is_not_a_bench_value": world * args.steps * step_bytes / t_dev / 1e9}))
+        return
+
+    # ---- roofline of the dominant kernel (timed alone, same inputs) --------------------------
+    by_kernel = {}
+    for item in plan:
+        c = item[0]
+        by_kernel.setdefault((c.op, c.fmt, c.in_dtype, c.out_dtype), []).append(item)
+    dom_key = max(by_kernel, key=lambda k: sum(i[0].bytes for i in by_kernel[k]))
+    dom = by_kernel[dom_key]
+    dom_graph, dom_launches = capture(dom)
+    for _ in range(3):
+        dom_graph.replay()
+    t_dom = timed_replays(dom_graph, args.steps)
+    dom_bytes = sum(i[0].bytes for i in dom)
+    # the big-stage launches of that kernel alone (bandwidth-bound regime; the early stages are launch-latency-bound)
+    big = [i for i in dom if i[0].bytes >= 64 << 20]
+    big_graph, _ = capture(big)
+    for _ in range(3):
+        big_graph.replay()
+    t_big = timed_replays(big_graph, args.steps)
+    big_bytes = sum(i[0].bytes for i in big)
+    clocks = sampler.stop() if sampler else None
+
+    # ---- e2e: host buffers through HostPipeline ----------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        max_in = max(c.in_bytes for c in calls)
+        max_out = max(c.out_bytes for c in calls)
+        pipe = HostPipeline(dev, max_in, max_out, smooth)
+        h_f32 = torch.randn(max(c.in_bytes for c in calls if c.in_dtype == "f32") // 4 if any(c.in_dtype == "f32" for c in calls) else 1).pin_memory()
+        h_f16 = torch.nn.functional.gelu(torch.randn(max(c.in_bytes for c in calls if c.in_dtype == "f16") // 2), approximate="tanh").to(torch.float16).pin_memory()
+        h_out = [torch.empty(max_out, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        v32, v16 = h_f32.view(torch.uint8), h_f16.view(torch.uint8)
+        hin = [v32 if c.in_dtype == "f32" else v16 for c in calls]
+        hout = [h_out[i % 2] for i in range(len(calls))]
+        pipe.run(calls[: 4 * hot.depth], hin, hout)        # warm-up: the first stage
+        pipe.synchronize()
+        n_e2e = max(1, args.e2e_steps)
+        barrier()
+        t0 = time.perf_counter()
+        n0 = lib.fpq_launch_count()
+        for _ in range(n_e2e):
+            pipe.run(calls, hin, hout)
+        pipe.synchronize()
+        barrier()
+        t_e2e = time.perf_counter() - t0
+        e2e_launches = int(lib.fpq_launch_count() - n0)
+        if world > 1:
+            t = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            t_e2e = float(t.item())
+        e2e = {"value": world * n_e2e * step_bytes / t_e2e / 1e9, "unit": UNIT, "h2d_bytes_per_step": world * in_bytes,
+               "d2h_bytes_per_step": world * out_bytes, "steps": n_e2e, "ms_per_step": t_e2e / n_e2e * 1e3,
+               "api": "fpqvar_b200.hotpath.HostPipeline.run (pinned host buffers -> C ABI -> pinned host buffers)",
+               "launches": e2e_launches}
+        del pipe
+
+    # ---- gather (the only collective) --------------------------------------------------------
+    if world > 1:
+        t = torch.tensor([t_dev, t_dom, t_big], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_dev, t_dom, t_big = (float(v) for v in t.tolist())
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        value = world * args.steps * step_bytes / t_dev / 1e9
+        dom_gbs = args.steps * dom_bytes / t_dom / 1e9
+        big_gbs = args.steps * big_bytes / t_big / 1e9
+        kname = {"group": "fake_quant_group_kernel", "signsplit": "signsplit_group_kernel", "rotate_quant": "transform_rotate_quant_kernel"}[dom_key[0]]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
+            "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32/f16", "data": "synthetic",
+            "config": {
+                "workload": hot.name,
+                "desc": f"VAR-d{hot.depth} W4A4 hot path: {len(calls)} activation fake-quant calls of one generation pass, B={hot.batch}/GPU "
+                        f"({hot.elems_per_pass() / 1e9:.2f} G elements, {step_bytes / 1e9:.1f} GB algorithmic per GPU per step)",
+                "l2": "inputs/outputs rotate through 2 GiB/1 GiB/2 GiB/2 GiB arenas (>> 126 MB L2); no address is re-read within 1 GiB of traffic",
+                "launch": "one CUDA-graph replay per step", "parallelism": f"dp{world} (independent image batches, no data-path collective)",
+            },
+            "roofline": {
+                "bound": "hbm", "kernel": f"{kname}<{dom_key[2]}->{dom_key[3]},{dom_key[1]}>", "achieved": dom_gbs, "peak": peak,
+                "unit": "GB/s", "frac": dom_gbs / peak, "traffic": None, "peak_source": peak_src,
+                "launches_per_step": dom_launches, "avg_launch_us": t_dom / args.steps / max(1, dom_launches) * 1e6,
+                "bytes_per_launch": dom_bytes / max(1, dom_launches),
+                "large_launches": {"min_bytes": 64 << 20, "achieved": big_gbs, "frac": big_gbs / peak, "n": len(big)},
+                "frac_of_nominal_8TBps": dom_gbs / 8000.0,
+            },
+            "gpu_launches": launches_per_step * args.steps,
+            "clocks": clocks,
+        }
+        if e2e is not None:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu:
+            base, _, _ = cpu_baseline(hot, args.cpu_seconds)
+            line["cpu_baseline"] = base
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

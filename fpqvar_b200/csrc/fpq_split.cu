@@ -192,7 +192,7 @@ using namespace fpq;
 
 extern "C" int fpq_fake_quant_signsplit(const void* x, void* out, size_t n_rows, size_t row_len, int in_dtype, int out_dtype,
                                         int split_format, int tie_mode, unsigned flags, void* workspace, void* stream) {
-    if (row_len == 0 || (n_rows && (!x || !out)) || x == out) return FPQ_ERR_ARG;
+    if (row_len == 0 || (n_rows && (!x || !out || x == out))) return FPQ_ERR_ARG;
     if (flags & ~FPQ_FLAG_GLOBAL_CLIP) return FPQ_ERR_ARG;
     if ((flags & FPQ_FLAG_GLOBAL_CLIP) && !workspace) return FPQ_ERR_ARG;
     if (n_rows == 0) return FPQ_OK;

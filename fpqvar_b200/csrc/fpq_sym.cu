@@ -138,7 +138,7 @@ using namespace fpq;
 
 extern "C" int fpq_fake_quant(const void* x, void* out, size_t n_rows, size_t row_len, int in_dtype, int out_dtype, int format,
                               int tie_mode, unsigned flags, void* stream) {
-    if (row_len == 0 || (n_rows && (!x || !out)) || x == out) return FPQ_ERR_ARG;
+    if (row_len == 0 || (n_rows && (!x || !out || x == out))) return FPQ_ERR_ARG;
     if (flags & ~FPQ_FLAG_CLAMP3) return FPQ_ERR_ARG;
     if (n_rows == 0) return FPQ_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
