@@ -37,6 +37,7 @@ SIGNATURES = {
     "fpq_score_formats": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int,
                                      _c.c_void_p, _c.c_void_p]),
     "fpq_selftest_rounding": (_c.c_int, [_c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
+    "fpq_selftest_f16_flow": (_c.c_int, [_c.c_int, _c.c_void_p, _c.c_void_p]),
 }
 
 _lib = None

@@ -53,6 +53,9 @@ static __constant__ GridTable c_grids[GT_COUNT] = {
 // launch bookkeeping (defined in fpq_grid.cu)
 int finish_launch();
 int sm_count();
+// packed fp16 -> fp16 group-of-128 kernels, kernel tie rule (fpq_h16.cu)
+int launch_sym_h16(int format, const void* x, void* out, size_t n_groups, cudaStream_t st);
+int launch_split_h16(int split, const void* x, void* out, size_t n_groups, unsigned* nan_flag, cudaStream_t st);
 static inline unsigned grid_for(size_t work_items, size_t items_per_block, int blocks_per_sm) {
     size_t need = (work_items + items_per_block - 1) / items_per_block;
     size_t cap = size_t(sm_count()) * blocks_per_sm;

@@ -1,0 +1,253 @@
+// libfpq_b200 -- packed fp16 -> fp16 kernels (kernel tie rule, groups of 128): the activation
+// quantizers of the hot path (reference rows a2, a3 of SURVEY.md section 8) at low instruction
+// count, see fpq_h16.cuh.  Part of the C ABI of include/fpq_b200.h; no torch types here.
+#include "fpq_h16.cuh"
+
+namespace fpq {
+
+constexpr int H16_LPG = 4;          // lanes per 128-group
+constexpr int H16_NV = 4;           // 16-byte vectors per lane and group: 32 halves = 16 packed words per lane
+constexpr int H16_NW = 4 * H16_NV;
+constexpr int H16_GPW = 32 / H16_LPG;   // groups per warp and loop trip
+
+// vector j of lane l covers halves [(j*LPG + l)*8, +8) of the group: a warp-wide 128-bit load touches
+// 8 groups x 64 contiguous bytes (whole 32-byte sectors; the other half of each 128-byte line follows
+// with the next j)
+__device__ __forceinline__ void load_tile_h16(const __half* base, int lig, uint32_t (&p)[H16_NW]) {
+#pragma unroll
+    for (int j = 0; j < H16_NV; ++j) {
+        const uint4 u = ldg_stream(base + (j * H16_LPG + lig) * 8);
+        p[4 * j] = u.x; p[4 * j + 1] = u.y; p[4 * j + 2] = u.z; p[4 * j + 3] = u.w;
+    }
+}
+__device__ __forceinline__ void store_tile_h16(__half* base, int lig, const uint32_t (&p)[H16_NW]) {
+#pragma unroll
+    for (int j = 0; j < H16_NV; ++j) stg_stream(base + (j * H16_LPG + lig) * 8, make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]));
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(256) fake_quant_group_h16_kernel(const __half* __restrict__ x, __half* __restrict__ out, size_t n_groups) {
+    const int lane = threadIdx.x & 31;
+    const int lig = lane % H16_LPG;
+    const size_t warp_global = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
+    const float delta = tie_delta_kernel(uint32_t(warp_global >> 33));
+    for (size_t gbase = warp_global * H16_GPW; gbase < n_groups; gbase += n_warps * H16_GPW) {
+        const size_t g = gbase + lane / H16_LPG;
+        const bool valid = g < n_groups;
+        uint32_t p[H16_NW];
+        if (valid) {
+            load_tile_h16(x + g * 128, lig, p);
+        } else {
+#pragma unroll
+            for (int i = 0; i < H16_NW; ++i) p[i] = 0u;
+        }
+        float s;
+        const bool ok = sym_quant_tile_h16<FMT, H16_LPG, H16_NW>(p, s, delta);
+        if (valid) {
+            if (ok) store_tile_h16(out + g * 128, lig, p);
+            else literal_sym_h16(x + g * 128, out + g * 128, lig, H16_LPG, 8, H16_NV, s, SymFmt<FMT>::GT);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// sign-split
+// ------------------------------------------------------------------------------------------
+template <int SPLIT> struct SplitH16;
+template <> struct SplitH16<FPQ_SPLIT_E1M2NEG_E2M1POS> { using NEG = HG_E1M2; using POS = HG_E2M1; static constexpr int GT_N = GT_E1M2_NEG, GT_P = GT_E2M1_POS; };
+template <> struct SplitH16<FPQ_SPLIT_INTNEG_E2M3POS> { using NEG = HG_INT32; using POS = HG_E2M3; static constexpr int GT_N = GT_INT_NEG, GT_P = GT_E2M3_POS; };
+template <> struct SplitH16<FPQ_SPLIT_AFPQ_E2M1> { using NEG = HG_E2M1; using POS = HG_E2M1; static constexpr int GT_N = GT_E2M1_NEG, GT_P = GT_E2M1_POS; };
+
+// Group maxima by integer order of the fp16 bit patterns (two elements per VIMNMX):
+//   signed 16-bit max   -> the largest positive value (bits < 0x8000 order like the values)
+//   unsigned 16-bit max -> 0x8000 | largest negative magnitude, if any element is negative
+// NaN patterns are the extreme of either order, so they surface in the result.
+// returns 0: handled; 1: irregular scale (sn, sp valid) -> literal_split_h16; 2: the group holds a NaN
+// -> literal_split_nan_group_h16
+template <int SPLIT, int LPG, int NW>
+__device__ __forceinline__ int split_quant_tile_h16(uint32_t (&p)[NW], float& sn, float& sp, float delta) {
+    using SF = SplitH16<SPLIT>;
+    uint32_t pm = 0u, nm = 0u;
+#pragma unroll
+    for (int i = 0; i < NW; ++i) { pm = __vmaxs2(pm, p[i]); nm = __vmaxu2(nm, p[i]); }
+    int pmax = max(int(short(pm & 0xffffu)), int(short(pm >> 16)));          // >= 0
+    uint32_t nmax = max(nm & 0xffffu, nm >> 16);
+#pragma unroll
+    for (int o = LPG / 2; o > 0; o >>= 1) {
+        pmax = max(pmax, __shfl_xor_sync(0xffffffffu, pmax, o));
+        nmax = max(nmax, __shfl_xor_sync(0xffffffffu, nmax, o));
+    }
+    const uint32_t pbits = uint32_t(pmax);
+    const uint32_t nbits = nmax >= 0x8000u ? (nmax & 0x7fffu) : 0u;
+    if (pbits > 0x7C00u || nbits > 0x7C00u) return 2;
+    const float an = h2f(uint16_t(nbits)), ap = h2f(uint16_t(pbits));
+    const __half snh = scale_from_absmax_h16<typename SF::NEG>(an);           // quant_utils.py:432
+    const __half sph = scale_from_absmax_h16<typename SF::POS>(ap);           // quant_utils.py:433
+    sn = __half2float(snh);
+    sp = __half2float(sph);
+    // a side without elements has absmax 0 and scale 0 exactly (nbits / pbits == 0)
+    const uint32_t snb = __half_as_ushort(snh), spb = __half_as_ushort(sph);
+    if (!((scale_bits_regular(snb) || nbits == 0u) && (scale_bits_regular(spb) || pbits == 0u))) {
+        sn = rnd_in<__half>(__fdiv_rn(an, SF::NEG::VMAX));                    // literal scales for the literal path
+        sp = rnd_in<__half>(__fdiv_rn(ap, SF::POS::VMAX));
+        return 1;
+    }
+    const float rn = nbits == 0u ? 0.0f : rcp_rn_normal(sn);
+    const float rp = pbits == 0u ? 0.0f : rcp_rn_normal(sp);
+#pragma unroll
+    for (int i = 0; i < NW; ++i) p[i] = split_pair_h16<typename SF::NEG, typename SF::POS>(p[i], rn, sn, rp, sp, delta);
+    return 0;
+}
+
+template <int SPLIT>
+__global__ void __launch_bounds__(256) signsplit_group_h16_kernel(const __half* __restrict__ x, __half* __restrict__ out, size_t n_groups,
+                                                                  unsigned* __restrict__ nan_flag) {
+    const int lane = threadIdx.x & 31;
+    const int lig = lane % H16_LPG;
+    const size_t warp_global = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
+    const float delta = tie_delta_kernel(uint32_t(warp_global >> 33));
+    for (size_t gbase = warp_global * H16_GPW; gbase < n_groups; gbase += n_warps * H16_GPW) {
+        const size_t g = gbase + lane / H16_LPG;
+        const bool valid = g < n_groups;
+        uint32_t p[H16_NW];
+        if (valid) {
+            load_tile_h16(x + g * 128, lig, p);
+        } else {
+#pragma unroll
+            for (int i = 0; i < H16_NW; ++i) p[i] = 0u;
+        }
+        float sn, sp;
+        const int rc = split_quant_tile_h16<SPLIT, H16_LPG, H16_NW>(p, sn, sp, delta);
+        if (rc == 2 && nan_flag != nullptr) atomicOr(nan_flag, 1u);
+        if (valid) {
+            using SF = SplitH16<SPLIT>;
+            if (rc == 0) store_tile_h16(out + g * 128, lig, p);
+            else if (rc == 1) literal_split_h16(x + g * 128, out + g * 128, lig, H16_LPG, 8, H16_NV, sn, sp, SF::GT_N, SF::GT_P);
+            else literal_split_nan_group_h16(x + g * 128, out + g * 128, lig, H16_LPG, 8, H16_NV, SF::NEG::VMAX, SF::POS::VMAX, SF::GT_N, SF::GT_P);
+        }
+    }
+}
+
+static unsigned grid_h16(size_t n_groups) {
+    // 8 warps x 8 groups per block and trip; enough blocks to fill every SM's thread slots
+    return grid_for(n_groups, 8 * H16_GPW, 8);
+}
+
+int launch_sym_h16(int format, const void* x, void* out, size_t n_groups, cudaStream_t st) {
+    const __half* xi = static_cast<const __half*>(x);
+    __half* oo = static_cast<__half*>(out);
+    const unsigned grid = grid_h16(n_groups);
+    switch (format) {
+        case FPQ_FMT_E2M1: fake_quant_group_h16_kernel<FPQ_FMT_E2M1><<<grid, 256, 0, st>>>(xi, oo, n_groups); break;
+        case FPQ_FMT_E1M2: fake_quant_group_h16_kernel<FPQ_FMT_E1M2><<<grid, 256, 0, st>>>(xi, oo, n_groups); break;
+        case FPQ_FMT_E3M0: fake_quant_group_h16_kernel<FPQ_FMT_E3M0><<<grid, 256, 0, st>>>(xi, oo, n_groups); break;
+        case FPQ_FMT_E2M3: fake_quant_group_h16_kernel<FPQ_FMT_E2M3><<<grid, 256, 0, st>>>(xi, oo, n_groups); break;
+        case FPQ_FMT_E3M2: fake_quant_group_h16_kernel<FPQ_FMT_E3M2><<<grid, 256, 0, st>>>(xi, oo, n_groups); break;
+        default: return FPQ_ERR_ARG;
+    }
+    return finish_launch();
+}
+
+int launch_split_h16(int split, const void* x, void* out, size_t n_groups, unsigned* nan_flag, cudaStream_t st) {
+    const __half* xi = static_cast<const __half*>(x);
+    __half* oo = static_cast<__half*>(out);
+    const unsigned grid = grid_h16(n_groups);
+    switch (split) {
+        case FPQ_SPLIT_E1M2NEG_E2M1POS: signsplit_group_h16_kernel<FPQ_SPLIT_E1M2NEG_E2M1POS><<<grid, 256, 0, st>>>(xi, oo, n_groups, nan_flag); break;
+        case FPQ_SPLIT_INTNEG_E2M3POS: signsplit_group_h16_kernel<FPQ_SPLIT_INTNEG_E2M3POS><<<grid, 256, 0, st>>>(xi, oo, n_groups, nan_flag); break;
+        case FPQ_SPLIT_AFPQ_E2M1: signsplit_group_h16_kernel<FPQ_SPLIT_AFPQ_E2M1><<<grid, 256, 0, st>>>(xi, oo, n_groups, nan_flag); break;
+        default: return FPQ_ERR_ARG;
+    }
+    return finish_launch();
+}
+
+// ------------------------------------------------------------------------------------------
+// Exhaustive self-test of the packed element functions: every (x, scale) pair of fp16 values
+// that can meet in a regular group, against the literal reference sequence
+// (divide -> half -> scan -> multiply -> half).
+// ------------------------------------------------------------------------------------------
+template <class HG>
+__device__ __forceinline__ bool pair_possible(float x, float s) {
+    // x can share a group with scale s only if |x| <= absmax and half(absmax/VMAX) == s, which
+    // implies half(|x|/VMAX) <= s
+    return rnd_in<__half>(__fdiv_rn(fabsf(x), HG::VMAX)) <= s;
+}
+
+template <int CODE>
+__global__ void selftest_f16_flow_kernel(unsigned long long* result) {
+    unsigned long long bad = 0, first = ~0ull;
+    // s: every regular fp16 scale 0x0400..0x7BFF; x: every fp16 bit pattern that is finite
+    const unsigned long long total = (0x7C00ull - 0x0400ull) << 16;
+    for (unsigned long long idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x; idx < total; idx += size_t(gridDim.x) * blockDim.x) {
+        const uint16_t sb = uint16_t(0x0400u + (idx >> 16));
+        const uint16_t xb = uint16_t(idx & 0xffffu);
+        if ((xb & 0x7fffu) >= 0x7C00u) continue;
+        const float s = h2f(sb), x = h2f(xb);
+        const float r = rcp_rn_normal(s);
+        const float delta = tie_delta_kernel(0u);
+        if (xb == 0 && __float_as_uint(r) != __float_as_uint(__frcp_rn(s))) { ++bad; if (idx < first) first = idx; }
+        uint32_t got, want;
+        if constexpr (CODE < 16) {
+            using HG = typename SymFmt<CODE>::HG;
+            if (!pair_possible<HG>(x, s)) continue;
+            got = sym_pair_h16<HG>(uint32_t(xb), pk(r, r), pk(s, s), delta) & 0xffffu;
+            want = f2h(quant_elem_literal<__half, TIE_KERNEL>(x, s, c_grids[SymFmt<CODE>::GT]) * s);
+        } else {
+            using SF = SplitH16<CODE - 16>;
+            // the other side's scale does not influence this element: use the same s on both sides
+            const bool pos = x > 0.0f;
+            if (pos ? !pair_possible<typename SF::POS>(x, s) : !pair_possible<typename SF::NEG>(x, s)) continue;
+            got = split_pair_h16<typename SF::NEG, typename SF::POS>(uint32_t(xb), r, s, r, s, delta) & 0xffffu;
+            const float xn = (x <= 0.0f) ? x : 0.0f, xp = pos ? x : 0.0f;
+            const float qn = scan_kernel_rule(rnd_in<__half>(__fdiv_rn(xn, s)), c_grids[SF::GT_N].v, c_grids[SF::GT_N].k);
+            const float qp = scan_kernel_rule(rnd_in<__half>(__fdiv_rn(xp, s)), c_grids[SF::GT_P].v, c_grids[SF::GT_P].k);
+            want = f2h(__fadd_rn(__fmul_rn(qn, s), __fmul_rn(qp, s)));
+        }
+        if (got != want) { ++bad; if (idx < first) first = idx; }
+    }
+    // scale: half(a * RN(1/VMAX)) == half(a / VMAX) for every fp16 absmax a whose scale is regular by
+    // either formula (irregular scales are recomputed with the true division)
+    for (unsigned ab = blockIdx.x * blockDim.x + threadIdx.x; ab <= 0x7C00u; ab += gridDim.x * blockDim.x) {
+        const float a = h2f(uint16_t(ab));
+        auto same = [&](uint32_t fast, uint32_t exact) {
+            return fast == exact || (!scale_bits_regular(fast) && !scale_bits_regular(exact));
+        };
+        bool ok;
+        if constexpr (CODE < 16) {
+            using HG = typename SymFmt<CODE>::HG;
+            ok = same(__half_as_ushort(scale_from_absmax_h16<HG>(a)), f2h(__fdiv_rn(a, HG::VMAX)));
+        } else {
+            using SF = SplitH16<CODE - 16>;
+            ok = same(__half_as_ushort(scale_from_absmax_h16<typename SF::NEG>(a)), f2h(__fdiv_rn(a, SF::NEG::VMAX))) &&
+                 same(__half_as_ushort(scale_from_absmax_h16<typename SF::POS>(a)), f2h(__fdiv_rn(a, SF::POS::VMAX)));
+        }
+        if (!ok) { ++bad; first = 0; }
+    }
+    if (bad) { atomicAdd(result, bad); atomicMin(result + 1, first); }
+}
+
+}  // namespace fpq
+
+using namespace fpq;
+
+extern "C" int fpq_selftest_f16_flow(int format, unsigned long long* result, void* stream) {
+    if (!result) return FPQ_ERR_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaMemsetAsync(result, 0, sizeof(unsigned long long), st);
+    cudaMemsetAsync(result + 1, 0xff, sizeof(unsigned long long), st);
+    const unsigned grid = unsigned(sm_count()) * 16;
+    switch (format) {
+        case 0: selftest_f16_flow_kernel<0><<<grid, 256, 0, st>>>(result); break;
+        case 1: selftest_f16_flow_kernel<1><<<grid, 256, 0, st>>>(result); break;
+        case 2: selftest_f16_flow_kernel<2><<<grid, 256, 0, st>>>(result); break;
+        case 3: selftest_f16_flow_kernel<3><<<grid, 256, 0, st>>>(result); break;
+        case 4: selftest_f16_flow_kernel<4><<<grid, 256, 0, st>>>(result); break;
+        case 16: selftest_f16_flow_kernel<16><<<grid, 256, 0, st>>>(result); break;
+        case 17: selftest_f16_flow_kernel<17><<<grid, 256, 0, st>>>(result); break;
+        case 18: selftest_f16_flow_kernel<18><<<grid, 256, 0, st>>>(result); break;
+        default: return FPQ_ERR_ARG;
+    }
+    return finish_launch();
+}

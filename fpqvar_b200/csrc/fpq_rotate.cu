@@ -10,93 +10,121 @@
 // (fpq_common.cuh).  With fp32 input, value v[4j+k] of lane l is element e = 32j + 4l + k of the
 // chunk, so the seven index bits split as k (2 bits, in registers), l (3 bits, across lanes:
 // shfl.xor 1,2,4) and j (2 bits, in registers).  A Sylvester Hadamard transform is the tensor
-// product of a 2-point butterfly over every index bit, in any order.
-#include "fpq_common.cuh"
+// product of a 2-point butterfly over every index bit, in any order (here: 0, 1, 5, 6, 2, 3, 4).
+#include "fpq_h16.cuh"
 
 namespace fpq {
 
 struct SignMask { uint32_t w[4]; };    // bit e of the 128-bit mask set  <=>  sigma[e] = +1
 
-// butterflies over the two register-resident index pairs (k: strides 1,2 ; j: strides 4,8 of v[])
-template <typename T>
-__device__ __forceinline__ void fwht16_regs(T (&v)[16]) {
-#pragma unroll
-    for (int h = 1; h < 16; h <<= 1) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            if ((i & h) == 0) {
-                const T a = v[i], b = v[i + h];
-                v[i] = a + b;
-                v[i + h] = a - b;
-            }
-        }
-    }
-}
-
-// butterflies over the three lane bits of an 8-lane group
-__device__ __forceinline__ void fwht_lanes8(float (&v)[16], int lig) {
-#pragma unroll
-    for (int o = 1; o < 8; o <<= 1) {
-        const float sg = (lig & o) ? -1.0f : 1.0f;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const float p = __shfl_xor_sync(0xffffffffu, v[i], o);
-            v[i] = fmaf(v[i], sg, p);          // upper lane: p - v ; lower lane: v + p  (exact: *+-1)
-        }
-    }
-}
-
 // 1 / fl32(sqrt(128)), rounded to fp32 (0x3DB504F3)
 __device__ __forceinline__ float inv_sqrt128() { return __uint_as_float(0x3DB504F3u); }
 
+// Activation kernel.  Work mapping: every 8-lane set owns ONE column chunk cc (so its 16
+// smooth*sign multipliers are loaded once and live in registers) and walks down the rows
+// k, k+K, k+2K, ... of that chunk column.  Arithmetic is two elements per instruction where the
+// ISA allows (FMUL2/FFMA2/FADD2 packed fp32, sm_100): P[2j] = (v[4j], v[4j+1]), P[2j+1] = (v[4j+2], v[4j+3]).
 template <int FMT, bool QUANT>
 __global__ void __launch_bounds__(256) transform_rotate_quant_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
                                                                      SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
-                                                                     size_t n_chunks, int chunks_per_row) {
+                                                                     size_t n_rows, int cpr, size_t sets_per_col) {
     constexpr int LPG = 8;
     const int lane = threadIdx.x & 31;
     const int lig = lane % LPG;
-    const size_t warp_global = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
+    const size_t ls = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) / LPG;       // lane-set id
+    const int cc = int(ls % size_t(cpr));
+    const size_t k0 = ls / size_t(cpr);
+    const bool active = k0 < sets_per_col;
+    const size_t row_stride = size_t(cpr) * 128;
 
-    // sign of the 16 chunk positions this lane owns, as an xor mask on the fp32 sign bit
-    uint32_t sgn[16];
+    // multipliers m = smooth * sign for the 16 chunk positions of this lane (sign flips are exact,
+    // so (x*s)*sigma == x*(s*sigma) bit for bit)
+    uint64_t ms[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
+    for (int j = 0; j < 4; ++j) {
+        float4 s4 = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+        if (smooth != nullptr) s4 = __ldg(reinterpret_cast<const float4*>(smooth + size_t(cc) * 128 + (j * LPG + lig) * 4));
+        float f[4] = {s4.x, s4.y, s4.z, s4.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) sgn[4 * j + k] = ((sm.w[j] >> (4 * lig + k)) & 1u) ? 0u : 0x80000000u;
+        for (int k = 0; k < 4; ++k)
+            if (!((sm.w[j] >> (4 * lig + k)) & 1u)) f[k] = -f[k];
+        ms[2 * j] = pk(f[0], f[1]);
+        ms[2 * j + 1] = pk(f[2], f[3]);
+    }
+    const uint64_t neg1 = pk(-1.0f, -1.0f);
+    const float delta = tie_delta_kernel(uint32_t(ls >> 36));
+    const float cinv = inv_sqrt128();
+    const uint64_t cinv2 = pk(cinv, cinv);
 
-    for (size_t cbase = warp_global * 4; cbase < n_chunks; cbase += n_warps * 4) {
-        const size_t c = cbase + lane / LPG;
-        const bool valid = c < n_chunks;
-        float v[16];
+    // uniform trip count across the warp (the shuffles need every lane)
+    const size_t trips = (n_rows + sets_per_col - 1) / sets_per_col;
+    for (size_t t = 0; t < trips; ++t) {
+        const size_t row = k0 + t * sets_per_col;
+        const bool valid = active && row < n_rows;
+        const size_t off = row * row_stride + size_t(cc) * 128;
+        uint64_t P[8];
         if (valid) {
-            Vec16<float>::load(x + c * 128, lig, LPG, v);
-            if (smooth != nullptr) {
-                const float* sp = smooth + size_t(c % chunks_per_row) * 128;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 s4 = __ldg(reinterpret_cast<const float4*>(sp + (j * LPG + lig) * 4));
-                    v[4 * j + 0] = __fmul_rn(v[4 * j + 0], s4.x);     // basic_var.py:263 `.mul(s)`, fp32
-                    v[4 * j + 1] = __fmul_rn(v[4 * j + 1], s4.y);
-                    v[4 * j + 2] = __fmul_rn(v[4 * j + 2], s4.z);
-                    v[4 * j + 3] = __fmul_rn(v[4 * j + 3], s4.w);
-                }
+            for (int j = 0; j < 4; ++j) {
+                const uint4 u = ldg_stream(x + off + (j * LPG + lig) * 4);
+                P[2 * j] = (uint64_t(u.y) << 32) | u.x;
+                P[2 * j + 1] = (uint64_t(u.w) << 32) | u.z;
             }
         } else {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+            for (int i = 0; i < 8; ++i) P[i] = 0ull;
         }
+        // x * (s * sigma): basic_var.py:263 `.mul(s)` in fp32, then the sign row of Q
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(__float_as_uint(v[i]) ^ sgn[i]);
-        fwht16_regs(v);
-        fwht_lanes8(v, lig);
-        const float cinv = inv_sqrt128();
+        for (int i = 0; i < 8; ++i) P[i] = fmul2(P[i], ms[i]);
+        // index bit 0: inside a packed pair
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __half2float(__float2half_rn(v[i] * cinv));   // the fp16 GEMM output of the reference
-        if (valid && rotated != nullptr) store16<__half, 4>(rotated + c * 128, lig, LPG, v);
-        if constexpr (QUANT) sym_quant_tile<__half, FMT, TIE_KERNEL, LPG>(v);
-        if (valid) store16<__half, 4>(out + c * 128, lig, LPG, v);
+        for (int i = 0; i < 8; ++i) {
+            const F2 f = unpk(P[i]);
+            P[i] = pk(f.lo + f.hi, f.lo - f.hi);
+        }
+        // index bits 1, 5, 6: between packed registers (distance 1, 2, 4 in P[])
+#pragma unroll
+        for (int h = 1; h < 8; h <<= 1) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if ((i & h) == 0) {
+                    const uint64_t a = P[i], b = P[i + h];
+                    P[i] = fadd2(a, b);
+                    P[i + h] = ffma2(b, neg1, a);
+                }
+            }
+        }
+        // index bits 2, 3, 4: across the lanes of the set
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+            const float sg = (lig & o) ? -1.0f : 1.0f;
+            const uint64_t sg2 = pk(sg, sg);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const F2 f = unpk(P[i]);
+                const uint64_t q = pk(__shfl_xor_sync(0xffffffffu, f.lo, o), __shfl_xor_sync(0xffffffffu, f.hi, o));
+                P[i] = ffma2(P[i], sg2, q);            // upper lane: partner - mine ; lower lane: mine + partner (exact: * +-1)
+            }
+        }
+        // / fl32(sqrt(128)), rounded to fp16: the fp16 GEMM output of the reference
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = pack_h2_u64(fmul2(P[i], cinv2));
+        if (valid && rotated != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) stg_stream(rotated + off + (j * LPG + lig) * 4, make_uint2(w[2 * j], w[2 * j + 1]));
+        }
+        bool ok = true;
+        float s = 0.0f;
+        if constexpr (QUANT) ok = sym_quant_tile_h16<FMT, LPG, 8>(w, s, delta);
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) stg_stream(out + off + (j * LPG + lig) * 4, make_uint2(w[2 * j], w[2 * j + 1]));
+            // irregular scale (zero / subnormal / inf / NaN): `out` now holds this lane's rotated values;
+            // quantize them in place with the literal reference sequence
+            if (!ok) literal_sym_h16(out + off, out + off, lig, LPG, 4, 4, s, SymFmt<FMT>::GT);
+        }
     }
 }
 
@@ -158,18 +186,25 @@ extern "C" int fpq_transform_rotate_quant(const float* x, const float* smooth, c
     SignMask sm;
     for (int i = 0; i < 4; ++i) sm.w[i] = sign_bits_host[i];
     const int cpr = int(n_cols / 128);
-    const size_t n_chunks = n_rows * size_t(cpr);
-    const unsigned grid = grid_for(n_chunks, 32, 64);
+    // lane sets: one per (chunk column, row phase); enough to fill every SM's 2048 thread slots
+    const size_t max_sets = size_t(sm_count()) * 2048 / 8;
+    size_t sets_per_col = max_sets / size_t(cpr);
+    if (sets_per_col < 1) sets_per_col = 1;
+    if (sets_per_col > n_rows) sets_per_col = n_rows;
+    const size_t n_sets = sets_per_col * size_t(cpr);
+    const unsigned grid = unsigned((n_sets + 31) / 32);            // 32 lane sets per 256-thread block
     __half* o = static_cast<__half*>(out);
     __half* rot = static_cast<__half*>(rotated);
+#define FPQ_TRQ(F, Q) transform_rotate_quant_kernel<F, Q><<<grid, 256, 0, st>>>(x, smooth, sm, o, rot, n_rows, cpr, sets_per_col)
     switch (format) {
-        case -1: transform_rotate_quant_kernel<0, false><<<grid, 256, 0, st>>>(x, smooth, sm, o, rot, n_chunks, cpr); break;
-        case FPQ_FMT_E2M1: transform_rotate_quant_kernel<FPQ_FMT_E2M1, true><<<grid, 256, 0, st>>>(x, smooth, sm, o, rot, n_chunks, cpr); break;
-        case FPQ_FMT_E1M2: transform_rotate_quant_kernel<FPQ_FMT_E1M2, true><<<grid, 256, 0, st>>>(x, smooth, sm, o, rot, n_chunks, cpr); break;
-        case FPQ_FMT_E3M0: transform_rotate_quant_kernel<FPQ_FMT_E3M0, true><<<grid, 256, 0, st>>>(x, smooth, sm, o, rot, n_chunks, cpr); break;
-        case FPQ_FMT_E2M3: transform_rotate_quant_kernel<FPQ_FMT_E2M3, true><<<grid, 256, 0, st>>>(x, smooth, sm, o, rot, n_chunks, cpr); break;
-        default: transform_rotate_quant_kernel<FPQ_FMT_E3M2, true><<<grid, 256, 0, st>>>(x, smooth, sm, o, rot, n_chunks, cpr); break;
+        case -1: FPQ_TRQ(0, false); break;
+        case FPQ_FMT_E2M1: FPQ_TRQ(FPQ_FMT_E2M1, true); break;
+        case FPQ_FMT_E1M2: FPQ_TRQ(FPQ_FMT_E1M2, true); break;
+        case FPQ_FMT_E3M0: FPQ_TRQ(FPQ_FMT_E3M0, true); break;
+        case FPQ_FMT_E2M3: FPQ_TRQ(FPQ_FMT_E2M3, true); break;
+        default: FPQ_TRQ(FPQ_FMT_E3M2, true); break;
     }
+#undef FPQ_TRQ
     return finish_launch();
 }
 

@@ -146,7 +146,16 @@ static int launch_split(const void* x, void* out, size_t n_rows, size_t row_len,
     OutT* oo = static_cast<OutT*>(out);
     const bool pow2_group = (row_len == 128 || row_len == 64) &&
                             ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
-    if (pow2_group) {
+    bool launched = false;
+    if constexpr (sizeof(InT) == 2 && sizeof(OutT) == 2 && TIE == TIE_KERNEL) {
+        if (pow2_group && row_len == 128) {
+            const int rc0 = launch_split_h16(SPLIT, x, out, n_rows, flag, st);
+            if (rc0 != FPQ_OK) return rc0;
+            launched = true;
+        }
+    }
+    if (launched) {
+    } else if (pow2_group) {
         const int lpg = int(row_len / 16);
         const size_t groups_per_block = (256 / 32) * (32 / lpg);
         const unsigned grid = grid_for(n_rows, groups_per_block, 64);
@@ -156,7 +165,7 @@ static int launch_split(const void* x, void* out, size_t n_rows, size_t row_len,
         const unsigned grid = grid_for(n_rows, 1, 16);
         signsplit_row_kernel<InT, OutT, SPLIT, TIE><<<grid, 256, 0, st>>>(xi, oo, n_rows, row_len, flag);
     }
-    int rc = finish_launch();
+    int rc = launched ? FPQ_OK : finish_launch();
     if (rc != FPQ_OK || flag == nullptr) return rc;
     // all-NaN tensor after the reference's clamp: kernel rule -> +0 everywhere; argmin rule ->
     // (grid_neg[0] + grid_pos[0]) * 0 = -0 everywhere

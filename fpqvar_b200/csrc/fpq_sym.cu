@@ -97,6 +97,9 @@ static int launch_sym(const void* x, void* out, size_t n_rows, size_t row_len, i
     OutT* oo = static_cast<OutT*>(out);
     const bool pow2_group = (row_len == 128 || row_len == 64) &&
                             ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+    if constexpr (sizeof(InT) == 2 && sizeof(OutT) == 2 && TIE == TIE_KERNEL) {
+        if (pow2_group && row_len == 128 && !clamp3) return launch_sym_h16(FMT, x, out, n_rows, st);
+    }
     if (pow2_group) {
         const int lpg = int(row_len / 16);
         const size_t groups_per_block = (256 / 32) * (32 / lpg);

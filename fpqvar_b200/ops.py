@@ -181,5 +181,15 @@ def selftest_rounding(fmt_code: int, tie: str) -> tuple[int, int]:
     return int(r[0]), int(r[1]) & 0xFFFFFFFF
 
 
+def selftest_f16_flow(fmt_code: int) -> tuple[int, int]:
+    """(mismatch count, first mismatching (scale, x) index) of the packed fp16 element function vs the
+    literal reference sequence over every possible (x, scale) fp16 pair."""
+    res = torch.zeros(2, dtype=torch.int64, device="cuda")
+    rc = L.lib().fpq_selftest_f16_flow(fmt_code, res.data_ptr(), _stream())
+    L.check(rc, "fpq_selftest_f16_flow")
+    r = res.cpu()
+    return int(r[0]), int(r[1])
+
+
 def launch_count() -> int:
     return int(L.lib().fpq_launch_count())

@@ -167,6 +167,15 @@ FPQ_API int fpq_score_formats(const void *x, size_t n_rows, size_t row_len, int 
  */
 FPQ_API int fpq_selftest_rounding(int format, int tie_mode, unsigned long long *result, void *stream);
 
+/*
+ * Exhaustive self-check of the packed fp16 activation path (fp16 in, fp16 out, FPQ_TIE_KERNEL):
+ * for EVERY pair (x, scale) of fp16 values that can meet in a group with a normal scale, compare
+ * the division-free element function of the fast kernels with the literal reference sequence
+ * divide -> half -> scan -> multiply -> half (qu.py:320-329 / :432-451).  `format`: FPQ_FMT_* or
+ * 16+FPQ_SPLIT_*.  result as in fpq_selftest_rounding.
+ */
+FPQ_API int fpq_selftest_f16_flow(int format, unsigned long long *result, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

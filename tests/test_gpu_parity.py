@@ -44,6 +44,15 @@ def test_rounding_exhaustive(ops, code, tie):
     assert bad == 0, f"format code {code} tie {tie}: {bad} mismatches, first at bits 0x{first:08x}"
 
 
+@pytest.mark.parametrize("code", [0, 1, 2, 3, 4, 16, 17, 18])
+def test_f16_flow_exhaustive(ops, code):
+    """Packed fp16 fast path (division-free, magic-number rounding) == literal reference sequence
+    for every (x, scale) pair of fp16 values that can occur in a regular group."""
+    bad, first = ops.selftest_f16_flow(code)
+    assert bad == 0, (f"format code {code}: {bad} mismatches, first at scale bits 0x{0x0400 + (first >> 16):04x}, "
+                      f"x bits 0x{first & 0xffff:04x}")
+
+
 # ----------------------------------------------------------------------------------------
 # 2. golden vectors produced by the reference's own Python functions
 # ----------------------------------------------------------------------------------------
