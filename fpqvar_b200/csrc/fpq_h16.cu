@@ -5,6 +5,15 @@
 
 namespace fpq {
 
+// Software pipelining (two register tiles in ping-pong).  Measured on B200 (tools/kbench.py,
+// profiles/r1_kbench_variants.txt): +3 % for the symmetric kernel (42 -> 70 registers), -8 % for the
+// sign-split kernel (52 -> 84 registers, occupancy drops to 3 CTAs), so only the former uses it.
+#ifndef FPQ_SYM_PREFETCH
+#define FPQ_SYM_PREFETCH 1
+#endif
+#ifndef FPQ_SPLIT_PREFETCH
+#define FPQ_SPLIT_PREFETCH 0
+#endif
 constexpr int H16_LPG = 4;          // lanes per 128-group
 constexpr int H16_NV = 4;           // 16-byte vectors per lane and group: 32 halves = 16 packed words per lane
 constexpr int H16_NW = 4 * H16_NV;
@@ -32,23 +41,44 @@ __global__ void __launch_bounds__(256) fake_quant_group_h16_kernel(const __half*
     const size_t warp_global = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
     const float delta = tie_delta_kernel(uint32_t(warp_global >> 33));
-    for (size_t gbase = warp_global * H16_GPW; gbase < n_groups; gbase += n_warps * H16_GPW) {
+    const size_t stride = n_warps * H16_GPW;
+    auto load = [&](size_t gbase, uint32_t (&p)[H16_NW]) {
         const size_t g = gbase + lane / H16_LPG;
-        const bool valid = g < n_groups;
-        uint32_t p[H16_NW];
-        if (valid) {
+        if (g < n_groups) {
             load_tile_h16(x + g * 128, lig, p);
         } else {
 #pragma unroll
             for (int i = 0; i < H16_NW; ++i) p[i] = 0u;
         }
+    };
+    auto work = [&](size_t gbase, uint32_t (&p)[H16_NW]) {
+        const size_t g = gbase + lane / H16_LPG;
         float s;
         const bool ok = sym_quant_tile_h16<FMT, H16_LPG, H16_NW>(p, s, delta);
-        if (valid) {
+        if (g < n_groups) {
             if (ok) store_tile_h16(out + g * 128, lig, p);
             else literal_sym_h16(x + g * 128, out + g * 128, lig, H16_LPG, 8, H16_NV, s, SymFmt<FMT>::GT);
         }
+    };
+#if FPQ_SYM_PREFETCH
+    // two register tiles in ping-pong: the loads of the next trip are in flight while this one computes
+    uint32_t A[H16_NW], B[H16_NW];
+    size_t g0 = warp_global * H16_GPW;
+    if (g0 < n_groups) load(g0, A);
+    for (; g0 < n_groups; g0 += 2 * stride) {
+        const size_t g1 = g0 + stride, g2 = g1 + stride;
+        if (g1 < n_groups) load(g1, B);
+        work(g0, A);
+        if (g2 < n_groups) load(g2, A);
+        if (g1 < n_groups) work(g1, B);
     }
+#else
+    for (size_t gbase = warp_global * H16_GPW; gbase < n_groups; gbase += stride) {
+        uint32_t p[H16_NW];
+        load(gbase, p);
+        work(gbase, p);
+    }
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -93,10 +123,12 @@ __device__ __forceinline__ int split_quant_tile_h16(uint32_t (&p)[NW], float& sn
         sp = rnd_in<__half>(__fdiv_rn(ap, SF::POS::VMAX));
         return 1;
     }
-    const float rn = nbits == 0u ? 0.0f : rcp_rn_normal(sn);
+    constexpr float K = SplitScale<typename SF::NEG, typename SF::POS>::K;      // power of two: both products exact
+    const float rn = nbits == 0u ? 0.0f : rcp_rn_normal(sn) * K;
     const float rp = pbits == 0u ? 0.0f : rcp_rn_normal(sp);
+    const float snk = sn * (1.0f / K);
 #pragma unroll
-    for (int i = 0; i < NW; ++i) p[i] = split_pair_h16<typename SF::NEG, typename SF::POS>(p[i], rn, sn, rp, sp, delta);
+    for (int i = 0; i < NW; ++i) p[i] = split_pair_h16<typename SF::NEG, typename SF::POS>(p[i], rn, snk, rp, sp, delta);
     return 0;
 }
 
@@ -108,26 +140,46 @@ __global__ void __launch_bounds__(256) signsplit_group_h16_kernel(const __half* 
     const size_t warp_global = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
     const float delta = tie_delta_kernel(uint32_t(warp_global >> 33));
-    for (size_t gbase = warp_global * H16_GPW; gbase < n_groups; gbase += n_warps * H16_GPW) {
+    const size_t stride = n_warps * H16_GPW;
+    auto load = [&](size_t gbase, uint32_t (&p)[H16_NW]) {
         const size_t g = gbase + lane / H16_LPG;
-        const bool valid = g < n_groups;
-        uint32_t p[H16_NW];
-        if (valid) {
+        if (g < n_groups) {
             load_tile_h16(x + g * 128, lig, p);
         } else {
 #pragma unroll
             for (int i = 0; i < H16_NW; ++i) p[i] = 0u;
         }
+    };
+    auto work = [&](size_t gbase, uint32_t (&p)[H16_NW]) {
+        using SF = SplitH16<SPLIT>;
+        const size_t g = gbase + lane / H16_LPG;
         float sn, sp;
         const int rc = split_quant_tile_h16<SPLIT, H16_LPG, H16_NW>(p, sn, sp, delta);
         if (rc == 2 && nan_flag != nullptr) atomicOr(nan_flag, 1u);
-        if (valid) {
-            using SF = SplitH16<SPLIT>;
+        if (g < n_groups) {
             if (rc == 0) store_tile_h16(out + g * 128, lig, p);
             else if (rc == 1) literal_split_h16(x + g * 128, out + g * 128, lig, H16_LPG, 8, H16_NV, sn, sp, SF::GT_N, SF::GT_P);
             else literal_split_nan_group_h16(x + g * 128, out + g * 128, lig, H16_LPG, 8, H16_NV, SF::NEG::VMAX, SF::POS::VMAX, SF::GT_N, SF::GT_P);
         }
+    };
+#if FPQ_SPLIT_PREFETCH
+    uint32_t A[H16_NW], B[H16_NW];
+    size_t g0 = warp_global * H16_GPW;
+    if (g0 < n_groups) load(g0, A);
+    for (; g0 < n_groups; g0 += 2 * stride) {
+        const size_t g1 = g0 + stride, g2 = g1 + stride;
+        if (g1 < n_groups) load(g1, B);
+        work(g0, A);
+        if (g2 < n_groups) load(g2, A);
+        if (g1 < n_groups) work(g1, B);
     }
+#else
+    for (size_t gbase = warp_global * H16_GPW; gbase < n_groups; gbase += stride) {
+        uint32_t p[H16_NW];
+        load(gbase, p);
+        work(gbase, p);
+    }
+#endif
 }
 
 static unsigned grid_h16(size_t n_groups) {
@@ -199,7 +251,8 @@ __global__ void selftest_f16_flow_kernel(unsigned long long* result) {
             // the other side's scale does not influence this element: use the same s on both sides
             const bool pos = x > 0.0f;
             if (pos ? !pair_possible<typename SF::POS>(x, s) : !pair_possible<typename SF::NEG>(x, s)) continue;
-            got = split_pair_h16<typename SF::NEG, typename SF::POS>(uint32_t(xb), r, s, r, s, delta) & 0xffffu;
+            constexpr float K = SplitScale<typename SF::NEG, typename SF::POS>::K;
+            got = split_pair_h16<typename SF::NEG, typename SF::POS>(uint32_t(xb), r * K, s * (1.0f / K), r, s, delta) & 0xffffu;
             const float xn = (x <= 0.0f) ? x : 0.0f, xp = pos ? x : 0.0f;
             const float qn = scan_kernel_rule(rnd_in<__half>(__fdiv_rn(xn, s)), c_grids[SF::GT_N].v, c_grids[SF::GT_N].k);
             const float qp = scan_kernel_rule(rnd_in<__half>(__fdiv_rn(xp, s)), c_grids[SF::GT_P].v, c_grids[SF::GT_P].k);

@@ -13,6 +13,10 @@
 // product of a 2-point butterfly over every index bit, in any order (here: 0, 1, 5, 6, 2, 3, 4).
 #include "fpq_h16.cuh"
 
+#ifndef FPQ_ROT_V2
+#define FPQ_ROT_V2 1
+#endif
+
 namespace fpq {
 
 struct SignMask { uint32_t w[4]; };    // bit e of the 128-bit mask set  <=>  sigma[e] = +1
@@ -128,6 +132,101 @@ __global__ void __launch_bounds__(256) transform_rotate_quant_kernel(const float
     }
 }
 
+// Activation kernel, second layout (default): 4 lanes per chunk, 32 values (16 packed registers) per
+// lane: vector j (0..7) of lane l holds elements 16j + 4l + k, so only index bits 2 and 3 cross lanes
+// (2 SHFL per element instead of 3, and half the per-group scalar work per element).  The
+// smooth*sign multipliers of the whole row live in shared memory (n_cols floats), which frees the
+// registers the first layout spent on them and lets the chunks be walked with a plain grid stride.
+template <int FMT, bool QUANT>
+__global__ void __launch_bounds__(256) transform_rotate_quant_v2_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
+                                                                        SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
+                                                                        size_t n_chunks, int cpr) {
+    // [cpr][ROW]: smooth[c] * sigma[c % 128]; rows padded by 16 floats so that the two lane sets of a
+    // quarter-warp (adjacent chunk columns) read from different banks
+    extern __shared__ float s_mul[];
+    constexpr int LPG = 4, NV = 8, ROW = 144;
+    for (int c = threadIdx.x; c < cpr * 128; c += blockDim.x) {
+        const int e = c & 127;
+        const float sv = smooth != nullptr ? __ldg(smooth + c) : 1.0f;
+        s_mul[(c >> 7) * ROW + e] = ((sm.w[e >> 5] >> (e & 31)) & 1u) ? sv : -sv;      // sign flips are exact: (x*s)*sigma == x*(s*sigma)
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const int lig = lane % LPG;
+    const size_t warp_global = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
+    const uint64_t neg1 = pk(-1.0f, -1.0f);
+    const float delta = tie_delta_kernel(uint32_t(warp_global >> 33));
+    const float cinv = inv_sqrt128();
+    const uint64_t cinv2 = pk(cinv, cinv);
+    const float sg1 = (lig & 1) ? -1.0f : 1.0f, sg2 = (lig & 2) ? -1.0f : 1.0f;
+
+    for (size_t cbase = warp_global * 8; cbase < n_chunks; cbase += n_warps * 8) {
+        const size_t c = cbase + lane / LPG;
+        const bool valid = c < n_chunks;
+        const size_t off = c * 128;
+        const float* mrow = s_mul + (valid ? int(c % size_t(cpr)) : 0) * ROW;
+        uint64_t P[16];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            uint4 u = make_uint4(0u, 0u, 0u, 0u);
+            if (valid) u = ldg_stream(x + off + (j * LPG + lig) * 4);
+            const float4 m4 = *reinterpret_cast<const float4*>(mrow + (j * LPG + lig) * 4);
+            // x * (s * sigma): basic_var.py:263 `.mul(s)` in fp32, then the sign row of Q
+            P[2 * j] = fmul2((uint64_t(u.y) << 32) | u.x, pk(m4.x, m4.y));
+            P[2 * j + 1] = fmul2((uint64_t(u.w) << 32) | u.z, pk(m4.z, m4.w));
+        }
+        // index bit 0: inside a packed pair
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const F2 f = unpk(P[i]);
+            P[i] = pk(f.lo + f.hi, f.lo - f.hi);
+        }
+        // index bits 1, 4, 5, 6: between packed registers (distance 1, 2, 4, 8 in P[])
+#pragma unroll
+        for (int h = 1; h < 16; h <<= 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if ((i & h) == 0) {
+                    const uint64_t a = P[i], b = P[i + h];
+                    P[i] = fadd2(a, b);
+                    P[i + h] = ffma2(b, neg1, a);
+                }
+            }
+        }
+        // index bits 2, 3: across the 4 lanes of the set
+#pragma unroll
+        for (int o = 1; o < 4; o <<= 1) {
+            const float sg = o == 1 ? sg1 : sg2;
+            const uint64_t sgp = pk(sg, sg);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const F2 f = unpk(P[i]);
+                const uint64_t q = pk(__shfl_xor_sync(0xffffffffu, f.lo, o), __shfl_xor_sync(0xffffffffu, f.hi, o));
+                P[i] = ffma2(P[i], sgp, q);            // upper lane: partner - mine ; lower lane: mine + partner (exact: * +-1)
+            }
+        }
+        // / fl32(sqrt(128)), rounded to fp16: the fp16 GEMM output of the reference
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = pack_h2_u64(fmul2(P[i], cinv2));
+        if (valid && rotated != nullptr) {
+#pragma unroll
+            for (int j = 0; j < NV; ++j) stg_stream(rotated + off + (j * LPG + lig) * 4, make_uint2(w[2 * j], w[2 * j + 1]));
+        }
+        bool ok = true;
+        float s = 0.0f;
+        if constexpr (QUANT) ok = sym_quant_tile_h16<FMT, LPG, 16>(w, s, delta);
+        if (valid) {
+#pragma unroll
+            for (int j = 0; j < NV; ++j) stg_stream(out + off + (j * LPG + lig) * 4, make_uint2(w[2 * j], w[2 * j + 1]));
+            // irregular scale (zero / subnormal / inf / NaN): `out` now holds this lane's rotated values;
+            // quantize them in place with the literal reference sequence
+            if (!ok) literal_sym_h16(out + off, out + off, lig, LPG, 4, NV, s, SymFmt<FMT>::GT);
+        }
+    }
+}
+
 // Weight side: one warp per (row, chunk); lane l holds elements 4l..4l+3 in fp64.
 __global__ void __launch_bounds__(256) transform_rotate_weight_kernel(const float* __restrict__ w, const float* __restrict__ smooth,
                                                                       SignMask sm, float* __restrict__ w_out, size_t n_chunks,
@@ -186,15 +285,37 @@ extern "C" int fpq_transform_rotate_quant(const float* x, const float* smooth, c
     SignMask sm;
     for (int i = 0; i < 4; ++i) sm.w[i] = sign_bits_host[i];
     const int cpr = int(n_cols / 128);
-    // lane sets: one per (chunk column, row phase); enough to fill every SM's 2048 thread slots
+    __half* o = static_cast<__half*>(out);
+    __half* rot = static_cast<__half*>(rotated);
+#if FPQ_ROT_V2
+    if (size_t(cpr) * 144 * sizeof(float) <= 48 * 1024) {
+        const size_t n_chunks = n_rows * size_t(cpr);
+        const unsigned grid = grid_for(n_chunks, 64, 4);              // 8 warps x 8 chunks per block and trip
+        const size_t smem = size_t(cpr) * 144 * sizeof(float);
+#define FPQ_TRQ2(F, Q) transform_rotate_quant_v2_kernel<F, Q><<<grid, 256, smem, st>>>(x, smooth, sm, o, rot, n_chunks, cpr)
+        switch (format) {
+            case -1: FPQ_TRQ2(0, false); break;
+            case FPQ_FMT_E2M1: FPQ_TRQ2(FPQ_FMT_E2M1, true); break;
+            case FPQ_FMT_E1M2: FPQ_TRQ2(FPQ_FMT_E1M2, true); break;
+            case FPQ_FMT_E3M0: FPQ_TRQ2(FPQ_FMT_E3M0, true); break;
+            case FPQ_FMT_E2M3: FPQ_TRQ2(FPQ_FMT_E2M3, true); break;
+            default: FPQ_TRQ2(FPQ_FMT_E3M2, true); break;
+        }
+#undef FPQ_TRQ2
+        return finish_launch();
+    }
+#endif
+    // first layout: lane sets, one per (chunk column, row phase); enough to fill every SM's 2048 thread slots
     const size_t max_sets = size_t(sm_count()) * 2048 / 8;
     size_t sets_per_col = max_sets / size_t(cpr);
     if (sets_per_col < 1) sets_per_col = 1;
     if (sets_per_col > n_rows) sets_per_col = n_rows;
+    // equal work per set: with `trips` passes over the rows, use just enough sets that every pass is full
+    // (25600 rows on 2525 sets would run 10 full passes and one at 10 %)
+    const size_t trips = (n_rows + sets_per_col - 1) / sets_per_col;
+    sets_per_col = (n_rows + trips - 1) / trips;
     const size_t n_sets = sets_per_col * size_t(cpr);
     const unsigned grid = unsigned((n_sets + 31) / 32);            // 32 lane sets per 256-thread block
-    __half* o = static_cast<__half*>(out);
-    __half* rot = static_cast<__half*>(rotated);
 #define FPQ_TRQ(F, Q) transform_rotate_quant_kernel<F, Q><<<grid, 256, 0, st>>>(x, smooth, sm, o, rot, n_rows, cpr, sets_per_col)
     switch (format) {
         case -1: FPQ_TRQ(0, false); break;

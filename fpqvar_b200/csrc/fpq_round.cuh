@@ -27,6 +27,7 @@ template <int EMIN_, int M_, int VNUM_, int VDEN_>
 struct HalfGrid {
     static constexpr int EMIN = EMIN_;
     static constexpr int M = M_;
+    static constexpr int VNUM = VNUM_, VDEN = VDEN_;
     static constexpr float VMAX = float(VNUM_) / float(VDEN_);
     static constexpr uint32_t LOW = (1u << (23 - M_)) - 1u;    // discarded mantissa bits
     static constexpr uint32_t HALF = 1u << (22 - M_);          // half of the kept LSB

@@ -1,0 +1,100 @@
+"""Format search (search/search_fp4_format.py, search/search_fp6_format.py) on the B200 kernels.
+
+Two scoring levels, as in the reference:
+  * tensor level  mean((x - x_q)^2) per candidate format (compute_quant_error, search_fp4_format.py:472-476,
+    loops :840-893) -- `score_tensor_formats`: ONE kernel reads x once and scores every candidate.
+  * output level  mean((x W^T - x_q W_q^T)^2) over the calibration activations per (weight format,
+    activation format) pair (loop :781-836) -- `search_layer`: fused quantizers + library GEMMs; y_fp is
+    computed once per activation instead of once per pair.
+Candidates are independent, so `search_layers` shards (layer, weight-format) units over ranks and
+gathers the small loss table at the end -- the only collective.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Sequence
+
+import torch
+
+from . import ops
+from .var_workload import shard_units
+
+FP4_FORMATS = ("e1m2", "e2m1", "e3m0")                       # search_fp4_format.py:797
+FP6_FORMATS = ("e2m3", "e3m2")                               # search_fp6_format.py
+_SPLIT = ("e1m2_neg_e2m1_pos", "int_neg_e2m3_pos", "afpq_e2m1")
+
+
+def fp4_quant(x, format):
+    """search_fp4_format.py:544-553."""
+    if format not in FP4_FORMATS:
+        raise NotImplementedError
+    return ops.fake_quant(x, format, 128, "kernel")
+
+
+def fp6_quant(x, format):
+    """search_fp6_format.py:547-554 (per-token, always fp16)."""
+    if format not in FP6_FORMATS:
+        raise NotImplementedError
+    return ops.fake_quant(x, format, None, "kernel", out_dtype=torch.float16)
+
+
+def quantize(x, fmt: str, per: str = "group"):
+    if fmt in _SPLIT:
+        return ops.fake_quant_signsplit(x, fmt, 128 if per == "group" else None, "kernel")
+    out_dtype = torch.float16 if fmt in FP6_FORMATS else None
+    return ops.fake_quant(x, fmt, 128 if per == "group" else None, "kernel", out_dtype=out_dtype)
+
+
+def compute_quant_error(x_fp, x_quant):
+    """search_fp4_format.py:472-476."""
+    return torch.mean((x_fp - x_quant) ** 2)
+
+
+def score_tensor_formats(x: torch.Tensor, formats: Sequence[str], tie: str = "kernel") -> torch.Tensor:
+    """mean((x - fake_quant(x, f))^2) for every f in `formats`, x read once; float64 [len(formats)]."""
+    return ops.score_formats(x, list(formats), tie) / x.numel()
+
+
+def search_layer(weight: torch.Tensor, activations: Sequence[torch.Tensor], weight_formats: Sequence[str] = FP4_FORMATS,
+                 act_formats: Sequence[str] = FP4_FORMATS, per: str = "group") -> torch.Tensor:
+    """Loss table [len(weight_formats), len(act_formats)] of search_fp4_format.py:798-816:
+    loss[w, a] = mean_j mean((x_j W^T - q_a(x_j) q_w(W)^T)^2)."""
+    wq = [quantize(weight, wf, per).to(weight.dtype) for wf in weight_formats]
+    loss = torch.zeros(len(weight_formats), len(act_formats), dtype=torch.float64, device=weight.device)
+    for x in activations:
+        y_fp = torch.matmul(x, weight.T)
+        for ai, af in enumerate(act_formats):
+            xq = quantize(x, af, per).to(x.dtype)
+            for wi in range(len(weight_formats)):
+                loss[wi, ai] += compute_quant_error(y_fp, torch.matmul(xq, wq[wi].T)).double()
+    return loss / max(1, len(activations))
+
+
+def best_formats(loss: torch.Tensor, weight_formats: Sequence[str], act_formats: Sequence[str]) -> Dict[str, object]:
+    """argmin in the reference's iteration order (weight format outer, activation format inner; the first
+    strictly smaller loss wins, search_fp4_format.py:818-821)."""
+    flat = loss.reshape(-1).cpu()
+    best, best_i = float("inf"), 0
+    for i, v in enumerate(flat.tolist()):
+        if v < best:
+            best, best_i = v, i
+    wi, ai = divmod(best_i, len(act_formats))
+    return {"weight_format": weight_formats[wi], "activation_format": act_formats[ai], "loss": best}
+
+
+def search_layers(layers: Sequence[dict], weight_formats: Sequence[str] = FP4_FORMATS, act_formats: Sequence[str] = FP4_FORMATS,
+                  rank: int = 0, world: int = 1, group=None, layer_fn=None) -> Optional[List[Dict[str, object]]]:
+    """`layers`: [{"name": ..., "weight": W, "activations": [x_j]}].  Units (layer, weight format) are dealt
+    round-robin to ranks; every rank fills its rows of the [layers, w, a] table and the tables are
+    summed at the end (each entry is written by exactly one rank).  Returns the per-layer optimum on
+    every rank.  `layer_fn` (default `search_layer`) scores one (layer, [weight format]) unit."""
+    layer_fn = layer_fn or search_layer
+    table = torch.zeros(len(layers), len(weight_formats), len(act_formats), dtype=torch.float64,
+                        device=layers[0]["weight"].device if layers else "cpu")
+    units = [(li, wi) for li in range(len(layers)) for wi in range(len(weight_formats))]
+    for u in shard_units(len(units), rank, world):
+        li, wi = units[u]
+        table[li, wi] = layer_fn(layers[li]["weight"], layers[li]["activations"], [weight_formats[wi]], act_formats)[0]
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(table, group=group)
+    return [dict(name=layers[li].get("name", li), **best_formats(table[li], weight_formats, act_formats)) for li in range(len(layers))]

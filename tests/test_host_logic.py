@@ -1,0 +1,235 @@
+"""CPU: host-side logic -- C-ABI surface, workload model, sharding (incl. a 2-rank gloo run), the
+drop-in API surface and its error behaviour.  No kernel is launched here."""
+import ctypes
+import inspect
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+# ---------------------------------------------------------------------------------------------
+# C ABI: the library loads and exports every symbol include/fpq_b200.h declares
+# ---------------------------------------------------------------------------------------------
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "fpq_b200.h")).read()
+    return sorted(set(re.findall(r"FPQ_API[^;(]*?\b(fpq_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from fpqvar_b200 import _lib
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.fail(f"{_lib.LIB_PATH} missing: run __graft_entry__.build()")
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    declared = _declared_symbols()
+    assert len(declared) >= 11
+    for name in declared:
+        assert hasattr(handle, name), f"{name} declared in include/fpq_b200.h but not exported"
+    # the ctypes signature table covers exactly the declared entry points
+    assert sorted(_lib.SIGNATURES) == declared
+    assert handle.fpq_version is not None
+    _lib.lib().fpq_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in _lib.lib().fpq_version()
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "fpqvar_b200")
+    for dirpath, _d, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f"{f} imports the oracle"
+                assert "liboracle" not in src, f"{f} links the oracle"
+
+
+def test_cpu_tensors_are_rejected_loudly():
+    from fpqvar_b200 import ops, quant_utils as Q
+    from fpqvar_b200._lib import FpqError
+    x = torch.zeros(4, 128)
+    for fn in (lambda: ops.fake_quant(x, "e2m1"), lambda: Q.fp_quant_e2_per_group_cuda(x, 4, 128),
+               lambda: Q.fp6_quant_e2m3_per_token_cuda(x, 6), lambda: ops.score_formats(x, ["e2m1"]),
+               lambda: Q.fp_quant_e1m2_neg_e2m1_pos_per_group_cuda(x, 4)):
+        with pytest.raises(FpqError, match="no CPU fallback"):
+            fn()
+
+
+# ---------------------------------------------------------------------------------------------
+# workload model
+# ---------------------------------------------------------------------------------------------
+def test_var_workload_shapes_and_bytes():
+    from fpqvar_b200.var_workload import WORKLOADS
+    d30 = WORKLOADS["var_d30_w4a4_rot"]
+    assert d30.width == 1920 and d30.stage_rows() == [100, 400, 900, 1600, 2500, 3600, 6400, 10000, 16900, 25600]
+    calls = d30.calls()
+    assert len(calls) == 10 * 30 * 4
+    assert {c.site for c in calls} == {"mat_qkv", "proj", "fc1", "fc2"}
+    # 548 M activation elements per image: 68000 rows x 7C x 30 blocks / 50 images
+    assert d30.elems_per_pass() == 68000 * 7 * 1920 * 30
+    assert d30.bytes_per_pass() == 68000 * 30 * 32 * 1920          # 6C + 4C + 6C + 16C bytes per token and block
+    d16 = WORKLOADS["var_d16_w4a4"]
+    assert d16.stage_rows()[-1] == 32768 and d16.width == 1024
+    assert all(c.op == "group" for c in d16.calls())
+    d36 = WORKLOADS["var_d36_w6a6_rot"]
+    assert d36.stage_rows() == [20, 80, 180, 320, 720, 1620, 3380, 6480, 11520, 20480] and d36.width == 2304
+    assert all(c.elems % 128 == 0 for w in WORKLOADS.values() for c in w.calls())
+
+
+def test_shard_units_partition():
+    from fpqvar_b200.var_workload import shard_units
+    for world in (1, 2, 3, 8):
+        seen = sorted(u for r in range(world) for u in shard_units(37, r, world))
+        assert seen == list(range(37))
+    with pytest.raises(ValueError):
+        shard_units(4, 2, 2)
+
+
+# ---------------------------------------------------------------------------------------------
+# rotation host utilities
+# ---------------------------------------------------------------------------------------------
+def test_block_hadamard_matrix_matches_reference_fixture(golden):
+    from fpqvar_b200 import rotation_utils as R
+    from fpqvar_b200.hotpath import SIGN_BITS_SEED42_128
+    q = R.block_random_hadamard_matrix(256, 128, "cpu", 42)
+    assert q.dtype == torch.float64
+    assert np.array_equal(q.numpy().view(np.uint64), golden["rot/q256"].view(np.uint64))
+    s = R.sign_vector(128, 42)
+    assert "".join("1" if v > 0 else "0" for v in s.tolist()) == SIGN_BITS_SEED42_128
+    bits = R.block_sign_bits(128, 42)
+    for i, c in enumerate(SIGN_BITS_SEED42_128):
+        assert ((bits[i >> 5] >> (i & 31)) & 1) == int(c)
+    # like the reference, building the matrix leaves the global RNG seeded with `seed`
+    R.block_random_hadamard_matrix(128, 128, "cpu", 7)
+    a = torch.rand(3)
+    torch.manual_seed(7)
+    torch.randint(low=0, high=2, size=(128,))
+    assert torch.equal(a, torch.rand(3))
+    assert torch.equal(R.block_random_hadamard_matrix(256, 128, "cpu", 42, force_identity=True), torch.eye(256, dtype=torch.float64))
+
+
+# ---------------------------------------------------------------------------------------------
+# drop-in API surface
+# ---------------------------------------------------------------------------------------------
+REFERENCE_SIGNATURES = {     # models_fp_quant_transform_rotate/quant_utils.py (+ models_fp_quant for the last two)
+    "quantize_to_nearest_grid": ["x", "quant_grid"],
+    "fp_quant_e1_per_token": ["x", "n_bits"], "fp_quant_e2_per_token": ["x", "n_bits"], "fp_quant_e3_per_token": ["x", "n_bits"],
+    "fp_quant_e1_per_group": ["x", "n_bits", "group_size"], "fp_quant_e2_per_group": ["x", "n_bits", "group_size"],
+    "fp_quant_e3_per_group": ["x", "n_bits", "group_size"],
+    "fp_quant_e1_per_group_cuda": ["x", "n_bits", "group_size"], "fp_quant_e2_per_group_cuda": ["x", "n_bits", "group_size"],
+    "fp_quant_e3_per_group_cuda": ["x", "n_bits", "group_size"],
+    "fp_quant_e1m2_neg_e2m1_pos_per_group": ["x", "n_bits", "group_size", "clipping_strength"],
+    "fp_quant_e1m2_neg_e2m1_pos_per_group_cuda": ["x", "n_bits", "group_size", "clipping_strength"],
+    "fp6_quant_e2m3_per_token_cuda": ["x", "n_bits"], "fp6_quant_e3m2_per_token_cuda": ["x", "n_bits"],
+    "fp6_quant_e2m3_per_group_cuda": ["x", "n_bits", "group_size"], "fp6_quant_e3m2_per_group_cuda": ["x", "n_bits", "group_size"],
+    "fp6_quant_int_neg_e2m3_pos_per_group_cuda": ["x", "n_bits", "group_size"],
+    "fp6_quant_int_neg_e2m3_pos_per_token_cuda": ["x", "n_bits"],
+    "fp4_afpq_per_group_cuda": ["x", "n_bits", "group_size", "clipping_strength"],
+    "fp_neg_reverse_quant_per_group_cuda": ["x", "n_bits", "group_size"],
+}
+CTOR = ["in_features", "out_features", "bias", "act_quant", "quantize_output", "w_bit", "a_bit", "act_quant_sym",
+        "fc2_act_log2_quant", "activation_fp_quant", "weight_fp_quant", "act_fp_type", "weight_fp_type"]
+FROM_FLOAT = ["module", "weight_quant", "act_quant", "quantize_output", "w_bit", "a_bit", "act_quant_sym", "fc2_act_log2_quant",
+              "activation_fp_quant", "weight_fp_quant", "act_fp_type", "weight_fp_type"]
+QUANTIZE_VAR = ["model", "weight_quant", "act_quant", "quantize_bmm_input", "w_bit", "a_bit", "kv_bit", "act_quant_sym",
+                "fc2_act_log2_quant", "quant_kv", "activation_fp_quant", "weight_fp_quant", "act_fp_type", "weight_fp_type", "fc2_fp_type"]
+
+
+def test_quant_utils_signatures_match_the_reference():
+    from fpqvar_b200 import quant_utils as Q
+    for name, params in REFERENCE_SIGNATURES.items():
+        assert list(inspect.signature(getattr(Q, name)).parameters) == params, name
+    for cls in (Q.QuantizedLinear, Q.QuantizedLinear_fc2):
+        assert list(inspect.signature(cls.__init__).parameters)[1:] == CTOR
+        assert list(inspect.signature(cls.from_float).parameters) == FROM_FLOAT
+    assert list(inspect.signature(Q.quantize_VAR).parameters) == QUANTIZE_VAR
+    assert inspect.signature(Q.fp_quant_e2_per_group_cuda).parameters["group_size"].default == 128
+
+
+def test_quantized_linear_dispatch_and_errors():
+    from fpqvar_b200 import quant_utils as Q
+    m = Q.QuantizedLinear(256, 128, True, act_quant="per_group", a_bit=4, activation_fp_quant=True, act_fp_type="fp_e2")
+    assert m.act_quant.func is Q.fp_quant_e2_per_group_cuda and m.act_quant.keywords == {"n_bits": 4, "group_size": 128}
+    assert m.act_quant_name == "per_group" and m.output_quant_name == "None"
+    assert m.weight.dtype == torch.float16 and tuple(m.weight.shape) == (128, 256) and tuple(m.bias.shape) == (1, 128)
+    assert "weight" in dict(m.named_buffers()) and not list(m.parameters())
+    m2 = Q.QuantizedLinear_fc2(256, 128, False, act_quant="per_group", a_bit=4, activation_fp_quant=True, act_fp_type="fp_e1m2_neg_e2m1_pos")
+    assert m2.act_quant.func is Q.fp_quant_e1m2_neg_e2m1_pos_per_group_cuda and m2.bias is None
+    m3 = Q.QuantizedLinear(64, 64, act_quant="per_token", a_bit=6, activation_fp_quant=True, act_fp_type="fp6_e3m2", quantize_output=True)
+    assert m3.act_quant.func is Q.fp6_quant_e3m2_per_token_cuda and m3.output_quant is m3.act_quant
+    with pytest.raises(ValueError, match="Unsupported fp_type"):
+        Q.QuantizedLinear(8, 8, act_quant="per_group", activation_fp_quant=True, act_fp_type="fp_e1m2_neg_e2m1_pos")   # fc2-only type
+    with pytest.raises(ValueError, match="Unsupported fp_type"):
+        Q.QuantizedLinear_fc2(8, 8, act_quant="per_token", activation_fp_quant=True, act_fp_type="nope")
+    with pytest.raises(ValueError, match="Invalid act_quant"):
+        Q.QuantizedLinear(8, 8, act_quant="per_row")
+    with pytest.raises(AssertionError):
+        Q.fp_quant_e2_per_group_cuda(torch.zeros(128), 6)
+    with pytest.raises(AssertionError):
+        Q.fp6_quant_e2m3_per_token_cuda(torch.zeros(128), 4)
+    # integer baselines are out of scope and say so
+    with pytest.raises(NotImplementedError, match="outside the FP"):
+        Q.QuantizedLinear(8, 8, act_quant="per_token", a_bit=8)(torch.zeros(1, 8))
+
+
+def test_dropin_install_registers_reference_module_names():
+    import sys
+    import fpqvar_b200.dropin as dropin
+    saved = {k: sys.modules.get(k) for k in ("quant_cuda", "quant_utils", "rotation_utils", "transform_model_utils")}
+    try:
+        dropin.install()
+        import quant_cuda
+        assert callable(quant_cuda.quant) and list(inspect.signature(quant_cuda.quant).parameters) == ["x", "y"]
+        import quant_utils
+        assert quant_utils.QuantizedLinear.__name__ == "QuantizedLinear"
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-rank search sharding over gloo (world_size 2), CPU stand-in scorer
+# ---------------------------------------------------------------------------------------------
+def _fake_layer_fn(weight, activations, weight_formats, act_formats):
+    # deterministic stand-in for search_layer: depends on the layer, the weight format and the act format
+    base = float(weight.sum())
+    row = [base + 10.0 * len(wf) + sum(ord(c) for c in wf) * 0.01 + ai + float(activations[0].sum()) for wf in weight_formats
+           for ai, _ in enumerate(act_formats)]
+    return torch.tensor(row, dtype=torch.float64).view(len(weight_formats), len(act_formats))
+
+
+def _make_layers():
+    g = torch.Generator().manual_seed(0)
+    return [{"name": f"blk{i}", "weight": torch.randn(4, 4, generator=g), "activations": [torch.randn(2, 4, generator=g)]} for i in range(5)]
+
+
+def _gloo_worker(rank, world, port, out):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from fpqvar_b200 import search
+    res = search.search_layers(_make_layers(), rank=rank, world=world, layer_fn=_fake_layer_fn)
+    if rank == 0:
+        torch.save(res, out)
+    dist.destroy_process_group()
+
+
+def test_search_sharding_two_ranks_gloo(tmp_path):
+    import socket
+    import torch.multiprocessing as mp
+    from fpqvar_b200 import search
+    want = search.search_layers(_make_layers(), layer_fn=_fake_layer_fn)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = str(tmp_path / "res.pt")
+    mp.spawn(_gloo_worker, args=(2, port, out), nprocs=2, join=True)
+    got = torch.load(out)
+    assert got == want
+    assert all(r["weight_format"] in search.FP4_FORMATS for r in got)
