@@ -1,7 +1,7 @@
 // libfpq_b200 -- packed fp16 -> fp16 kernels (kernel tie rule, groups of 128): the activation
 // quantizers of the hot path (reference rows a2, a3 of SURVEY.md section 8) at low instruction
 // count, see fpq_h16.cuh.  Part of the C ABI of include/fpq_b200.h; no torch types here.
-#include "fpq_h16.cuh"
+#include "fpq_stream.cuh"
 
 namespace fpq {
 
@@ -132,6 +132,28 @@ __device__ __forceinline__ int split_quant_tile_h16(uint32_t (&p)[NW], float& sn
     return 0;
 }
 
+// Whole-tensor clip of the reference (qu.py:421-422) when the tensor holds a NaN: every output becomes
+// +0.  workspace = {flag, ticket}: every CTA takes a ticket when its stores are done; the last one looks
+// at the flag, rewrites `out` if it is set (rare, slow, correct) and leaves the workspace zeroed for the
+// next call -- no second launch, no memset between calls.
+__device__ __forceinline__ void poison_epilogue(__half* __restrict__ out, size_t n, unsigned* __restrict__ ws) {
+    __shared__ unsigned s_last;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(ws + 1, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (*reinterpret_cast<volatile unsigned*>(ws) != 0u) {
+        for (size_t i = threadIdx.x; i < n / 8; i += blockDim.x) reinterpret_cast<uint4*>(out)[i] = make_uint4(0u, 0u, 0u, 0u);
+        for (size_t i = (n / 8) * 8 + threadIdx.x; i < n; i += blockDim.x) out[i] = __ushort_as_half(0);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { ws[0] = 0u; ws[1] = 0u; }
+}
+
 template <int SPLIT>
 __global__ void __launch_bounds__(256) signsplit_group_h16_kernel(const __half* __restrict__ x, __half* __restrict__ out, size_t n_groups,
                                                                   unsigned* __restrict__ nan_flag) {
@@ -180,6 +202,126 @@ __global__ void __launch_bounds__(256) signsplit_group_h16_kernel(const __half* 
         work(gbase, p);
     }
 #endif
+    if (nan_flag != nullptr) poison_epilogue(out, n_groups * 128, nan_flag);
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA-staged variants (fpq_stream.cuh): tiles of 64 groups (16 KB), 4 stages, 8 consumer warps x 8 groups
+// ------------------------------------------------------------------------------------------
+constexpr int ST_TILE_GROUPS = ST_CONSUMER_WARPS * H16_GPW;
+constexpr int ST_TILE_BYTES_H16 = ST_TILE_GROUPS * 256;
+using StreamSmemH16 = StreamSmem<ST_TILE_BYTES_H16, 4>;
+
+// Consumer side of one tile: lane set gi (of 8 in the warp) owns group warp*8+gi of the tile.  Vector
+// order is swizzled by the parity of gi so that the two lane sets of a quarter-warp (LDS.128 phase) read
+// different 64-byte halves of the 128-byte bank window: conflict-free.
+__device__ __forceinline__ int h16_vec(int j, int gi, int lig) { return ((j ^ (gi & 1)) * H16_LPG + lig); }
+
+__device__ __forceinline__ void lds_tile_h16(const unsigned char* gsm, int gi, int lig, bool valid, uint32_t (&p)[H16_NW]) {
+#pragma unroll
+    for (int j = 0; j < H16_NV; ++j) {
+        uint4 u = make_uint4(0u, 0u, 0u, 0u);
+        if (valid) u = *reinterpret_cast<const uint4*>(gsm + h16_vec(j, gi, lig) * 16);
+        p[4 * j] = u.x; p[4 * j + 1] = u.y; p[4 * j + 2] = u.z; p[4 * j + 3] = u.w;
+    }
+}
+__device__ __forceinline__ void stg_tile_h16_swz(__half* base, int gi, int lig, const uint32_t (&p)[H16_NW]) {
+#pragma unroll
+    for (int j = 0; j < H16_NV; ++j) stg_stream(base + h16_vec(j, gi, lig) * 8, make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]));
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(ST_THREADS) fake_quant_group_h16_tma_kernel(const __half* __restrict__ x, __half* __restrict__ out, size_t n_groups) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    StreamSmemH16& sm = *reinterpret_cast<StreamSmemH16*>(smem_raw);
+    stream_init(sm);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t n_tiles = (n_groups + ST_TILE_GROUPS - 1) / ST_TILE_GROUPS;
+    if (warp == ST_CONSUMER_WARPS) {
+        if (lane == 0)
+            stream_producer(sm, n_tiles, [&](size_t t) { return x + t * ST_TILE_GROUPS * 128; },
+                            [&](size_t t) { const size_t g = n_groups - t * ST_TILE_GROUPS; return uint32_t((g < ST_TILE_GROUPS ? g : ST_TILE_GROUPS) * 256); });
+        return;
+    }
+    const int gi = lane / H16_LPG, lig = lane % H16_LPG;
+    const float delta = tie_delta_kernel(uint32_t((size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 38));
+    uint32_t k = 0;
+    for (size_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
+        const uint32_t s = k % StreamSmemH16::NSTAGES, ph = (k / StreamSmemH16::NSTAGES) & 1u;
+        const size_t g = t * ST_TILE_GROUPS + warp * H16_GPW + gi;
+        const bool valid = g < n_groups;
+        mbar_wait(&sm.full[s], ph);
+        uint32_t p[H16_NW];
+        lds_tile_h16(sm.tile[s] + (warp * H16_GPW + gi) * 256, gi, lig, valid, p);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[s]);                  // the stage can be refilled while we compute
+        float sc;
+        const bool ok = sym_quant_tile_h16<FMT, H16_LPG, H16_NW>(p, sc, delta);
+        if (valid) {
+            if (ok) stg_tile_h16_swz(out + g * 128, gi, lig, p);
+            else literal_sym_h16(x + g * 128, out + g * 128, lig, H16_LPG, 8, H16_NV, sc, SymFmt<FMT>::GT);
+        }
+    }
+}
+
+template <int SPLIT>
+__global__ void __launch_bounds__(ST_THREADS) signsplit_group_h16_tma_kernel(const __half* __restrict__ x, __half* __restrict__ out, size_t n_groups,
+                                                                             unsigned* __restrict__ nan_flag) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    StreamSmemH16& sm = *reinterpret_cast<StreamSmemH16*>(smem_raw);
+    stream_init(sm);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const size_t n_tiles = (n_groups + ST_TILE_GROUPS - 1) / ST_TILE_GROUPS;
+    if (warp == ST_CONSUMER_WARPS) {
+        if (lane == 0)
+            stream_producer(sm, n_tiles, [&](size_t t) { return x + t * ST_TILE_GROUPS * 128; },
+                            [&](size_t t) { const size_t g = n_groups - t * ST_TILE_GROUPS; return uint32_t((g < ST_TILE_GROUPS ? g : ST_TILE_GROUPS) * 256); });
+        return;
+    }
+    using SF = SplitH16<SPLIT>;
+    const int gi = lane / H16_LPG, lig = lane % H16_LPG;
+    const float delta = tie_delta_kernel(uint32_t((size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 38));
+    uint32_t k = 0;
+    for (size_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
+        const uint32_t s = k % StreamSmemH16::NSTAGES, ph = (k / StreamSmemH16::NSTAGES) & 1u;
+        const size_t g = t * ST_TILE_GROUPS + warp * H16_GPW + gi;
+        const bool valid = g < n_groups;
+        mbar_wait(&sm.full[s], ph);
+        uint32_t p[H16_NW];
+        lds_tile_h16(sm.tile[s] + (warp * H16_GPW + gi) * 256, gi, lig, valid, p);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[s]);
+        float sn, sp;
+        const int rc = split_quant_tile_h16<SPLIT, H16_LPG, H16_NW>(p, sn, sp, delta);
+        if (rc == 2 && nan_flag != nullptr) atomicOr(nan_flag, 1u);
+        if (valid) {
+            if (rc == 0) stg_tile_h16_swz(out + g * 128, gi, lig, p);
+            else if (rc == 1) literal_split_h16(x + g * 128, out + g * 128, lig, H16_LPG, 8, H16_NV, sn, sp, SF::GT_N, SF::GT_P);
+            else literal_split_nan_group_h16(x + g * 128, out + g * 128, lig, H16_LPG, 8, H16_NV, SF::NEG::VMAX, SF::POS::VMAX, SF::GT_N, SF::GT_P);
+        }
+    }
+}
+
+// Measured on B200 (tools/kbench.py, profiles/r1_kbench.txt, kbench_6): the TMA-staged variants are
+// parity-green but SLOWER than the LDG kernels back to back (sign-split 6.06 vs 6.29 TB/s burst, 5.32 vs
+// 5.66 sustained; symmetric 5.57 vs 6.30), although a single cold launch under ncu runs at the same
+// 6.2 TB/s (127 us): 3 CTAs x 8 consumer warps per SM and a static tile round-robin leave the SMs idle
+// 16 % of the cycles.  Kept behind this switch for the next round (dynamic tile scheduler, 2 CTAs x 16
+// warps); off by default.
+#ifndef FPQ_H16_TMA
+#define FPQ_H16_TMA 0
+#endif
+// below this many groups the plain LDG kernels are used (fewer than ~2 tiles per SM: nothing to pipeline)
+constexpr size_t ST_MIN_GROUPS = size_t(ST_TILE_GROUPS) * 148 * 2;
+
+template <class K>
+static bool tma_smem_ok(K kernel) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(StreamSmemH16))) == cudaSuccess;
+}
+static unsigned grid_tma(size_t n_groups) {
+    const size_t n_tiles = (n_groups + ST_TILE_GROUPS - 1) / ST_TILE_GROUPS;
+    const size_t cap = size_t(sm_count()) * 3;                    // 3 CTAs x 64 KB of stages per SM
+    return unsigned(n_tiles < cap ? n_tiles : cap);
 }
 
 static unsigned grid_h16(size_t n_groups) {
@@ -190,6 +332,24 @@ static unsigned grid_h16(size_t n_groups) {
 int launch_sym_h16(int format, const void* x, void* out, size_t n_groups, cudaStream_t st) {
     const __half* xi = static_cast<const __half*>(x);
     __half* oo = static_cast<__half*>(out);
+#if FPQ_H16_TMA
+    if (n_groups >= ST_MIN_GROUPS) {
+        const unsigned g = grid_tma(n_groups);
+        const size_t smem = sizeof(StreamSmemH16);
+#define FPQ_SYM_TMA(F) { static const bool ok = tma_smem_ok(fake_quant_group_h16_tma_kernel<F>); if (!ok) return FPQ_ERR_CUDA; \
+                         fake_quant_group_h16_tma_kernel<F><<<g, ST_THREADS, smem, st>>>(xi, oo, n_groups); }
+        switch (format) {
+            case FPQ_FMT_E2M1: FPQ_SYM_TMA(FPQ_FMT_E2M1) break;
+            case FPQ_FMT_E1M2: FPQ_SYM_TMA(FPQ_FMT_E1M2) break;
+            case FPQ_FMT_E3M0: FPQ_SYM_TMA(FPQ_FMT_E3M0) break;
+            case FPQ_FMT_E2M3: FPQ_SYM_TMA(FPQ_FMT_E2M3) break;
+            case FPQ_FMT_E3M2: FPQ_SYM_TMA(FPQ_FMT_E3M2) break;
+            default: return FPQ_ERR_ARG;
+        }
+#undef FPQ_SYM_TMA
+        return finish_launch();
+    }
+#endif
     const unsigned grid = grid_h16(n_groups);
     switch (format) {
         case FPQ_FMT_E2M1: fake_quant_group_h16_kernel<FPQ_FMT_E2M1><<<grid, 256, 0, st>>>(xi, oo, n_groups); break;
@@ -205,6 +365,22 @@ int launch_sym_h16(int format, const void* x, void* out, size_t n_groups, cudaSt
 int launch_split_h16(int split, const void* x, void* out, size_t n_groups, unsigned* nan_flag, cudaStream_t st) {
     const __half* xi = static_cast<const __half*>(x);
     __half* oo = static_cast<__half*>(out);
+#if FPQ_H16_TMA
+    if (n_groups >= ST_MIN_GROUPS && nan_flag == nullptr) {       // the whole-tensor clip epilogue lives in the LDG kernel only
+        const unsigned g = grid_tma(n_groups);
+        const size_t smem = sizeof(StreamSmemH16);
+#define FPQ_SPLIT_TMA(F) { static const bool ok = tma_smem_ok(signsplit_group_h16_tma_kernel<F>); if (!ok) return FPQ_ERR_CUDA; \
+                           signsplit_group_h16_tma_kernel<F><<<g, ST_THREADS, smem, st>>>(xi, oo, n_groups, nan_flag); }
+        switch (split) {
+            case FPQ_SPLIT_E1M2NEG_E2M1POS: FPQ_SPLIT_TMA(FPQ_SPLIT_E1M2NEG_E2M1POS) break;
+            case FPQ_SPLIT_INTNEG_E2M3POS: FPQ_SPLIT_TMA(FPQ_SPLIT_INTNEG_E2M3POS) break;
+            case FPQ_SPLIT_AFPQ_E2M1: FPQ_SPLIT_TMA(FPQ_SPLIT_AFPQ_E2M1) break;
+            default: return FPQ_ERR_ARG;
+        }
+#undef FPQ_SPLIT_TMA
+        return finish_launch();
+    }
+#endif
     const unsigned grid = grid_h16(n_groups);
     switch (split) {
         case FPQ_SPLIT_E1M2NEG_E2M1POS: signsplit_group_h16_kernel<FPQ_SPLIT_E1M2NEG_E2M1POS><<<grid, 256, 0, st>>>(xi, oo, n_groups, nan_flag); break;

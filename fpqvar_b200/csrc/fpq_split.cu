@@ -135,9 +135,12 @@ __global__ void __launch_bounds__(256) signsplit_row_kernel(const InT* __restric
 // where() halves become 0, every scale 0, every quotient 0/0 -> q = 0 (kernel rule) or
 // grid[0] (argmin rule), and the output is (+0)*0 + (+0)*0 = +0, resp. (g0n + g0p) * 0 = -0.
 template <typename OutT>
-__global__ void poison_fill_kernel(OutT* __restrict__ out, size_t n, const unsigned* __restrict__ nan_flag, float fill) {
-    if (*nan_flag == 0u) return;
-    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) store_elem(out + i, fill);
+__global__ void poison_fill_kernel(OutT* __restrict__ out, size_t n, unsigned* __restrict__ ws, float fill) {
+    if (*reinterpret_cast<volatile unsigned*>(ws) != 0u)
+        for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) store_elem(out + i, fill);
+    // leave the workspace {flag, ticket} zeroed for the next call: the last CTA to get here resets it
+    __syncthreads();
+    if (threadIdx.x == 0 && atomicAdd(ws + 1, 1u) == gridDim.x - 1) { ws[0] = 0u; ws[1] = 0u; }
 }
 
 template <typename InT, typename OutT, int SPLIT, int TIE>
@@ -165,7 +168,8 @@ static int launch_split(const void* x, void* out, size_t n_rows, size_t row_len,
         const unsigned grid = grid_for(n_rows, 1, 16);
         signsplit_row_kernel<InT, OutT, SPLIT, TIE><<<grid, 256, 0, st>>>(xi, oo, n_rows, row_len, flag);
     }
-    int rc = launched ? FPQ_OK : finish_launch();
+    if (launched) return FPQ_OK;                      // the packed kernels handle the whole-tensor clip in their epilogue
+    int rc = finish_launch();
     if (rc != FPQ_OK || flag == nullptr) return rc;
     // all-NaN tensor after the reference's clamp: kernel rule -> +0 everywhere; argmin rule ->
     // (grid_neg[0] + grid_pos[0]) * 0 = -0 everywhere

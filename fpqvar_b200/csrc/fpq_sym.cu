@@ -1,6 +1,6 @@
 // libfpq_b200 -- symmetric fake-quant kernels (reference rows a2, a4, a5, a6 of SURVEY.md section 8)
 // Part of the C ABI of include/fpq_b200.h; no torch types here.
-#include "fpq_common.cuh"
+#include "fpq_h16.cuh"
 
 namespace fpq {
 
@@ -91,6 +91,135 @@ __global__ void __launch_bounds__(256) fake_quant_row_kernel(const InT* __restri
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Per-row fake quant with the row resident in registers: one CTA per row, V 16-byte vectors per
+// thread, ONE pass over HBM (load -> block absmax -> quantize -> store).  Covers the per_token /
+// per_channel shapes of the FP6 README configs (rows of 1920 .. 9216) when the row is 16-byte
+// aligned and fits V <= 4 vectors x 1024 threads.
+// ------------------------------------------------------------------------------------------
+template <typename InT, typename OutT, int FMT, int TIE, int V>
+__global__ void __launch_bounds__(1024) fake_quant_row_reg_kernel(const InT* __restrict__ x, OutT* __restrict__ out, size_t n_rows,
+                                                                  int row_vecs, int clamp3) {
+    using HG = typename SymFmt<FMT>::HG;
+    constexpr int VEC = 16 / sizeof(InT);
+    __shared__ float red[32];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const float delta = tie_delta_kernel(uint32_t((size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 40));
+    auto load_row = [&](size_t row, uint4 (&dst)[V]) {
+        const InT* xr = x + row * size_t(row_vecs) * VEC;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const int vi = tid + k * nt;
+            dst[k] = (row < n_rows && vi < row_vecs) ? ldg_stream(xr + size_t(vi) * VEC) : make_uint4(0u, 0u, 0u, 0u);
+        }
+    };
+    uint4 u[V], un[V];
+    load_row(blockIdx.x, un);
+    for (size_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        OutT* orow = out + row * size_t(row_vecs) * VEC;
+#pragma unroll
+        for (int k = 0; k < V; ++k) u[k] = un[k];
+        load_row(row + gridDim.x, un);                 // next row's loads fly while this one reduces and computes
+        // absmax over the row (NaN propagates, as torch's abs().max())
+        float a = 0.0f;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if constexpr (sizeof(InT) == 2) {
+                    float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+                    if (clamp3) { f.x = clamp3_keep_nan(f.x); f.y = clamp3_keep_nan(f.y); }
+                    a = fmax_nan(a, fmax_nan(fabsf(f.x), fabsf(f.y)));
+                } else {
+                    float f = __uint_as_float(w[q]);
+                    if (clamp3) f = clamp3_keep_nan(f);
+                    a = fmax_nan(a, fabsf(f));
+                }
+            }
+        }
+        a = block_max_nan(a, red);
+        const float s = rnd_in<InT>(__fdiv_rn(a, HG::VMAX));                     // quant_utils.py:505 / :239
+        const bool regular = scale_regular<InT>(s);
+        const float r = regular ? __frcp_rn(s) : 0.0f;
+        const GridTable& gt = c_grids[SymFmt<FMT>::GT];
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const int vi = tid + k * nt;
+            if (vi >= row_vecs) continue;
+            const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+            if constexpr (sizeof(InT) == 2 && sizeof(OutT) == 2 && TIE == TIE_KERNEL) {
+                uint32_t o[4];
+                if (regular && !clamp3) {
+                    const uint64_t r2 = pk(r, r), s2 = pk(s, s);
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) o[q] = sym_pair_h16<HG>(w[q], r2, s2, delta);
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+                        if (clamp3) { f.x = clamp3_keep_nan(f.x); f.y = clamp3_keep_nan(f.y); }
+                        const float q0 = regular ? quant_elem_fast<InT, HG, TIE>(f.x, s, r) : quant_elem_literal<InT, TIE>(f.x, s, gt);
+                        const float q1 = regular ? quant_elem_fast<InT, HG, TIE>(f.y, s, r) : quant_elem_literal<InT, TIE>(f.y, s, gt);
+                        o[q] = pack_h2(q0 * s, q1 * s);
+                    }
+                }
+                stg_stream(orow + size_t(vi) * VEC, make_uint4(o[0], o[1], o[2], o[3]));
+            } else {
+                float f[VEC];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if constexpr (sizeof(InT) == 2) {
+                        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+                        f[2 * q] = t.x; f[2 * q + 1] = t.y;
+                    } else {
+                        f[q] = __uint_as_float(w[q]);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < VEC; ++e) {
+                    float t = f[e];
+                    if (clamp3) t = clamp3_keep_nan(t);
+                    f[e] = (regular ? quant_elem_fast<InT, HG, TIE>(t, s, r) : quant_elem_literal<InT, TIE>(t, s, gt)) * s;
+                }
+                OutT* po = orow + size_t(vi) * VEC;
+                if constexpr (sizeof(OutT) == 4) {
+#pragma unroll
+                    for (int e = 0; e < VEC; e += 4)
+                        stg_stream(po + e, make_uint4(__float_as_uint(f[e]), __float_as_uint(f[e + 1]), __float_as_uint(f[e + 2]), __float_as_uint(f[e + 3])));
+                } else if constexpr (VEC == 8) {
+                    stg_stream(po, make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7])));
+                } else {
+                    stg_stream(po, make_uint2(pack_h2(f[0], f[1]), pack_h2(f[2], f[3])));
+                }
+            }
+        }
+        // `red` is reused by the next row's reduction: block_max_nan starts with a __syncthreads
+    }
+}
+
+template <typename InT, typename OutT, int FMT, int TIE>
+static bool launch_row_reg(const InT* xi, OutT* oo, size_t n_rows, size_t row_len, int clamp3, cudaStream_t st) {
+    constexpr int VEC = 16 / sizeof(InT);
+    if (row_len % VEC != 0 || row_len < 256) return false;
+    if ((reinterpret_cast<uintptr_t>(xi) & 15) || (reinterpret_cast<uintptr_t>(oo) & 15)) return false;
+    if ((row_len * sizeof(OutT)) % 16 != 0 && sizeof(OutT) < sizeof(InT)) {
+        if ((row_len * sizeof(OutT)) % 8 != 0) return false;
+    }
+    const size_t row_vecs = row_len / VEC;
+    if (row_vecs > 4096) return false;
+    const int v = row_vecs <= 1024 ? 1 : (row_vecs <= 2048 ? 2 : 4);
+    int threads = int((row_vecs + v - 1) / v);
+    threads = (threads + 31) / 32 * 32;
+    const int ctas_per_sm = 2048 / threads > 0 ? 2048 / threads : 1;
+    const size_t cap = size_t(sm_count()) * ctas_per_sm;
+    const unsigned grid = unsigned(n_rows < cap ? n_rows : cap);
+    if (v == 1) fake_quant_row_reg_kernel<InT, OutT, FMT, TIE, 1><<<grid, threads, 0, st>>>(xi, oo, n_rows, int(row_vecs), clamp3);
+    else if (v == 2) fake_quant_row_reg_kernel<InT, OutT, FMT, TIE, 2><<<grid, threads, 0, st>>>(xi, oo, n_rows, int(row_vecs), clamp3);
+    else fake_quant_row_reg_kernel<InT, OutT, FMT, TIE, 4><<<grid, threads, 0, st>>>(xi, oo, n_rows, int(row_vecs), clamp3);
+    return true;
+}
+
 template <typename InT, typename OutT, int FMT, int TIE>
 static int launch_sym(const void* x, void* out, size_t n_rows, size_t row_len, int clamp3, cudaStream_t st) {
     const InT* xi = static_cast<const InT*>(x);
@@ -106,7 +235,7 @@ static int launch_sym(const void* x, void* out, size_t n_rows, size_t row_len, i
         const unsigned grid = grid_for(n_rows, groups_per_block, 64);
         if (lpg == 8) fake_quant_group_kernel<InT, OutT, FMT, TIE, 8><<<grid, 256, 0, st>>>(xi, oo, n_rows, clamp3);
         else fake_quant_group_kernel<InT, OutT, FMT, TIE, 4><<<grid, 256, 0, st>>>(xi, oo, n_rows, clamp3);
-    } else {
+    } else if (!launch_row_reg<InT, OutT, FMT, TIE>(xi, oo, n_rows, row_len, clamp3, st)) {
         const unsigned grid = grid_for(n_rows, 1, 16);
         fake_quant_row_kernel<InT, OutT, FMT, TIE><<<grid, 256, 0, st>>>(xi, oo, n_rows, row_len, clamp3);
     }

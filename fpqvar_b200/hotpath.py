@@ -1,9 +1,9 @@
 """Replaying the hot path of a VAR pass over the C ABI (include/fpq_b200.h).
 
 Two ways in:
-  * :class:`DeviceReplay` -- inputs already resident in HBM; every call of the pass is one
-    (sign-split with the reference's whole-tensor clip: two) kernel launch on a caller-chosen
-    stream, with no allocation, so the whole pass can be captured in a CUDA graph.
+  * :class:`DeviceReplay` -- inputs already resident in HBM; every call of the pass is one kernel
+    launch on a caller-chosen stream, with no allocation, so the whole pass can be captured in a
+    CUDA graph.
   * :class:`HostPipeline` -- HOST buffers in, HOST buffers out: pinned-memory H2D copy, kernel,
     D2H copy, triple-stream pipelined with two staging slots so copies overlap compute.
 
@@ -48,7 +48,7 @@ class DeviceReplay:
         self.sign_bits = sign_bits if sign_bits is not None else seed42_sign_bits()
         self.global_clip = global_clip
         # NaN flag of the sign-split whole-tensor clip (fpq_fake_quant_signsplit, FPQ_FLAG_GLOBAL_CLIP)
-        self.flag = torch.zeros(1, dtype=torch.int32, device=device) if global_clip else None
+        self.flag = torch.zeros(2, dtype=torch.int32, device=device) if global_clip else None      # {flag, ticket}
 
     def launch(self, call: Call, in_ptr: int, out_ptr: int, stream: int) -> None:
         lib = self.lib

@@ -60,6 +60,18 @@ def fake_quant(x: torch.Tensor, fmt: str, row_len: Optional[int] = 128, tie: str
     return out
 
 
+_WS = {}
+
+
+def _clip_workspace(device: torch.device) -> torch.Tensor:
+    """{flag, ticket} of FPQ_FLAG_GLOBAL_CLIP, one per (device, stream): the kernels leave it zeroed."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WS.get(key)
+    if ws is None:
+        ws = _WS[key] = torch.zeros(2, dtype=torch.int32, device=device)
+    return ws
+
+
 def fake_quant_signsplit(x: torch.Tensor, split_fmt: str, row_len: Optional[int] = 128, tie: str = "kernel",
                          global_clip: bool = False, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """Sign-split fake-quant (fpq_fake_quant_signsplit).  ``global_clip=True`` reproduces the
@@ -71,7 +83,7 @@ def fake_quant_signsplit(x: torch.Tensor, split_fmt: str, row_len: Optional[int]
         out_dtype = x.dtype if tie == "kernel" else torch.float32
     out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
     n_rows, rl = _rows(x, row_len)
-    ws = torch.zeros(1, dtype=torch.int32, device=x.device) if global_clip else None
+    ws = _clip_workspace(x.device) if global_clip else None
     with torch.cuda.device_of(x):
         rc = L.lib().fpq_fake_quant_signsplit(x.data_ptr(), out.data_ptr(), n_rows, rl, _dt(x, "signsplit"), _dt(out, "signsplit"),
                                               L.SPLIT[split_fmt], L.TIE[tie], L.FLAG_GLOBAL_CLIP if global_clip else 0,

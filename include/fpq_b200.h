@@ -114,10 +114,12 @@ FPQ_API int fpq_fake_quant(const void *x, void *out, size_t n_rows, size_t row_l
 /*
  * Sign-split fake-quant (fc2 inputs): x<=0 and x>0 get their own grid and their own absmax
  * scale per row; out = q_neg*s_neg + q_pos*s_pos.  Arguments as fpq_fake_quant;
- * `split_format` is FPQ_SPLIT_*.  With FPQ_FLAG_GLOBAL_CLIP, `workspace` must point to 4
- * zero-initialised bytes of device memory; the kernel raises it when the tensor holds a NaN
- * and a second (tiny) launch then rewrites `out` as the reference would (all +0).  Without
- * the flag a NaN element is treated as 0 locally (qu.py:428-429) and `workspace` is unused.
+ * `split_format` is FPQ_SPLIT_*.  With FPQ_FLAG_GLOBAL_CLIP, `workspace` must point to 8 bytes
+ * of device memory that were zero when first used ({flag, ticket}); the kernel raises the flag
+ * when the tensor holds a NaN, the last CTA to finish then rewrites `out` as the reference would
+ * (all +0) and zeroes the workspace again, so one workspace serves any number of calls on one
+ * stream without a memset in between.  Without the flag a NaN element is treated as 0 locally
+ * (qu.py:428-429) and `workspace` is unused.
  */
 FPQ_API int fpq_fake_quant_signsplit(const void *x, void *out, size_t n_rows, size_t row_len,
                              int in_dtype, int out_dtype, int split_format, int tie_mode,

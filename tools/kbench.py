@@ -52,7 +52,7 @@ def timeit(fn, nbytes):
 def main():
     rows = int(os.environ.get("ROWS", "25600"))
     C = 1920
-    flag = torch.zeros(2, dtype=torch.int32, device=dev)
+    flag = torch.zeros(2, dtype=torch.int32, device=dev)      # {flag, ticket}
     sb = seed42_sign_bits()
     smooth = torch.exp(torch.rand(C, device=dev) * 2 - 1)
     class R(dict):
@@ -73,7 +73,20 @@ def main():
         res["group e2m1 f16 (4C)"] = timeit(lambda i: lib.fpq_fake_quant(x[i].data_ptr(), o[i].data_ptr(), n // 128, 128, 1, 1, 0, 0, 0, st), n * 4)
     if want("group e2m3 f16 (4C)"):
         res["group e2m3 f16 (4C)"] = timeit(lambda i: lib.fpq_fake_quant(x[i].data_ptr(), o[i].data_ptr(), n // 128, 128, 1, 1, 3, 0, 0, st), n * 4)
-    del x, o
+    # per-token / per-channel rows (FP6 README configs: rows of 9216 = 4C of VAR-d36)
+    nr = (rows * 4 * C) // 9216
+    xr = [t.view(-1)[: nr * 9216] for t in x]
+    orr = [t.view(-1)[: nr * 9216] for t in o]
+    if want("rows e2m3 f16 (per_token 9216)"):
+        res["rows e2m3 f16 (per_token 9216)"] = timeit(lambda i: lib.fpq_fake_quant(xr[i].data_ptr(), orr[i].data_ptr(), nr, 9216, 1, 1, 3, 0, 0, st), nr * 9216 * 4)
+    xk = [t.view(-1, 64) for t in x]
+    if want("rows e2m3 f16 (KV rows of 64)"):
+        res["rows e2m3 f16 (KV rows of 64)"] = timeit(lambda i: lib.fpq_fake_quant(x[i].data_ptr(), o[i].data_ptr(), n // 64, 64, 1, 1, 3, 0, 0, st), n * 4)
+    if want("score 3 fmts f16 (read-only)"):
+        res["score 3 fmts f16 (read-only)"] = timeit(lambda i: ops.score_formats(x[i], ["e2m1", "e1m2", "e3m0"]), n * 2)
+    if want("score 4 fmts f16 incl split"):
+        res["score 4 fmts f16 incl split"] = timeit(lambda i: ops.score_formats(x[i], ["e2m1", "e1m2", "e3m0", "e1m2_neg_e2m1_pos"]), n * 2)
+    del x, o, xr, orr, xk
     # rotate + quant (mat_qkv / fc1 input), 4 row-blocks to get a comparable byte volume
     r4 = rows * 4
     xf = [torch.randn(r4, C, device=dev) for _ in range(NBUF)]
