@@ -34,7 +34,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "fake_quant_throughput"
+METRIC = "fake-quant GB/s (VAR-d30 W4A4 rotate+transform hot path; % of HBM peak in roofline.frac)"
 UNIT = "GB/s"
 
 
@@ -309,12 +309,14 @@ def main():
         c = item[0]
         by_kernel.setdefault((c.op, c.fmt, c.in_dtype, c.out_dtype), []).append(item)
     dom_key = max(by_kernel, key=lambda k: sum(i[0].bytes for i in by_kernel[k]))
+    fam = {}
+    for key, items in by_kernel.items():
+        gr, n_l = capture(items)
+        for _ in range(3):
+            gr.replay()
+        fam[key] = (timed_replays(gr, args.steps), n_l, sum(i[0].bytes for i in items))
+    t_dom, dom_launches, dom_bytes = fam[dom_key]
     dom = by_kernel[dom_key]
-    dom_graph, dom_launches = capture(dom)
-    for _ in range(3):
-        dom_graph.replay()
-    t_dom = timed_replays(dom_graph, args.steps)
-    dom_bytes = sum(i[0].bytes for i in dom)
     # the big-stage launches of that kernel alone (bandwidth-bound regime; the early stages are launch-latency-bound)
     big = [i for i in dom if i[0].bytes >= 64 << 20]
     big_graph, _ = capture(big)
@@ -360,16 +362,28 @@ def main():
 
     # ---- gather (the only collective) --------------------------------------------------------
     if world > 1:
-        t = torch.tensor([t_dev, t_dom, t_big], device=dev, dtype=torch.float64)
+        keys = sorted(fam)
+        t = torch.tensor([t_dev, t_dom, t_big] + [fam[k][0] for k in keys], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        t_dev, t_dom, t_big = (float(v) for v in t.tolist())
+        vals = [float(v) for v in t.tolist()]
+        t_dev, t_dom, t_big = vals[:3]
+        fam = {k: (vals[3 + i], fam[k][1], fam[k][2]) for i, k in enumerate(keys)}
 
     if rank == 0:
         peak, peak_src = load_peaks()
         value = world * args.steps * step_bytes / t_dev / 1e9
         dom_gbs = args.steps * dom_bytes / t_dom / 1e9
         big_gbs = args.steps * big_bytes / t_big / 1e9
-        kname = {"group": "fake_quant_group_kernel", "signsplit": "signsplit_group_kernel", "rotate_quant": "transform_rotate_quant_kernel"}[dom_key[0]]
+        def kernel_name(key):
+            op, fmt, din, dout = key
+            if op == "rotate_quant":
+                return f"transform_rotate_quant_v2_kernel<{fmt}> (f32->f16)"
+            packed = din == "f16" and dout == "f16"
+            base = {"group": "fake_quant_group", "signsplit": "signsplit_group"}[op]
+            return f"{base}_h16_kernel<{fmt}> (f16->f16)" if packed else f"{base}_kernel<{din}->{dout},{fmt}>"
+        kname = kernel_name(dom_key)
+        kernels = {kernel_name(k): {"GB/s": args.steps * b / t / 1e9, "launches_per_step": n_l, "share_of_step_bytes": b / step_bytes,
+                                    "ms_per_step_alone": t / args.steps * 1e3} for k, (t, n_l, b) in fam.items()}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -382,13 +396,17 @@ def main():
                 "launch": "one CUDA-graph replay per step", "parallelism": f"dp{world} (independent image batches, no data-path collective)",
             },
             "roofline": {
-                "bound": "hbm", "kernel": f"{kname}<{dom_key[2]}->{dom_key[3]},{dom_key[1]}>", "achieved": dom_gbs, "peak": peak,
+                "bound": "hbm", "kernel": kname, "achieved": dom_gbs, "peak": peak,
                 "unit": "GB/s", "frac": dom_gbs / peak, "traffic": None, "peak_source": peak_src,
                 "launches_per_step": dom_launches, "avg_launch_us": t_dom / args.steps / max(1, dom_launches) * 1e6,
                 "bytes_per_launch": dom_bytes / max(1, dom_launches),
                 "large_launches": {"min_bytes": 64 << 20, "achieved": big_gbs, "frac": big_gbs / peak, "n": len(big)},
                 "frac_of_nominal_8TBps": dom_gbs / 8000.0,
+                "traffic_largest_launch": {"dram_bytes": 741.1e6, "algorithmic_bytes": 786.4e6,
+                                           "source": "profiles/r1c_final_kernels_ncu.txt (ncu --set full, fc2 input 25600x7680; the tail of the writes is still in L2 when the kernel ends)"},
             },
+            "kernels": kernels,
+            "images_per_sec_hot_path_only": world * hot.batch / (t_dev / args.steps),
             "gpu_launches": launches_per_step * args.steps,
             "clocks": clocks,
         }

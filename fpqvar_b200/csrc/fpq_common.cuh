@@ -64,6 +64,34 @@ static inline unsigned grid_for(size_t work_items, size_t items_per_block, int b
 }
 
 // ------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  The activation kernels are short (2-130 us) and a VAR pass
+// issues 1200 of them back to back; a kernel launched with the programmatic-serialization attribute may
+// have its CTAs scheduled while the previous kernel in the stream is still draining, and runs its
+// prologue (index math, shared-memory tables built from PARAMETER tensors) until pdl_wait(), which
+// returns once the previous kernel has completed and its writes are visible.  Nothing that a previous
+// kernel may have produced (x) is read, and nothing is written, before pdl_wait().
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+bool pdl_enabled();      // fpq_grid.cu: on unless FPQ_NO_PDL is set in the environment
+
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ------------------------------------------------------------------------------------------
 // small device helpers
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float fmax_nan(float a, float b) {

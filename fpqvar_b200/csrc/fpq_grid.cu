@@ -1,5 +1,6 @@
 // libfpq_b200 -- quant_cuda.quant compatibility entry (row a1), the exhaustive rounding self-test, and launch bookkeeping
 // Part of the C ABI of include/fpq_b200.h; no torch types here.
+#include <cstdlib>
 #include "fpq_common.cuh"
 
 namespace fpq {
@@ -89,6 +90,11 @@ int finish_launch() {
     ++t_launches;
     if (e != cudaSuccess) { t_last_err = e; return FPQ_ERR_CUDA; }
     return FPQ_OK;
+}
+
+bool pdl_enabled() {
+    static const bool on = (getenv("FPQ_NO_PDL") == nullptr);
+    return on;
 }
 
 int sm_count() {

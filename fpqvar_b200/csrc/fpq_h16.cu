@@ -36,12 +36,14 @@ __device__ __forceinline__ void store_tile_h16(__half* base, int lig, const uint
 
 template <int FMT>
 __global__ void __launch_bounds__(256) fake_quant_group_h16_kernel(const __half* __restrict__ x, __half* __restrict__ out, size_t n_groups) {
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int lig = lane % H16_LPG;
     const size_t warp_global = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
     const float delta = tie_delta_kernel(uint32_t(warp_global >> 33));
     const size_t stride = n_warps * H16_GPW;
+    pdl_wait();
     auto load = [&](size_t gbase, uint32_t (&p)[H16_NW]) {
         const size_t g = gbase + lane / H16_LPG;
         if (g < n_groups) {
@@ -157,12 +159,14 @@ __device__ __forceinline__ void poison_epilogue(__half* __restrict__ out, size_t
 template <int SPLIT>
 __global__ void __launch_bounds__(256) signsplit_group_h16_kernel(const __half* __restrict__ x, __half* __restrict__ out, size_t n_groups,
                                                                   unsigned* __restrict__ nan_flag) {
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int lig = lane % H16_LPG;
     const size_t warp_global = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
     const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
     const float delta = tie_delta_kernel(uint32_t(warp_global >> 33));
     const size_t stride = n_warps * H16_GPW;
+    pdl_wait();
     auto load = [&](size_t gbase, uint32_t (&p)[H16_NW]) {
         const size_t g = gbase + lane / H16_LPG;
         if (g < n_groups) {
@@ -352,11 +356,11 @@ int launch_sym_h16(int format, const void* x, void* out, size_t n_groups, cudaSt
 #endif
     const unsigned grid = grid_h16(n_groups);
     switch (format) {
-        case FPQ_FMT_E2M1: fake_quant_group_h16_kernel<FPQ_FMT_E2M1><<<grid, 256, 0, st>>>(xi, oo, n_groups); break;
-        case FPQ_FMT_E1M2: fake_quant_group_h16_kernel<FPQ_FMT_E1M2><<<grid, 256, 0, st>>>(xi, oo, n_groups); break;
-        case FPQ_FMT_E3M0: fake_quant_group_h16_kernel<FPQ_FMT_E3M0><<<grid, 256, 0, st>>>(xi, oo, n_groups); break;
-        case FPQ_FMT_E2M3: fake_quant_group_h16_kernel<FPQ_FMT_E2M3><<<grid, 256, 0, st>>>(xi, oo, n_groups); break;
-        case FPQ_FMT_E3M2: fake_quant_group_h16_kernel<FPQ_FMT_E3M2><<<grid, 256, 0, st>>>(xi, oo, n_groups); break;
+        case FPQ_FMT_E2M1: launch_pdl(fake_quant_group_h16_kernel<FPQ_FMT_E2M1>, grid, 256, 0, st, xi, oo, n_groups); break;
+        case FPQ_FMT_E1M2: launch_pdl(fake_quant_group_h16_kernel<FPQ_FMT_E1M2>, grid, 256, 0, st, xi, oo, n_groups); break;
+        case FPQ_FMT_E3M0: launch_pdl(fake_quant_group_h16_kernel<FPQ_FMT_E3M0>, grid, 256, 0, st, xi, oo, n_groups); break;
+        case FPQ_FMT_E2M3: launch_pdl(fake_quant_group_h16_kernel<FPQ_FMT_E2M3>, grid, 256, 0, st, xi, oo, n_groups); break;
+        case FPQ_FMT_E3M2: launch_pdl(fake_quant_group_h16_kernel<FPQ_FMT_E3M2>, grid, 256, 0, st, xi, oo, n_groups); break;
         default: return FPQ_ERR_ARG;
     }
     return finish_launch();
@@ -383,9 +387,9 @@ int launch_split_h16(int split, const void* x, void* out, size_t n_groups, unsig
 #endif
     const unsigned grid = grid_h16(n_groups);
     switch (split) {
-        case FPQ_SPLIT_E1M2NEG_E2M1POS: signsplit_group_h16_kernel<FPQ_SPLIT_E1M2NEG_E2M1POS><<<grid, 256, 0, st>>>(xi, oo, n_groups, nan_flag); break;
-        case FPQ_SPLIT_INTNEG_E2M3POS: signsplit_group_h16_kernel<FPQ_SPLIT_INTNEG_E2M3POS><<<grid, 256, 0, st>>>(xi, oo, n_groups, nan_flag); break;
-        case FPQ_SPLIT_AFPQ_E2M1: signsplit_group_h16_kernel<FPQ_SPLIT_AFPQ_E2M1><<<grid, 256, 0, st>>>(xi, oo, n_groups, nan_flag); break;
+        case FPQ_SPLIT_E1M2NEG_E2M1POS: launch_pdl(signsplit_group_h16_kernel<FPQ_SPLIT_E1M2NEG_E2M1POS>, grid, 256, 0, st, xi, oo, n_groups, nan_flag); break;
+        case FPQ_SPLIT_INTNEG_E2M3POS: launch_pdl(signsplit_group_h16_kernel<FPQ_SPLIT_INTNEG_E2M3POS>, grid, 256, 0, st, xi, oo, n_groups, nan_flag); break;
+        case FPQ_SPLIT_AFPQ_E2M1: launch_pdl(signsplit_group_h16_kernel<FPQ_SPLIT_AFPQ_E2M1>, grid, 256, 0, st, xi, oo, n_groups, nan_flag); break;
         default: return FPQ_ERR_ARG;
     }
     return finish_launch();

@@ -145,12 +145,19 @@ __global__ void __launch_bounds__(256) transform_rotate_quant_v2_kernel(const fl
     // quarter-warp (adjacent chunk columns) read from different banks
     extern __shared__ float s_mul[];
     constexpr int LPG = 4, NV = 8, ROW = 144;
+    // `smooth` and the sign mask are parameters of the model, not products of the previous kernel: the
+    // table is built before pdl_wait(), i.e. while the previous kernel is still draining
+    pdl_launch_dependents();
     for (int c = threadIdx.x; c < cpr * 128; c += blockDim.x) {
         const int e = c & 127;
         const float sv = smooth != nullptr ? __ldg(smooth + c) : 1.0f;
         s_mul[(c >> 7) * ROW + e] = ((sm.w[e >> 5] >> (e & 31)) & 1u) ? sv : -sv;      // sign flips are exact: (x*s)*sigma == x*(s*sigma)
     }
     __syncthreads();
+    pdl_wait();
+    // (Measured and rejected, profiles/r1_kbench.txt: requesting the first chunk before the barrier, or the
+    // next chunk before computing this one, costs 32 live registers -- 100 instead of 61, or spills at 64 --
+    // and loses 10-25 % at every size.)
     const int lane = threadIdx.x & 31;
     const int lig = lane % LPG;
     const size_t warp_global = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -292,7 +299,7 @@ extern "C" int fpq_transform_rotate_quant(const float* x, const float* smooth, c
         const size_t n_chunks = n_rows * size_t(cpr);
         const unsigned grid = grid_for(n_chunks, 64, 4);              // 8 warps x 8 chunks per block and trip
         const size_t smem = size_t(cpr) * 144 * sizeof(float);
-#define FPQ_TRQ2(F, Q) transform_rotate_quant_v2_kernel<F, Q><<<grid, 256, smem, st>>>(x, smooth, sm, o, rot, n_chunks, cpr)
+#define FPQ_TRQ2(F, Q) launch_pdl(transform_rotate_quant_v2_kernel<F, Q>, grid, 256, smem, st, x, smooth, sm, o, rot, n_chunks, cpr)
         switch (format) {
             case -1: FPQ_TRQ2(0, false); break;
             case FPQ_FMT_E2M1: FPQ_TRQ2(FPQ_FMT_E2M1, true); break;
