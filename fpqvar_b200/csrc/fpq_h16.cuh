@@ -97,7 +97,14 @@ __device__ __forceinline__ uint64_t round_pair_magic(uint32_t v2, float delta, f
     return ffma2(p, pk(-sc0, -sc1), y);
 }
 
-// One packed pair of the symmetric flow: x2 (two fp16 inputs) -> two fp16 outputs q*s.
+// One packed pair of the symmetric flow: two fp16 inputs (already widened to packed fp32) -> two fp16
+// outputs q*s.
+template <class HG>
+__device__ __forceinline__ uint32_t sym_pair_h16_w(uint64_t xf2, uint64_t r2, uint64_t s2, float delta) {
+    const uint32_t v2 = pack_h2_u64(fmul2(xf2, r2));                              // half(x/s)
+    const uint64_t q = round_pair_magic(v2, delta, Magic<HG>::EM, Magic<HG>::EM, Magic<HG>::SC, Magic<HG>::SC);
+    return pack_h2_u64(fmul2(q, s2));                                             // half(q*s)
+}
 template <class HG>
 __device__ __forceinline__ uint32_t sym_pair_h16(uint32_t x2, uint64_t r2, uint64_t s2, float delta) {
     const uint32_t v2 = pack_h2_u64(fmul2(widen_h2(x2), r2));                     // half(x/s)
@@ -242,9 +249,16 @@ template <class NEG, class POS> struct SplitScale {
 };
 
 template <class NEG, class POS>
+__device__ __forceinline__ uint32_t split_pair_h16_w(float2 x, float rn, float sn, float rp, float sp, float delta);
+
+template <class NEG, class POS>
 __device__ __forceinline__ uint32_t split_pair_h16(uint32_t x2, float rn, float sn, float rp, float sp, float delta) {
+    return split_pair_h16_w<NEG, POS>(__half22float2(*reinterpret_cast<const __half2*>(&x2)), rn, sn, rp, sp, delta);
+}
+
+template <class NEG, class POS>
+__device__ __forceinline__ uint32_t split_pair_h16_w(float2 x, float rn, float sn, float rp, float sp, float delta) {
     // rn, sn arrive pre-scaled by the caller when SplitScale::UNIFORM_NEG (rn*K, sn/K)
-    const float2 x = __half22float2(*reinterpret_cast<const __half2*>(&x2));
 #if FPQ_SPLIT_IMAD >= 4
     const int m0 = -int(__umulhi(__float_as_uint(x.x), 2u)), m1 = -int(__umulhi(__float_as_uint(x.y), 2u));
 #else
