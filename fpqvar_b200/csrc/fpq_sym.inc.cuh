@@ -264,8 +264,23 @@ static int dispatch_sym_types(int in_dtype, int out_dtype, int format, const voi
     return FPQ_ERR_ARG;
 }
 
+// One translation unit per tie rule (FPQ_SYM_TIE_PART = 0 / 1, see fpq_sym_k.cu / fpq_sym_a.cu): the 4 dtype
+// pairs x 5 formats x {group, row-in-registers x3, row} instantiations of one rule take ~80 s of nvcc each.
+#if FPQ_SYM_TIE_PART == 0
+int fake_quant_kernel_tie(int in_dtype, int out_dtype, int format, const void* x, void* out, size_t n_rows, size_t row_len, int clamp3,
+                          cudaStream_t st) {
+    return dispatch_sym_types<TIE_KERNEL>(in_dtype, out_dtype, format, x, out, n_rows, row_len, clamp3, st);
+}
+#else
+int fake_quant_argmin_tie(int in_dtype, int out_dtype, int format, const void* x, void* out, size_t n_rows, size_t row_len, int clamp3,
+                          cudaStream_t st) {
+    return dispatch_sym_types<TIE_ARGMIN>(in_dtype, out_dtype, format, x, out, n_rows, row_len, clamp3, st);
+}
+#endif
+
 }  // namespace fpq
 
+#if FPQ_SYM_TIE_PART == 0
 using namespace fpq;
 
 extern "C" int fpq_fake_quant(const void* x, void* out, size_t n_rows, size_t row_len, int in_dtype, int out_dtype, int format,
@@ -275,7 +290,8 @@ extern "C" int fpq_fake_quant(const void* x, void* out, size_t n_rows, size_t ro
     if (n_rows == 0) return FPQ_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int clamp3 = (flags & FPQ_FLAG_CLAMP3) ? 1 : 0;
-    if (tie_mode == FPQ_TIE_KERNEL) return dispatch_sym_types<TIE_KERNEL>(in_dtype, out_dtype, format, x, out, n_rows, row_len, clamp3, st);
-    if (tie_mode == FPQ_TIE_ARGMIN) return dispatch_sym_types<TIE_ARGMIN>(in_dtype, out_dtype, format, x, out, n_rows, row_len, clamp3, st);
+    if (tie_mode == FPQ_TIE_KERNEL) return fake_quant_kernel_tie(in_dtype, out_dtype, format, x, out, n_rows, row_len, clamp3, st);
+    if (tie_mode == FPQ_TIE_ARGMIN) return fake_quant_argmin_tie(in_dtype, out_dtype, format, x, out, n_rows, row_len, clamp3, st);
     return FPQ_ERR_ARG;
 }
+#endif
