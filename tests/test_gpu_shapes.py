@@ -1,0 +1,113 @@
+"""GPU: shape / alignment / layout coverage of the C-ABI entry points against the oracle -- group sizes other
+than 128, rows of odd lengths, views that are only 2- or 4-byte aligned, non-contiguous inputs, every dtype
+pair of the row kernels, and use from a side stream with and without programmatic dependent launch."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import bits_equal, mismatch_report
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+NP = {torch.float32: np.float32, torch.float16: np.float16}
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from fpqvar_b200 import ops as _ops
+    return _ops
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+@pytest.mark.parametrize("group", [16, 32, 64, 128, 256, 512, 1920])
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16])
+def test_group_sizes(ops, group, dt):
+    torch.manual_seed(group)
+    x = (torch.randn(77, group * 3, device="cuda") * 1.7).to(dt)
+    for fmt, tie in (("e2m1", "kernel"), ("e3m2", "kernel"), ("e1m2", "argmin")):
+        want = O.fake_quant(host(x), fmt, group, tie)
+        got = host(ops.fake_quant(x, fmt, group, tie))
+        assert bits_equal(got, want), f"group {group} {fmt} {tie}\n" + mismatch_report(got, want)
+    want = O.fake_quant_signsplit(host(x), "e1m2_neg_e2m1_pos", group, "kernel", clipping_strength=None)
+    got = host(ops.fake_quant_signsplit(x, "e1m2_neg_e2m1_pos", group, "kernel"))
+    assert bits_equal(got, want), f"split group {group}"
+
+
+@pytest.mark.parametrize("row_len", [256, 264, 1000, 1920, 2304, 4096, 7680, 9216, 16384, 40000])
+@pytest.mark.parametrize("din,dout", [(torch.float16, torch.float16), (torch.float32, torch.float16), (torch.float32, torch.float32),
+                                      (torch.float16, torch.float32)])
+def test_row_kernels_every_dtype_pair(ops, row_len, din, dout):
+    torch.manual_seed(row_len)
+    x = (torch.randn(19, row_len, device="cuda") * torch.exp(torch.randn(19, 1, device="cuda"))).to(din)
+    x[3] = 0
+    x[5, 7] = float("nan")
+    x[6, 1] = float("inf")
+    tie = "argmin" if dout == torch.float32 and din == torch.float16 else "kernel"
+    for fmt in ("e2m3", "e2m1"):
+        want = O.fake_quant(host(x), fmt, None, tie, clamp3=(tie == "argmin"), out_dtype=NP[dout])
+        got = host(ops.fake_quant(x, fmt, None, tie, clamp3=(tie == "argmin"), out_dtype=dout))
+        assert bits_equal(got, want), f"rows {row_len} {din}->{dout} {fmt}\n" + mismatch_report(got, want)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16])
+def test_unaligned_and_noncontiguous_inputs(ops, dt):
+    torch.manual_seed(1)
+    base = torch.randn(128 * 50 + 3, device="cuda").to(dt)
+    for off in (1, 2, 3):                                   # 2/4-byte aligned views: the vector paths must not be taken
+        v = base[off: off + 128 * 50]
+        want = O.fake_quant(host(v), "e2m1", 128, "kernel")
+        assert bits_equal(host(ops.fake_quant(v, "e2m1", 128, "kernel")), want), f"offset {off}"
+        want = O.fake_quant_signsplit(host(v), "e1m2_neg_e2m1_pos", 128, "kernel", clipping_strength=None)
+        assert bits_equal(host(ops.fake_quant_signsplit(v, "e1m2_neg_e2m1_pos", 128, "kernel")), want), f"split offset {off}"
+    t = torch.randn(64, 512, device="cuda").to(dt).t()      # non-contiguous: made contiguous by the host layer
+    want = O.fake_quant(np.ascontiguousarray(host(t)), "e2m1", 128, "kernel")
+    assert bits_equal(host(ops.fake_quant(t, "e2m1", 128, "kernel")), want)
+    rows = torch.randn(33, 1000, device="cuda").to(dt)[:, 1:]      # rows of 999 elements starting at odd offsets
+    want = O.fake_quant(host(rows), "e2m3", None, "kernel", out_dtype=np.float16)
+    assert bits_equal(host(ops.fake_quant(rows, "e2m3", None, "kernel", out_dtype=torch.float16)), want)
+
+
+def test_side_stream_and_graph_replay(ops):
+    torch.manual_seed(2)
+    x = torch.nn.functional.gelu(torch.randn(4096, 1024, device="cuda")).half()
+    want = O.fake_quant_signsplit(host(x), "e1m2_neg_e2m1_pos", 128, "kernel")
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        y = ops.fake_quant_signsplit(x, "e1m2_neg_e2m1_pos", 128, "kernel", global_clip=True)
+        z = ops.fake_quant(y, "e2m1", 128, "kernel")                      # dependent launch right behind (PDL edge)
+    s.synchronize()
+    assert bits_equal(host(y), want)
+    assert bits_equal(host(z), O.fake_quant(want, "e2m1", 128, "kernel"))
+    # NaN poisoning through the whole-tensor clip, then a clean call on the same stream/workspace
+    xn = x.clone()
+    xn[17, 5] = float("nan")
+    with torch.cuda.stream(s):
+        yn = ops.fake_quant_signsplit(xn, "e1m2_neg_e2m1_pos", 128, "kernel", global_clip=True)
+        y2 = ops.fake_quant_signsplit(x, "e1m2_neg_e2m1_pos", 128, "kernel", global_clip=True)
+    s.synchronize()
+    assert bits_equal(host(yn), O.fake_quant_signsplit(host(xn), "e1m2_neg_e2m1_pos", 128, "kernel"))
+    assert float(yn.abs().max()) == 0.0
+    assert bits_equal(host(y2), want), "workspace not reset after a poisoned call"
+
+
+def test_results_identical_without_pdl():
+    """FPQ_NO_PDL=1 (plain stream-ordered launches) must give the same bits."""
+    code = ("import torch, hashlib; from fpqvar_b200 import ops; from fpqvar_b200.hotpath import seed42_sign_bits;"
+            "torch.manual_seed(0); x=torch.randn(3000,1920,device='cuda'); h=torch.nn.functional.gelu(x).half();"
+            "a=ops.transform_rotate_quant(x, None, seed42_sign_bits(), 'e2m1'); b=ops.fake_quant_signsplit(h,'e1m2_neg_e2m1_pos',128,'kernel',global_clip=True);"
+            "c=ops.fake_quant(h,'e2m1',128,'kernel'); torch.cuda.synchronize();"
+            "print(hashlib.sha256(a.cpu().numpy().tobytes()+b.cpu().numpy().tobytes()+c.cpu().numpy().tobytes()).hexdigest())")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for env_extra in ({}, {"FPQ_NO_PDL": "1"}):
+        env = dict(os.environ, **env_extra)
+        outs.append(subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300).stdout.strip())
+    assert outs[0] and outs[0] == outs[1], outs
