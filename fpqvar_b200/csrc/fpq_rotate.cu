@@ -137,10 +137,15 @@ __global__ void __launch_bounds__(256) transform_rotate_quant_kernel(const float
 // (2 SHFL per element instead of 3, and half the per-group scalar work per element).  The
 // smooth*sign multipliers of the whole row live in shared memory (n_cols floats), which frees the
 // registers the first layout spent on them and lets the chunks be walked with a plain grid stride.
-template <int FMT, bool QUANT>
+// MOD: the adaLN modulate in front of it is fused as well (basic_var.py:263,266):
+//     t = (x * (scale[b, c] + 1) + shift[b, c]) * smooth[c]        b = row / rows_per_batch
+// as four separately rounded fp32 operations, exactly the reference's `.mul(scale.add(1)).add_(shift).mul(s)`.
+struct Modulate { const float* scale; const float* shift; size_t rows_per_batch; };
+
+template <int FMT, bool QUANT, bool MOD>
 __global__ void __launch_bounds__(256) transform_rotate_quant_v2_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
                                                                         SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
-                                                                        size_t n_chunks, int cpr) {
+                                                                        size_t n_chunks, int cpr, Modulate mod) {
     // [cpr][ROW]: smooth[c] * sigma[c % 128]; rows padded by 16 floats so that the two lane sets of a
     // quarter-warp (adjacent chunk columns) read from different banks
     extern __shared__ float s_mul[];
@@ -172,16 +177,33 @@ __global__ void __launch_bounds__(256) transform_rotate_quant_v2_kernel(const fl
         const size_t c = cbase + lane / LPG;
         const bool valid = c < n_chunks;
         const size_t off = c * 128;
-        const float* mrow = s_mul + (valid ? int(c % size_t(cpr)) : 0) * ROW;
+        const int ccol = valid ? int(c % size_t(cpr)) : 0;
+        const float* mrow = s_mul + ccol * ROW;
+        size_t moff = 0;
+        if constexpr (MOD) moff = (valid ? (c / size_t(cpr)) / mod.rows_per_batch : 0) * (size_t(cpr) * 128) + size_t(ccol) * 128;
         uint64_t P[16];
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
             uint4 u = make_uint4(0u, 0u, 0u, 0u);
             if (valid) u = ldg_stream(x + off + (j * LPG + lig) * 4);
             const float4 m4 = *reinterpret_cast<const float4*>(mrow + (j * LPG + lig) * 4);
+            uint64_t xa = (uint64_t(u.y) << 32) | u.x, xb = (uint64_t(u.w) << 32) | u.z;
+            if constexpr (MOD) {
+                const size_t mo = moff + (j * LPG + lig) * 4;
+                const float4 sc = __ldg(reinterpret_cast<const float4*>(mod.scale + mo));
+                const float4 sh = __ldg(reinterpret_cast<const float4*>(mod.shift + mo));
+                const uint64_t one2 = pk(1.0f, 1.0f);
+                // .mul(scale.add(1)).add_(shift).  The product uses the SCALAR mul.rn.f32 (never contracted):
+                // ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 -- even through a *1 -- which would skip
+                // the rounding of the product that the reference's separate ATen kernels perform.
+                const F2 a0 = unpk(fadd2(pk(sc.x, sc.y), one2)), a1 = unpk(fadd2(pk(sc.z, sc.w), one2));
+                const F2 x0 = unpk(xa), x1 = unpk(xb);
+                xa = fadd2(pk(__fmul_rn(x0.lo, a0.lo), __fmul_rn(x0.hi, a0.hi)), pk(sh.x, sh.y));
+                xb = fadd2(pk(__fmul_rn(x1.lo, a1.lo), __fmul_rn(x1.hi, a1.hi)), pk(sh.z, sh.w));
+            }
             // x * (s * sigma): basic_var.py:263 `.mul(s)` in fp32, then the sign row of Q
-            P[2 * j] = fmul2((uint64_t(u.y) << 32) | u.x, pk(m4.x, m4.y));
-            P[2 * j + 1] = fmul2((uint64_t(u.w) << 32) | u.z, pk(m4.z, m4.w));
+            P[2 * j] = fmul2(xa, pk(m4.x, m4.y));
+            P[2 * j + 1] = fmul2(xb, pk(m4.z, m4.w));
         }
         // index bit 0: inside a packed pair
 #pragma unroll
@@ -280,13 +302,17 @@ __global__ void __launch_bounds__(256) transform_rotate_weight_kernel(const floa
 
 using namespace fpq;
 
-extern "C" int fpq_transform_rotate_quant(const float* x, const float* smooth, const uint32_t* sign_bits_host, void* out, void* rotated,
-                                          size_t n_rows, size_t n_cols, int format, void* stream) {
+static int launch_rotate_quant(const float* x, const Modulate* mod, const float* smooth, const uint32_t* sign_bits_host, void* out, void* rotated,
+                               size_t n_rows, size_t n_cols, int format, void* stream) {
     if (n_cols == 0 || n_cols % 128 != 0 || !sign_bits_host || (n_rows && (!x || !out))) return FPQ_ERR_ARG;
     if (format < -1 || format >= FPQ_NUM_SYM_FORMATS) return FPQ_ERR_ARG;
     if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(smooth)) & 15) || (reinterpret_cast<uintptr_t>(out) & 7) ||
         (reinterpret_cast<uintptr_t>(rotated) & 7))
         return FPQ_ERR_ARG;
+    if (mod != nullptr) {
+        if (!mod->scale || !mod->shift || mod->rows_per_batch == 0 || n_rows % mod->rows_per_batch != 0) return FPQ_ERR_ARG;
+        if ((reinterpret_cast<uintptr_t>(mod->scale) | reinterpret_cast<uintptr_t>(mod->shift)) & 15) return FPQ_ERR_ARG;
+    }
     if (n_rows == 0) return FPQ_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     SignMask sm;
@@ -299,7 +325,10 @@ extern "C" int fpq_transform_rotate_quant(const float* x, const float* smooth, c
         const size_t n_chunks = n_rows * size_t(cpr);
         const unsigned grid = grid_for(n_chunks, 64, 4);              // 8 warps x 8 chunks per block and trip
         const size_t smem = size_t(cpr) * 144 * sizeof(float);
-#define FPQ_TRQ2(F, Q) launch_pdl(transform_rotate_quant_v2_kernel<F, Q>, grid, 256, smem, st, x, smooth, sm, o, rot, n_chunks, cpr)
+        const Modulate m = mod ? *mod : Modulate{nullptr, nullptr, 1};
+#define FPQ_TRQ2(F, Q)                                                                                                                     \
+    if (mod) launch_pdl(transform_rotate_quant_v2_kernel<F, Q, true>, grid, 256, smem, st, x, smooth, sm, o, rot, n_chunks, cpr, m);       \
+    else launch_pdl(transform_rotate_quant_v2_kernel<F, Q, false>, grid, 256, smem, st, x, smooth, sm, o, rot, n_chunks, cpr, m)
         switch (format) {
             case -1: FPQ_TRQ2(0, false); break;
             case FPQ_FMT_E2M1: FPQ_TRQ2(FPQ_FMT_E2M1, true); break;
@@ -312,6 +341,7 @@ extern "C" int fpq_transform_rotate_quant(const float* x, const float* smooth, c
         return finish_launch();
     }
 #endif
+    if (mod != nullptr) return FPQ_ERR_UNSUPPORTED;                  // rows wider than 10 922 columns: first layout has no modulate variant
     // first layout: lane sets, one per (chunk column, row phase); enough to fill every SM's 2048 thread slots
     const size_t max_sets = size_t(sm_count()) * 2048 / 8;
     size_t sets_per_col = max_sets / size_t(cpr);
@@ -334,6 +364,18 @@ extern "C" int fpq_transform_rotate_quant(const float* x, const float* smooth, c
     }
 #undef FPQ_TRQ
     return finish_launch();
+}
+
+extern "C" int fpq_transform_rotate_quant(const float* x, const float* smooth, const uint32_t* sign_bits_host, void* out, void* rotated,
+                                          size_t n_rows, size_t n_cols, int format, void* stream) {
+    return launch_rotate_quant(x, nullptr, smooth, sign_bits_host, out, rotated, n_rows, n_cols, format, stream);
+}
+
+extern "C" int fpq_modulate_transform_rotate_quant(const float* x, const float* scale, const float* shift, size_t rows_per_batch,
+                                                   const float* smooth, const uint32_t* sign_bits_host, void* out, void* rotated,
+                                                   size_t n_rows, size_t n_cols, int format, void* stream) {
+    const Modulate m{scale, shift, rows_per_batch};
+    return launch_rotate_quant(x, &m, smooth, sign_bits_host, out, rotated, n_rows, n_cols, format, stream);
 }
 
 extern "C" int fpq_transform_rotate_weight(const float* w, const float* smooth, const uint32_t* sign_bits_host, float* w_out, size_t n_rows,

@@ -145,6 +145,38 @@ def transform_rotate_quant(x: torch.Tensor, smooth: Optional[torch.Tensor], sign
     return (out, rot) if return_rotated else out
 
 
+def modulate_transform_rotate_quant(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, smooth: Optional[torch.Tensor], sign_bits,
+                                    fmt: Optional[str], return_rotated: bool = False):
+    """Fused ``((x * (scale + 1) + shift) * smooth) @ Q_block128`` -> fp16 -> per-group fake quant
+    (fpq_modulate_transform_rotate_quant).  x: fp32 [B, L, C] (LayerNorm output); scale, shift: fp32
+    broadcastable [B, 1, C] (the adaLN tensors of basic_var.py:258)."""
+    _require_cuda(x, "modulate_transform_rotate_quant")
+    if x.dtype != torch.float32 or x.dim() < 2:
+        raise L.FpqError("modulate_transform_rotate_quant: x must be float32 [B, ..., C]")
+    x = x.contiguous()
+    b, c = x.shape[0], x.shape[-1]
+    rows_per_batch = x.numel() // (b * c) if b * c else 0
+    mods = []
+    for name, t in (("scale", scale), ("shift", shift)):
+        _require_cuda(t, f"modulate_transform_rotate_quant({name})")
+        if t.numel() != b * c or t.shape[0] != b or t.shape[-1] != c:
+            raise L.FpqError(f"{name} must be [B, 1, C] = [{b}, 1, {c}], got {tuple(t.shape)}")
+        mods.append(t.detach().to(torch.float32).contiguous())
+    if smooth is not None:
+        smooth = smooth.detach().to(torch.float32).contiguous()
+        if smooth.numel() != c:
+            raise L.FpqError(f"smooth has {smooth.numel()} entries, expected {c}")
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    rot = torch.empty_like(out) if return_rotated else None
+    with torch.cuda.device_of(x):
+        rc = L.lib().fpq_modulate_transform_rotate_quant(x.data_ptr(), mods[0].data_ptr(), mods[1].data_ptr(), rows_per_batch,
+                                                         smooth.data_ptr() if smooth is not None else None, sign_bits, out.data_ptr(),
+                                                         rot.data_ptr() if rot is not None else None, b * rows_per_batch, c,
+                                                         -1 if fmt is None else L.FMT[fmt], _stream())
+    L.check(rc, "fpq_modulate_transform_rotate_quant")
+    return (out, rot) if return_rotated else out
+
+
 def transform_rotate_weight(w: torch.Tensor, smooth: Optional[torch.Tensor], sign_bits, inplace: bool = False) -> torch.Tensor:
     """``(W / smooth).double() @ Q_block128`` -> fp32 (fpq_transform_rotate_weight)."""
     _require_cuda(w, "transform_rotate_weight")

@@ -114,4 +114,17 @@ def transform_rotate_quant_activation(x: torch.Tensor, smooth: Optional[torch.Te
     return ops.transform_rotate_quant(x, smooth, sign_bits, fmt)
 
 
+def adaln_transform_rotate_quant_activation(ln_out: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, smooth: Optional[torch.Tensor],
+                                            act_fp_type: Optional[str] = "fp_e2", sign_bits=None) -> torch.Tensor:
+    """basic_var.py:263,266 in ONE kernel, adaLN modulate included:
+        act_quant( matmul( ln_out.mul(scale.add(1)).add_(shift).mul(smooth), Q_block ) )
+    ln_out: fp32 [B, L, C] (`self.ln_wo_grad(x)`); scale, shift: fp32 [B, 1, C] (scale1/shift1 or scale2/shift2)."""
+    fmt = {None: None, "fp_e1": "e1m2", "fp_e2": "e2m1", "fp_e3": "e3m0", "fp6_e2m3": "e2m3", "fp6_e3m2": "e3m2"}.get(act_fp_type, "?")
+    if fmt == "?":
+        raise ValueError("Unsupported fp_type.")
+    if sign_bits is None:
+        sign_bits = block_sign_bits()
+    return ops.modulate_transform_rotate_quant(ln_out, scale, shift, smooth, sign_bits, fmt)
+
+
 assert math  # keep the import the reference has (callers sometimes reach through the module)

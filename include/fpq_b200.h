@@ -143,6 +143,18 @@ FPQ_API int fpq_transform_rotate_quant(const float *x, const float *smooth, cons
                                int format, void *stream);
 
 /*
+ * Same, with the adaLN modulate that precedes it in the reference fused in as well (SURVEY.md section 8f,
+ * rank 1; basic_var.py:263,266 `self.ln_wo_grad(x).mul(scale1.add(1)).add_(shift1).mul(best_s)`):
+ *     t[r, c] = ( x[r, c] * (scale[b, c] + 1) + shift[b, c] ) * smooth[c],   b = r / rows_per_batch
+ * computed as the reference's four separately rounded fp32 operations, then rotated and quantized as above.
+ *   x            : fp32 [n_rows, n_cols], the LayerNorm output; n_rows % rows_per_batch == 0
+ *   scale, shift : fp32 [n_rows / rows_per_batch, n_cols] (the [B, 1, C] adaLN tensors), 16-byte aligned
+ */
+FPQ_API int fpq_modulate_transform_rotate_quant(const float *x, const float *scale, const float *shift, size_t rows_per_batch,
+                                        const float *smooth, const uint32_t *sign_bits_host, void *out, void *rotated,
+                                        size_t n_rows, size_t n_cols, int format, void *stream);
+
+/*
  * Weight side of the same transform (transform_model_utils.py:8-28, rotation_utils.py:129-154):
  *     w_out[r, :] = float( FWHT_128_f64( (w[r, c] / smooth[c]) * sign[c % 128] ) / fl32(sqrt(128)) )
  * fp32 in/out, fp64 butterflies; in-place allowed (w_out == w).  smooth may be NULL.

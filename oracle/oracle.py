@@ -345,6 +345,13 @@ def transform_rotate_activation_f64(x: np.ndarray, s: np.ndarray, q: np.ndarray)
     return xs @ q
 
 
+def adaln_modulate(ln_out: np.ndarray, scale: np.ndarray, shift: np.ndarray) -> np.ndarray:
+    """basic_var.py:263,266 ``self.ln_wo_grad(x).mul(scale1.add(1)).add_(shift1)``: three fp32 elementwise ops,
+    each rounded to fp32 ([B, L, C] with [B, 1, C] operands)."""
+    a = (scale.astype(np.float32) + np.float32(1)).astype(np.float32)
+    return ((ln_out.astype(np.float32) * a).astype(np.float32) + shift.astype(np.float32)).astype(np.float32)
+
+
 # --------------------------------------------------------------------------------------
 # Format scoring (search scripts)
 # --------------------------------------------------------------------------------------

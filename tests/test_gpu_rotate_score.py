@@ -85,6 +85,44 @@ def test_transform_rotate_quant_matches_unfused_path(ops, sign_bits):
     assert torch.equal(fused.view(torch.int16), two_step.view(torch.int16))
 
 
+@pytest.mark.parametrize("fmt", ["e2m1", "e2m3", None])
+@pytest.mark.parametrize("B,Lr,C", [(3, 7, 256), (100, 16, 1920), (2, 1, 2304), (5, 33, 128)])
+def test_modulate_transform_rotate_quant(ops, sign_bits, B, Lr, C, fmt):
+    """adaLN modulate fused in: bit-identical to the reference's three ATen ops
+    followed by the un-modulated fused kernel, and within the stated tolerance of the fp64 statement."""
+    g = torch.Generator(device="cuda").manual_seed(B * 1000 + C)
+    x = torch.randn(B, Lr, C, device="cuda", generator=g)
+    scale = torch.randn(B, 1, C, device="cuda", generator=g) * 0.3
+    shift = torch.randn(B, 1, C, device="cuda", generator=g) * 0.5
+    s = torch.exp(torch.rand(C, device="cuda", generator=g) * 2 - 1)
+    fused, frot = ops.modulate_transform_rotate_quant(x, scale, shift, s, sign_bits, fmt, return_rotated=True)
+    mod = x.mul(scale.add(1)).add_(shift)                                 # basic_var.py:263, on the GPU with ATen
+    two, trot = ops.transform_rotate_quant(mod, s, sign_bits, fmt, return_rotated=True)
+    assert torch.equal(frot.view(torch.int16), trot.view(torch.int16))
+    assert torch.equal(fused.view(torch.int16), two.view(torch.int16))
+    # oracle: the modulate restated in numpy, then the fp64 rotation
+    mo = O.adaln_modulate(host(x), host(scale), host(shift))
+    assert bits_equal(mo, host(mod))
+    want = O.transform_rotate_activation_f64(mo.reshape(-1, C), host(s), O.block_random_hadamard_matrix(C, 128))
+    xs = mo.reshape(-1, C) * host(s)
+    tol = 0.5 * np.spacing(np.abs(want).astype(np.float16)).astype(np.float64) + 2e-6 * np.abs(xs).max(axis=1, keepdims=True)
+    assert np.all(np.abs(host(frot).reshape(-1, C).astype(np.float64) - want) <= tol)
+    if fmt is not None:
+        assert bits_equal(host(fused), O.fake_quant(host(frot), fmt, 128, "kernel"))
+
+
+def test_modulate_argument_checks(ops, sign_bits):
+    from fpqvar_b200._lib import FpqError
+    x = torch.randn(4, 3, 256, device="cuda")
+    ok = torch.zeros(4, 1, 256, device="cuda")
+    with pytest.raises(FpqError):
+        ops.modulate_transform_rotate_quant(x, torch.zeros(3, 1, 256, device="cuda"), ok, None, sign_bits, "e2m1")
+    with pytest.raises(FpqError):
+        ops.modulate_transform_rotate_quant(x, ok, ok.cpu(), None, sign_bits, "e2m1")
+    out = ops.modulate_transform_rotate_quant(x, ok, ok, None, sign_bits, "e2m1")       # scale 0, shift 0 == no modulate
+    assert torch.equal(out.view(torch.int16), ops.transform_rotate_quant(x, None, sign_bits, "e2m1").view(torch.int16))
+
+
 @pytest.mark.parametrize("shape", [(384, 256), (1920 * 3, 1920), (100, 128)])
 @pytest.mark.parametrize("with_smooth", [True, False])
 def test_transform_rotate_weight(ops, sign_bits, shape, with_smooth):
