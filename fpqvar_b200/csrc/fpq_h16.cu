@@ -11,6 +11,9 @@ namespace fpq {
 #ifndef FPQ_SYM_PREFETCH
 #define FPQ_SYM_PREFETCH 1
 #endif
+// Occupancy of the sign-split kernel, measured (profiles/r1_kbench.txt, kbench_11): as compiled (56 registers, 4 CTAs/SM)
+// 6.31 TB/s burst / 5.67 sustained; forced to 5 CTAs (48 registers, spills) 5.75 / 5.35; 6 CTAs (40 registers) 5.48 / 5.49;
+// 2 CTAs (90 registers) 5.26 / 5.20.  Plain __launch_bounds__(256) it stays.
 #ifndef FPQ_SPLIT_PREFETCH
 #define FPQ_SPLIT_PREFETCH 0
 #endif
