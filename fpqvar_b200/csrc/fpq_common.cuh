@@ -56,6 +56,8 @@ int sm_count();
 // symmetric fake quant, one translation unit per tie rule (fpq_sym_k.cu / fpq_sym_a.cu)
 int fake_quant_kernel_tie(int in_dtype, int out_dtype, int format, const void* x, void* out, size_t n_rows, size_t row_len, int clamp3, cudaStream_t st);
 int fake_quant_argmin_tie(int in_dtype, int out_dtype, int format, const void* x, void* out, size_t n_rows, size_t row_len, int clamp3, cudaStream_t st);
+int signsplit_kernel_tie(int in_dtype, int out_dtype, int split, const void* x, void* out, size_t n_rows, size_t row_len, unsigned* flag, cudaStream_t st);
+int signsplit_argmin_tie(int in_dtype, int out_dtype, int split, const void* x, void* out, size_t n_rows, size_t row_len, unsigned* flag, cudaStream_t st);
 // packed fp16 -> fp16 group-of-128 kernels, kernel tie rule (fpq_h16.cu)
 int launch_sym_h16(int format, const void* x, void* out, size_t n_groups, cudaStream_t st);
 int launch_split_h16(int split, const void* x, void* out, size_t n_groups, unsigned* nan_flag, cudaStream_t st);

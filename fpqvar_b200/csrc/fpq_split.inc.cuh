@@ -1,6 +1,6 @@
 // libfpq_b200 -- sign-split fake-quant kernels (reference row a3 of SURVEY.md section 8)
 // Part of the C ABI of include/fpq_b200.h; no torch types here.
-#include "fpq_common.cuh"
+#include "fpq_h16.cuh"
 
 namespace fpq {
 
@@ -131,6 +131,166 @@ __global__ void __launch_bounds__(256) signsplit_row_kernel(const InT* __restric
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// Per-row sign-split with the row resident in registers (per_token variants of the FP6 configs,
+// fp6_quant_int_neg_e2m3_pos_per_token_cuda qu.py:614-646): one CTA per row, V 16-byte vectors per
+// thread, one HBM pass, the next row's loads in flight during the block reduction.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void block_max2(float& a, float& b, float (&red)[64]) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+        b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+    }
+    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) { red[w] = a; red[32 + w] = b; }
+    __syncthreads();
+    a = red[0]; b = red[32];
+    for (int i = 1; i < nw; ++i) { a = fmaxf(a, red[i]); b = fmaxf(b, red[32 + i]); }
+}
+
+template <typename InT, typename OutT, int SPLIT, int TIE, int V>
+__global__ void __launch_bounds__(1024) signsplit_row_reg_kernel(const InT* __restrict__ x, OutT* __restrict__ out, size_t n_rows,
+                                                                 int row_vecs, unsigned* __restrict__ nan_flag) {
+    using SF = SplitFmt<SPLIT>;
+    constexpr int VEC = 16 / sizeof(InT);
+    __shared__ float red[64];
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const float delta = tie_delta_kernel(uint32_t((size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 40));
+    auto load_row = [&](size_t row, uint4 (&dst)[V]) {
+        const InT* xr = x + row * size_t(row_vecs) * VEC;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const int vi = tid + k * nt;
+            dst[k] = (row < n_rows && vi < row_vecs) ? ldg_stream(xr + size_t(vi) * VEC) : make_uint4(0u, 0u, 0u, 0u);
+        }
+    };
+    uint4 u[V], un[V];
+    load_row(blockIdx.x, un);
+    for (size_t row = blockIdx.x; row < n_rows; row += gridDim.x) {
+        OutT* orow = out + row * size_t(row_vecs) * VEC;
+#pragma unroll
+        for (int k = 0; k < V; ++k) u[k] = un[k];
+        load_row(row + gridDim.x, un);
+        float an = 0.0f, ap = 0.0f;
+        bool has_nan = false;
+        auto float_maxima = [&]() {                    // where(x<=0, x, 0) / where(x>0, x, 0): a NaN counts as 0 (qu.py:619-620)
+            an = 0.0f; ap = 0.0f;
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float f[2];
+                    int n = 1;
+                    if constexpr (sizeof(InT) == 2) {
+                        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+                        f[0] = t.x; f[1] = t.y; n = 2;
+                    } else {
+                        f[0] = __uint_as_float(w[q]); f[1] = 0.0f;
+                    }
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        if (e < n) {
+                            an = fmaxf(an, (f[e] <= 0.0f) ? -f[e] : 0.0f);
+                            ap = fmaxf(ap, (f[e] > 0.0f) ? f[e] : 0.0f);
+                            has_nan |= (f[e] != f[e]);
+                        }
+                    }
+                }
+            }
+        };
+        if constexpr (sizeof(InT) == 2) {
+            // both maxima from the integer order of the fp16 bit patterns, two elements per VIMNMX (fpq_h16.cu)
+            uint32_t pm = 0u, nm = 0u;
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                pm = __vmaxs2(__vmaxs2(pm, u[k].x), __vmaxs2(u[k].y, __vmaxs2(u[k].z, u[k].w)));
+                nm = __vmaxu2(__vmaxu2(nm, u[k].x), __vmaxu2(u[k].y, __vmaxu2(u[k].z, u[k].w)));
+            }
+            const uint32_t pbits = uint32_t(max(int(short(pm & 0xffffu)), int(short(pm >> 16))));
+            const uint32_t nraw = max(nm & 0xffffu, nm >> 16);
+            const uint32_t nbits = nraw >= 0x8000u ? (nraw & 0x7fffu) : 0u;
+            if (pbits > 0x7C00u || nbits > 0x7C00u) float_maxima();          // this thread holds a NaN
+            else { an = h2f(uint16_t(nbits)); ap = h2f(uint16_t(pbits)); }
+        } else {
+            float_maxima();
+        }
+        block_max2(an, ap, red);
+        const bool row_nan = __syncthreads_or(has_nan ? 1 : 0) != 0;
+        if (nan_flag != nullptr && has_nan) atomicOr(nan_flag, 1u);
+        const float sn = rnd_in<InT>(__fdiv_rn(an, SF::NEG::VMAX));
+        const float sp = rnd_in<InT>(__fdiv_rn(ap, SF::POS::VMAX));
+        const bool fast = split_fast_ok<InT, TIE>(sn, sp) && !row_nan;      // rows holding a NaN take the literal sequence
+        const float rn = (fast && sn != 0.0f) ? __frcp_rn(sn) : 0.0f;
+        const float rp = (fast && sp != 0.0f) ? __frcp_rn(sp) : 0.0f;
+        constexpr float K = SplitScale<typename SF::NEG, typename SF::POS>::K;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const int vi = tid + k * nt;
+            if (vi >= row_vecs) continue;
+            const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+            if constexpr (sizeof(InT) == 2 && sizeof(OutT) == 2 && TIE == TIE_KERNEL) {
+                uint32_t o[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+                    if (fast) {
+                        o[q] = split_pair_h16_w<typename SF::NEG, typename SF::POS>(t, rn * K, sn * (1.0f / K), rp, sp, delta);
+                    } else {
+                        o[q] = pack_h2(signsplit_elem_literal<InT, OutT, SPLIT, TIE>(t.x, sn, sp), signsplit_elem_literal<InT, OutT, SPLIT, TIE>(t.y, sn, sp));
+                    }
+                }
+                stg_stream(orow + size_t(vi) * VEC, make_uint4(o[0], o[1], o[2], o[3]));
+            } else {
+                float f[VEC];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if constexpr (sizeof(InT) == 2) {
+                        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+                        f[2 * q] = t.x; f[2 * q + 1] = t.y;
+                    } else {
+                        f[q] = __uint_as_float(w[q]);
+                    }
+                }
+#pragma unroll
+                for (int e = 0; e < VEC; ++e)
+                    f[e] = fast ? signsplit_elem_fast<InT, SPLIT, TIE>(f[e], sn, rn, sp, rp) : signsplit_elem_literal<InT, OutT, SPLIT, TIE>(f[e], sn, sp);
+                OutT* po = orow + size_t(vi) * VEC;
+                if constexpr (sizeof(OutT) == 4) {
+#pragma unroll
+                    for (int e = 0; e < VEC; e += 4)
+                        stg_stream(po + e, make_uint4(__float_as_uint(f[e]), __float_as_uint(f[e + 1]), __float_as_uint(f[e + 2]), __float_as_uint(f[e + 3])));
+                } else if constexpr (VEC == 8) {
+                    stg_stream(po, make_uint4(pack_h2(f[0], f[1]), pack_h2(f[2], f[3]), pack_h2(f[4], f[5]), pack_h2(f[6], f[7])));
+                } else {
+                    stg_stream(po, make_uint2(pack_h2(f[0], f[1]), pack_h2(f[2], f[3])));
+                }
+            }
+        }
+    }
+}
+
+template <typename InT, typename OutT, int SPLIT, int TIE>
+static bool launch_split_row_reg(const InT* xi, OutT* oo, size_t n_rows, size_t row_len, unsigned* flag, cudaStream_t st) {
+    constexpr int VEC = 16 / sizeof(InT);
+    if (row_len % VEC != 0 || row_len < 256) return false;
+    if ((reinterpret_cast<uintptr_t>(xi) & 15) || (reinterpret_cast<uintptr_t>(oo) & 15)) return false;
+    const size_t row_vecs = row_len / VEC;
+    if (row_vecs > 4096) return false;
+    const int v = row_vecs <= 1024 ? 1 : (row_vecs <= 2048 ? 2 : 4);
+    int threads = int((row_vecs + v - 1) / v);
+    threads = (threads + 31) / 32 * 32;
+    const int ctas_per_sm = 2048 / threads > 0 ? 2048 / threads : 1;
+    const size_t cap = size_t(sm_count()) * ctas_per_sm;
+    const unsigned grid = unsigned(n_rows < cap ? n_rows : cap);
+    if (v == 1) signsplit_row_reg_kernel<InT, OutT, SPLIT, TIE, 1><<<grid, threads, 0, st>>>(xi, oo, n_rows, int(row_vecs), flag);
+    else if (v == 2) signsplit_row_reg_kernel<InT, OutT, SPLIT, TIE, 2><<<grid, threads, 0, st>>>(xi, oo, n_rows, int(row_vecs), flag);
+    else signsplit_row_reg_kernel<InT, OutT, SPLIT, TIE, 4><<<grid, threads, 0, st>>>(xi, oo, n_rows, int(row_vecs), flag);
+    return true;
+}
+
 // qu.py:421-422 with a NaN in the tensor: clamp(x, -NaN, NaN) makes every element NaN, both
 // where() halves become 0, every scale 0, every quotient 0/0 -> q = 0 (kernel rule) or
 // grid[0] (argmin rule), and the output is (+0)*0 + (+0)*0 = +0, resp. (g0n + g0p) * 0 = -0.
@@ -164,7 +324,7 @@ static int launch_split(const void* x, void* out, size_t n_rows, size_t row_len,
         const unsigned grid = grid_for(n_rows, groups_per_block, 64);
         if (lpg == 8) signsplit_group_kernel<InT, OutT, SPLIT, TIE, 8><<<grid, 256, 0, st>>>(xi, oo, n_rows, flag);
         else signsplit_group_kernel<InT, OutT, SPLIT, TIE, 4><<<grid, 256, 0, st>>>(xi, oo, n_rows, flag);
-    } else {
+    } else if (!launch_split_row_reg<InT, OutT, SPLIT, TIE>(xi, oo, n_rows, row_len, flag, st)) {
         const unsigned grid = grid_for(n_rows, 1, 16);
         signsplit_row_kernel<InT, OutT, SPLIT, TIE><<<grid, 256, 0, st>>>(xi, oo, n_rows, row_len, flag);
     }
@@ -199,8 +359,22 @@ static int dispatch_split_types(int in_dtype, int out_dtype, int split, const vo
     return FPQ_ERR_ARG;
 }
 
+// One translation unit per tie rule (FPQ_SPLIT_TIE_PART = 0 / 1: fpq_split_k.cu / fpq_split_a.cu), as for fpq_sym.
+#if FPQ_SPLIT_TIE_PART == 0
+int signsplit_kernel_tie(int in_dtype, int out_dtype, int split, const void* x, void* out, size_t n_rows, size_t row_len, unsigned* flag,
+                         cudaStream_t st) {
+    return dispatch_split_types<TIE_KERNEL>(in_dtype, out_dtype, split, x, out, n_rows, row_len, flag, st);
+}
+#else
+int signsplit_argmin_tie(int in_dtype, int out_dtype, int split, const void* x, void* out, size_t n_rows, size_t row_len, unsigned* flag,
+                         cudaStream_t st) {
+    return dispatch_split_types<TIE_ARGMIN>(in_dtype, out_dtype, split, x, out, n_rows, row_len, flag, st);
+}
+#endif
+
 }  // namespace fpq
 
+#if FPQ_SPLIT_TIE_PART == 0
 using namespace fpq;
 
 extern "C" int fpq_fake_quant_signsplit(const void* x, void* out, size_t n_rows, size_t row_len, int in_dtype, int out_dtype,
@@ -211,7 +385,8 @@ extern "C" int fpq_fake_quant_signsplit(const void* x, void* out, size_t n_rows,
     if (n_rows == 0) return FPQ_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     unsigned* flag = (flags & FPQ_FLAG_GLOBAL_CLIP) ? static_cast<unsigned*>(workspace) : nullptr;
-    if (tie_mode == FPQ_TIE_KERNEL) return dispatch_split_types<TIE_KERNEL>(in_dtype, out_dtype, split_format, x, out, n_rows, row_len, flag, st);
-    if (tie_mode == FPQ_TIE_ARGMIN) return dispatch_split_types<TIE_ARGMIN>(in_dtype, out_dtype, split_format, x, out, n_rows, row_len, flag, st);
+    if (tie_mode == FPQ_TIE_KERNEL) return signsplit_kernel_tie(in_dtype, out_dtype, split_format, x, out, n_rows, row_len, flag, st);
+    if (tie_mode == FPQ_TIE_ARGMIN) return signsplit_argmin_tie(in_dtype, out_dtype, split_format, x, out, n_rows, row_len, flag, st);
     return FPQ_ERR_ARG;
 }
+#endif

@@ -79,6 +79,8 @@ def main():
     orr = [t.view(-1)[: nr * 9216] for t in o]
     if want("rows e2m3 f16 (per_token 9216)"):
         res["rows e2m3 f16 (per_token 9216)"] = timeit(lambda i: lib.fpq_fake_quant(xr[i].data_ptr(), orr[i].data_ptr(), nr, 9216, 1, 1, 3, 0, 0, st), nr * 9216 * 4)
+    if want("rows int_neg_e2m3_pos f16 (per_token 9216)"):
+        res["rows int_neg_e2m3_pos f16 (per_token 9216)"] = timeit(lambda i: lib.fpq_fake_quant_signsplit(xr[i].data_ptr(), orr[i].data_ptr(), nr, 9216, 1, 1, 1, 0, 0, None, st), nr * 9216 * 4)
     xk = [t.view(-1, 64) for t in x]
     if want("rows e2m3 f16 (KV rows of 64)"):
         res["rows e2m3 f16 (KV rows of 64)"] = timeit(lambda i: lib.fpq_fake_quant(x[i].data_ptr(), o[i].data_ptr(), n // 64, 64, 1, 1, 3, 0, 0, st), n * 4)
