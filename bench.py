@@ -49,6 +49,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--sample-stages", type=int, default=0,
+                    help="CPU legs only: restrict the bounded sample to the first N stages (0 = all; used by the CPU unit test)")
     ap.add_argument("--profile", action="store_true",
                     help="for ncu: one warm-up replay + the timed steps only (no roofline graphs, no e2e, no CPU baseline)")
     return ap.parse_args()
@@ -113,11 +115,11 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------
 # CPU baseline / reference arm (oracle port; the ONLY place bench.py touches oracle/)
 # ----------------------------------------------------------------------------------------------
-def cpu_sample_inputs(hot, np, seed=0):
+def cpu_sample_inputs(hot, np, seed=0, stages=0):
     """Bounded sample: the four quantizer calls of ONE block (of `depth`) at every one of the 10
     stages, i.e. 1/depth of a step."""
     rng = np.random.default_rng(seed)
-    calls = hot.calls(blocks=[0])
+    calls = [c for c in hot.calls(blocks=[0]) if not stages or c.stage < stages]
     data = []
     for c in calls:
         x = rng.standard_normal((c.rows, c.cols), dtype=np.float32)
@@ -139,10 +141,10 @@ def cpu_run_sample(calls, data, smooth, P):
             P.transform_rotate_quant(x, smooth, c.fmt)
 
 
-def cpu_baseline(hot, seconds, steps=None, warmup=1):
+def cpu_baseline(hot, seconds, steps=None, warmup=1, stages=0):
     import numpy as np
     from oracle import port as P       # test infrastructure, used here as the timed CPU baseline only
-    calls, data = cpu_sample_inputs(hot, np)
+    calls, data = cpu_sample_inputs(hot, np, stages=stages)
     smooth = np.exp(np.random.default_rng(1).uniform(-1, 1, hot.width)).astype(np.float32)
     nbytes = sum(c.bytes for c in calls)
     for _ in range(warmup):
@@ -158,7 +160,7 @@ def cpu_baseline(hot, seconds, steps=None, warmup=1):
     mean = sum(times) / len(times)
     return {
         "value": nbytes / mean / 1e9, "unit": UNIT, "cores": P.num_threads(), "kind": "port",
-        "sample": f"1 of {hot.depth} blocks x all {len(hot.patch_nums)} stages of {hot.name} ({nbytes / 1e9:.2f} GB algorithmic, "
+        "sample": f"1 of {hot.depth} blocks x {'all ' + str(len(hot.patch_nums)) if not stages else 'the first ' + str(stages)} stages of {hot.name} ({nbytes / 1e9:.2f} GB algorithmic, "
                   f"{len(calls)} calls), {len(times)} repeats, {mean:.3f} s each; oracle/fakequant_port.c on {P.num_threads()} threads",
     }, mean, len(times)
 
@@ -167,7 +169,7 @@ def run_reference(args, hot):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base, mean, n = cpu_baseline(hot, 0.0, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)))
+    base, mean, n = cpu_baseline(hot, 0.0, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)), stages=args.sample_stages)
     line = {
         "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": n,
         "warmup": max(1, min(args.warmup, 2)), "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak",

@@ -226,3 +226,54 @@ def test_host_pipeline_matches_device_path(ops):
     for c, x, ho in zip(calls, xs, h_out):
         want = run_call(c, x.cuda(), smooth.get(c.site)).cpu().view(-1).view(torch.uint8)
         assert torch.equal(ho, want), (c.site, c.stage)
+
+
+def test_device_replay_in_a_cuda_graph_matches_oracle():
+    """The bench's device path at small scale: every call of a tiny VAR pass captured in ONE CUDA graph (as bench.py
+    does), replayed twice, every output checked against the oracle."""
+    from fpqvar_b200.hotpath import DeviceReplay
+    from fpqvar_b200.var_workload import VarHotPath
+    hot = VarHotPath("tiny", 2, 1, (1, 2, 3), True)
+    calls = hot.calls()
+    dev_ = torch.device("cuda", 0)
+    g = torch.Generator().manual_seed(3)
+    smooth = {s: torch.exp(torch.rand(hot.width, generator=g) * 2 - 1).cuda() for s in ("mat_qkv", "fc1")}
+    rep = DeviceReplay(dev_, smooth)
+    xs, outs = [], []
+    for c in calls:
+        x = torch.randn(c.rows, c.cols, generator=g)
+        if c.site == "fc2":
+            x = torch.nn.functional.gelu(x, approximate="tanh")
+        xs.append(x.to(torch.float16 if c.in_dtype == "f16" else torch.float32).cuda())
+        outs.append(torch.zeros(c.rows, c.cols, dtype=torch.float16 if c.out_dtype == "f16" else torch.float32, device="cuda"))
+    side = torch.cuda.Stream()
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        for c, x, o in zip(calls[:2], xs, outs):
+            rep.launch(c, x.data_ptr(), o.data_ptr(), side.cuda_stream)
+        side.synchronize()
+        with torch.cuda.graph(gr, stream=side):
+            for c, x, o in zip(calls, xs, outs):
+                rep.launch(c, x.data_ptr(), o.data_ptr(), side.cuda_stream)
+    for o in outs:
+        o.zero_()
+    gr.replay()
+    gr.replay()
+    torch.cuda.synchronize()
+    q = O.block_random_hadamard_matrix(hot.width, 128)
+    for c, x, o in zip(calls, xs, outs):
+        xn, got = host(x), host(o)
+        if c.op == "group":
+            want = O.fake_quant(xn, c.fmt, 128, "kernel")
+        elif c.op == "signsplit":
+            want = O.fake_quant_signsplit(xn, c.fmt, 128, "kernel")
+        else:
+            # rotated values are tolerance-checked elsewhere; here: the graph path equals the eager op bit for bit
+            want = host(ops_module().transform_rotate_quant(x, smooth[c.site], rep.sign_bits, c.fmt))
+            assert q.shape[0] == hot.width
+        assert bits_equal(got, want), (c.site, c.stage, c.block)
+
+
+def ops_module():
+    from fpqvar_b200 import ops as _ops
+    return _ops

@@ -233,3 +233,24 @@ def test_search_sharding_two_ranks_gloo(tmp_path):
     got = torch.load(out)
     assert got == want
     assert all(r["weight_format"] in search.FP4_FORMATS for r in got)
+
+
+# ---------------------------------------------------------------------------------------------
+# bench.py reference arm (CPU port) prints the contract's JSON line
+# ---------------------------------------------------------------------------------------------
+def test_bench_reference_arm_json_contract():
+    import json
+    import subprocess
+    import sys
+    env = dict(os.environ, ORACLE_THREADS=str(min(8, os.cpu_count() or 1)))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                          "--workload", "var_d16_w4a4", "--sample-stages", "6"], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert key in line, key
+    assert line["impl"] == "reference" and line["unit"] == "GB/s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["config"]["workload"] == "var_d16_w4a4"
