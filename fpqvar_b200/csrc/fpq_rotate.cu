@@ -10,7 +10,7 @@
 // (fpq_common.cuh).  With fp32 input, value v[4j+k] of lane l is element e = 32j + 4l + k of the
 // chunk, so the seven index bits split as k (2 bits, in registers), l (3 bits, across lanes:
 // shfl.xor 1,2,4) and j (2 bits, in registers).  A Sylvester Hadamard transform is the tensor
-// product of a 2-point butterfly over every index bit, in any order (here: 0, 1, 5, 6, 2, 3, 4).
+// product of a 2-point butterfly over every index bit, in any order (here: 0, 1, 4, 5, 6, 2, 3, in both layouts).
 #include "fpq_h16.cuh"
 
 #ifndef FPQ_ROT_V2
@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) transform_rotate_quant_kernel(const float
                                                                      SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
                                                                      size_t n_rows, int cpr, size_t sets_per_col) {
     constexpr int LPG = 8;
+    pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
     const int lig = lane % LPG;
     const size_t ls = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) / LPG;       // lane-set id
@@ -62,6 +63,7 @@ __global__ void __launch_bounds__(256) transform_rotate_quant_kernel(const float
 
     // uniform trip count across the warp (the shuffles need every lane)
     const size_t trips = (n_rows + sets_per_col - 1) / sets_per_col;
+    pdl_wait();                                       // smooth / sign mask are parameters; x may come from the previous kernel
     for (size_t t = 0; t < trips; ++t) {
         const size_t row = k0 + t * sets_per_col;
         const bool valid = active && row < n_rows;
@@ -87,9 +89,10 @@ __global__ void __launch_bounds__(256) transform_rotate_quant_kernel(const float
             const F2 f = unpk(P[i]);
             P[i] = pk(f.lo + f.hi, f.lo - f.hi);
         }
-        // index bits 1, 5, 6: between packed registers (distance 1, 2, 4 in P[])
-#pragma unroll
-        for (int h = 1; h < 8; h <<= 1) {
+        // The butterfly ORDER is part of the numerics (it fixes the fp32 summation tree).  Both layouts use the
+        // same one -- index bits 0, 1, 4, 5, 6, 2, 3 -- so a row rotates to the same bits whichever kernel the
+        // launcher picks for the tensor's size.
+        auto reg_stage = [&](int h) {                 // between packed registers at distance h in P[]
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 if ((i & h) == 0) {
@@ -98,10 +101,8 @@ __global__ void __launch_bounds__(256) transform_rotate_quant_kernel(const float
                     P[i + h] = ffma2(b, neg1, a);
                 }
             }
-        }
-        // index bits 2, 3, 4: across the lanes of the set
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
+        };
+        auto lane_stage = [&](int o) {                // across the lanes of the set
             const float sg = (lig & o) ? -1.0f : 1.0f;
             const uint64_t sg2 = pk(sg, sg);
 #pragma unroll
@@ -110,7 +111,13 @@ __global__ void __launch_bounds__(256) transform_rotate_quant_kernel(const float
                 const uint64_t q = pk(__shfl_xor_sync(0xffffffffu, f.lo, o), __shfl_xor_sync(0xffffffffu, f.hi, o));
                 P[i] = ffma2(P[i], sg2, q);            // upper lane: partner - mine ; lower lane: mine + partner (exact: * +-1)
             }
-        }
+        };
+        reg_stage(1);      // index bit 1
+        lane_stage(4);     // index bit 4
+        reg_stage(2);      // index bit 5
+        reg_stage(4);      // index bit 6
+        lane_stage(1);     // index bit 2
+        lane_stage(2);     // index bit 3
         // / fl32(sqrt(128)), rounded to fp16: the fp16 GEMM output of the reference
         uint32_t w[8];
 #pragma unroll
@@ -321,7 +328,11 @@ static int launch_rotate_quant(const float* x, const Modulate* mod, const float*
     __half* o = static_cast<__half*>(out);
     __half* rot = static_cast<__half*>(rotated);
 #if FPQ_ROT_V2
-    if (size_t(cpr) * 144 * sizeof(float) <= 48 * 1024) {
+    // Small launches (the first four stages of a VAR pass) are latency-bound: the first layout has no
+    // shared-memory table to build and twice as many lane sets per chunk, and is 5-35 % faster there
+    // (profiles/r1_stagebench.txt); from ~25 k chunks on the second layout wins (fewer instructions).
+    const bool small = mod == nullptr && n_rows * size_t(cpr) <= 24576;
+    if (!small && size_t(cpr) * 144 * sizeof(float) <= 48 * 1024) {
         const size_t n_chunks = n_rows * size_t(cpr);
         const unsigned grid = grid_for(n_chunks, 64, 4);              // 8 warps x 8 chunks per block and trip
         const size_t smem = size_t(cpr) * 144 * sizeof(float);
@@ -353,7 +364,7 @@ static int launch_rotate_quant(const float* x, const Modulate* mod, const float*
     sets_per_col = (n_rows + trips - 1) / trips;
     const size_t n_sets = sets_per_col * size_t(cpr);
     const unsigned grid = unsigned((n_sets + 31) / 32);            // 32 lane sets per 256-thread block
-#define FPQ_TRQ(F, Q) transform_rotate_quant_kernel<F, Q><<<grid, 256, 0, st>>>(x, smooth, sm, o, rot, n_rows, cpr, sets_per_col)
+#define FPQ_TRQ(F, Q) launch_pdl(transform_rotate_quant_kernel<F, Q>, grid, 256, 0, st, x, smooth, sm, o, rot, n_rows, cpr, sets_per_col)
     switch (format) {
         case -1: FPQ_TRQ(0, false); break;
         case FPQ_FMT_E2M1: FPQ_TRQ(FPQ_FMT_E2M1, true); break;

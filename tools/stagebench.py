@@ -7,6 +7,9 @@ import torch
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+from fpqvar_b200 import _lib as _L  # noqa: E402
+if os.environ.get("FPQ_LIB_PATH"):
+    _L.LIB_PATH = os.environ["FPQ_LIB_PATH"]
 from fpqvar_b200.hotpath import DeviceReplay  # noqa: E402
 from fpqvar_b200.var_workload import WORKLOADS  # noqa: E402
 
