@@ -17,8 +17,13 @@ namespace fpq {
 #ifndef FPQ_SPLIT_PREFETCH
 #define FPQ_SPLIT_PREFETCH 0
 #endif
-constexpr int H16_LPG = 4;          // lanes per 128-group
-constexpr int H16_NV = 4;           // 16-byte vectors per lane and group: 32 halves = 16 packed words per lane
+// lanes per 128-group.  Measured: 2 lanes x 64 halves is slower (sign-split 5.36 vs 6.40 TB/s burst, 5.30 vs 5.66 sustained;
+// symmetric 5.59 vs 6.34): a warp-wide load then touches 16 groups x 32 bytes instead of 8 x 64.
+#ifndef FPQ_H16_LPG
+#define FPQ_H16_LPG 4
+#endif
+constexpr int H16_LPG = FPQ_H16_LPG;          // lanes per 128-group
+constexpr int H16_NV = 16 / H16_LPG;   // 16-byte vectors per lane and group (4 lanes: 32 halves = 16 packed words per lane)
 constexpr int H16_NW = 4 * H16_NV;
 constexpr int H16_GPW = 32 / H16_LPG;   // groups per warp and loop trip
 
