@@ -227,6 +227,39 @@ class Arena:
         return p
 
 
+def config1_extra(torch, lib, dev, side):
+    """BASELINE configs[0]: per-group (g=128) fp_e2 fake-quant of a synthetic fp32 4096x4096 tensor -- this library on the GPU
+    (8 rotating buffer pairs = 1 GiB, so L2 cannot serve repeats) next to the CPU port of the reference's torch path
+    (fp_quant_e2_per_group, argmin rule) on the same tensor."""
+    import numpy as np
+    from oracle import port as P
+    n = 4096 * 4096
+    xs = [torch.randn(4096, 4096, device=dev) for _ in range(8)]
+    os_ = [torch.empty_like(t) for t in xs]
+    out = {}
+    for tie_name, tie in (("kernel_rule", 0), ("argmin_rule", 1)):
+        with torch.cuda.stream(side):
+            for i in range(8):
+                lib.fpq_fake_quant(xs[i].data_ptr(), os_[i].data_ptr(), n // 128, 128, 0, 0, 0, tie, 0, side.cuda_stream)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(side)
+            for i in range(64):
+                lib.fpq_fake_quant(xs[i % 8].data_ptr(), os_[i % 8].data_ptr(), n // 128, 128, 0, 0, 0, tie, 0, side.cuda_stream)
+            e1.record(side)
+            side.synchronize()
+        out[f"gpu_GBps_{tie_name}"] = 64 * n * 8 / (e0.elapsed_time(e1) / 1e3) / 1e9
+    xh = xs[0].cpu().numpy()
+    P.fake_quant(xh, "e2m1", 128, "argmin")
+    t0 = time.perf_counter()
+    for _ in range(3):
+        P.fake_quant(xh, "e2m1", 128, "argmin")
+    t_cpu = (time.perf_counter() - t0) / 3
+    out["cpu_port_GBps_argmin_rule"] = n * 8 / t_cpu / 1e9
+    out["cpu_cores"] = P.num_threads()
+    out["workload"] = "fp32 4096x4096, g=128, fp_e2 (134 MB algorithmic per call)"
+    return out
+
+
 def main():
     args = parse_args()
     from fpqvar_b200.var_workload import WORKLOADS
@@ -438,6 +471,7 @@ def main():
         if world == 1 and not args.no_cpu:
             base, _, _ = cpu_baseline(hot, args.cpu_seconds)
             line["cpu_baseline"] = base
+            line["config1"] = config1_extra(torch, lib, dev, side)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

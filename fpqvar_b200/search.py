@@ -44,6 +44,40 @@ def quantize(x, fmt: str, per: str = "group"):
     return ops.fake_quant(x, fmt, 128 if per == "group" else None, "kernel", out_dtype=out_dtype)
 
 
+class FPQuant(torch.autograd.Function):
+    """search_fp4_format.py:340-374 (also the GALT trainers): whole-tensor clip, per-group absmax scale, argmin
+    rounding onto e1m2 / e2m1 / e3m0, straight-through gradient."""
+
+    @staticmethod
+    def forward(ctx, x, n_bits=4, group_size=128, format=None, clipping_strength=1.0):
+        assert n_bits == 4
+        if format not in FP4_FORMATS:
+            raise ValueError("Unsupported format type")
+        clip_value = clipping_strength * x.abs().max()                     # identity at 1.0 for finite data; NaN poisons, as in the reference
+        x = torch.clamp(x, -clip_value, clip_value)
+        return ops.fake_quant(x, format, group_size, "argmin")
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output.clone(), None, None, None, None
+
+
+class FPQuant_e1m2_neg_e2m1_pos(torch.autograd.Function):
+    """search_fp4_format.py:378-422: the sign-split fc2 format with argmin rounding, straight-through gradient."""
+
+    @staticmethod
+    def forward(ctx, x, n_bits=4, group_size=128, clipping_strength=1.0):
+        assert n_bits == 4
+        if clipping_strength != 1.0:
+            clip_value = clipping_strength * x.abs().max()
+            x = torch.clamp(x, -clip_value, clip_value)
+        return ops.fake_quant_signsplit(x, "e1m2_neg_e2m1_pos", group_size, "argmin", global_clip=True)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        return grad_output.clone(), None, None, None
+
+
 def compute_quant_error(x_fp, x_quant):
     """search_fp4_format.py:472-476."""
     return torch.mean((x_fp - x_quant) ** 2)

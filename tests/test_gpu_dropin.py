@@ -221,3 +221,24 @@ def test_search_layer_and_tensor_scores():
     assert res[0]["weight_format"] == best["weight_format"] and res[0]["activation_format"] == best["activation_format"]
     with pytest.raises(NotImplementedError):
         search.fp4_quant(w, "e5m9")
+
+
+def test_fpquant_autograd_functions():
+    """search_fp4_format.py:340-422 FPQuant / FPQuant_e1m2_neg_e2m1_pos: argmin rounding forward, straight-through backward."""
+    from fpqvar_b200 import search
+    torch.manual_seed(8)
+    x = (torch.randn(32, 256, device="cuda") * 2).requires_grad_()
+    for fmt in search.FP4_FORMATS:
+        y = search.FPQuant.apply(x, 4, 128, fmt, 1.0)
+        want = O.fake_quant(x.detach().cpu().numpy(), fmt, 128, "argmin")
+        assert bits_equal(y.detach().cpu().numpy(), want), fmt
+    y.sum().backward()
+    assert torch.equal(x.grad, torch.ones_like(x))
+    h = torch.nn.functional.gelu(torch.randn(32, 256, device="cuda")).requires_grad_()
+    z = search.FPQuant_e1m2_neg_e2m1_pos.apply(h, 4, 128, 1.0)
+    want = O.fake_quant_signsplit(h.detach().cpu().numpy(), "e1m2_neg_e2m1_pos", 128, "argmin")
+    assert bits_equal(z.detach().cpu().numpy(), want)
+    (z * 2).sum().backward()
+    assert torch.equal(h.grad, torch.full_like(h, 2.0))
+    with pytest.raises(ValueError):
+        search.FPQuant.apply(x, 4, 128, "e5m2", 1.0)
