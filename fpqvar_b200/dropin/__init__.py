@@ -11,8 +11,9 @@ import sys
 
 def install(overwrite: bool = True) -> None:
     from . import quant_cuda
-    from .. import quant_utils, rotation_utils, transform_model_utils
+    from .. import block_rotation_utils, hadamard_utils, quant_utils, rotation_utils, transform_model_utils
     for name, mod in (("quant_cuda", quant_cuda), ("quant_utils", quant_utils), ("rotation_utils", rotation_utils),
+                      ("block_rotation_utils", block_rotation_utils), ("hadamard_utils", hadamard_utils),
                       ("transform_model_utils", transform_model_utils)):
         if overwrite or name not in sys.modules:
             sys.modules[name] = mod

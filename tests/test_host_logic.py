@@ -108,6 +108,14 @@ def test_block_hadamard_matrix_matches_reference_fixture(golden):
     torch.randint(low=0, high=2, size=(128,))
     assert torch.equal(a, torch.rand(3))
     assert torch.equal(R.block_random_hadamard_matrix(256, 128, "cpu", 42, force_identity=True), torch.eye(256, dtype=torch.float64))
+    # hadamard_utils mirror: the reference's butterfly builds the same matrix; non power-of-two sizes are out of scope
+    from fpqvar_b200 import hadamard_utils as H, block_rotation_utils as BR
+    signs = R.sign_vector(128, 42)
+    q128 = H.matmul_hadU(torch.diag(signs))
+    assert np.array_equal(q128.numpy().view(np.uint64), golden["rot/q256"][:128, :128].view(np.uint64))
+    assert H.get_hadK(128) == (None, 1) and BR.rotate_model is R.rotate_model
+    with pytest.raises(NotImplementedError):
+        H.matmul_hadU(torch.zeros(2, 1920, dtype=torch.float64))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -177,7 +185,8 @@ def test_quantized_linear_dispatch_and_errors():
 def test_dropin_install_registers_reference_module_names():
     import sys
     import fpqvar_b200.dropin as dropin
-    saved = {k: sys.modules.get(k) for k in ("quant_cuda", "quant_utils", "rotation_utils", "transform_model_utils")}
+    saved = {k: sys.modules.get(k) for k in ("quant_cuda", "quant_utils", "rotation_utils", "transform_model_utils",
+                                             "block_rotation_utils", "hadamard_utils")}
     try:
         dropin.install()
         import quant_cuda
