@@ -111,3 +111,43 @@ def test_results_identical_without_pdl():
         env = dict(os.environ, **env_extra)
         outs.append(subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300).stdout.strip())
     assert outs[0] and outs[0] == outs[1], outs
+
+
+def test_randomized_differential_against_oracle(ops):
+    """60 random (shape, dtype, format, tie, scale distribution) cases against the oracle -- a cheap fuzz of the dispatch
+    (group kernels, packed fp16 path, row-in-registers kernels, two-pass fallback)."""
+    rng = np.random.default_rng(20261018)
+    syms = ["e2m1", "e1m2", "e3m0", "e2m3", "e3m2"]
+    splits = ["e1m2_neg_e2m1_pos", "int_neg_e2m3_pos", "afpq_e2m1"]
+    for case in range(60):
+        dt = [torch.float16, torch.float32][int(rng.integers(2))]
+        per_row = bool(rng.integers(2))
+        if per_row:
+            row_len = int(rng.choice([64, 96, 128, 200, 256, 520, 1024, 1920, 3000, 4608, 8192, 9216, 20000]))
+            rows = int(rng.integers(1, 40))
+            shape, group = (rows, row_len), None
+        else:
+            group = int(rng.choice([32, 64, 128, 128, 128, 256]))
+            shape, _ = (int(rng.integers(1, 300)), group * int(rng.integers(1, 20))), None
+        x = rng.standard_normal(shape).astype(np.float32) * np.exp(rng.uniform(-6, 4, (shape[0], 1))).astype(np.float32)
+        kind = int(rng.integers(4))
+        if kind == 0:
+            x = np.where(x > 0, x, x * 0.03).astype(np.float32)          # GELU-like skew
+        elif kind == 1:
+            x[rng.integers(shape[0])] = 0.0
+        elif kind == 2 and x.size > 10:
+            x.reshape(-1)[rng.integers(x.size)] = [np.nan, np.inf, -np.inf][int(rng.integers(3))]
+        with np.errstate(over="ignore"):
+            xh = x.astype(NP[dt])
+        xt = torch.from_numpy(xh).cuda()
+        tie = ["kernel", "argmin"][int(rng.integers(2))]
+        if rng.integers(3) == 0:
+            fmt = splits[int(rng.integers(3))]
+            want = O.fake_quant_signsplit(xh, fmt, group, tie, clipping_strength=None)
+            got = host(ops.fake_quant_signsplit(xt, fmt, group, tie))
+        else:
+            fmt = syms[int(rng.integers(5))]
+            clamp3 = bool(rng.integers(2)) and tie == "argmin"
+            want = O.fake_quant(xh, fmt, group, tie, clamp3=clamp3)
+            got = host(ops.fake_quant(xt, fmt, group, tie, clamp3=clamp3))
+        assert bits_equal(got, want), f"case {case}: {shape} {dt} group={group} {fmt} {tie}\n" + mismatch_report(got, want)
