@@ -233,12 +233,13 @@ template <typename InT> __device__ __forceinline__ bool scale_regular(float s) {
 // dtype) and r = RN(1/s).
 //
 // fp16 tensors: the reference computes v = half(float(x)/float(s)).  For 11-bit operands
-//   x*RN(1/s) is within 2^-23 (relative) of x/s while x/s is either farther than that from
-//   every fp16 rounding boundary or not near one at all (a quotient of two 11-bit integers
-//   cannot sit closer than 1/(2^11 * 2^12) to a 12-bit midpoint without being equal to it,
-//   and it cannot be equal) -- so half(x*r) == half(x/s) for every input.  DESIGN.md, "fp16
-//   contract", has the derivation; tests/test_gpu_exhaustive.py checks all 2^16 x for a sweep
-//   of scales.
+//   x*RN(1/s) is within 2^-23 (relative) of x/s, while a quotient of two 11-bit integers cannot sit
+//   closer than 1/(2^11 * 2^12) (relative) to a 12-bit rounding boundary without being equal to it,
+//   and it cannot be equal -- so half(x*r) == half(x/s) whenever the quotient is a NORMAL fp16
+//   number.  Among subnormal quotients (|v| < 2^-14) x/s can be an exact tie (3*2^-24 / 6 = 2^-25)
+//   and the two may round to neighbouring subnormals; both lie far below the first grid midpoint of
+//   every format, so the grid value is the same.  fpq_selftest_f16_flow (fpq_h16.cu) compares the
+//   final outputs of this path with the literal sequence for EVERY (x, scale) pair of fp16 values.
 // fp32 tensors: v = x/s in fp32.  x*r is within 2 ulp of it; the closed-form rounding reports
 //   when its argument is within 32 ulp of a decision boundary and only those elements pay for
 //   an IEEE division.

@@ -2,7 +2,7 @@
 // rotated models: fp16 in, fp16 out).
 //
 // The generic path (fpq_common.cuh) spends ~20-38 instructions per element and is issue-bound on
-// B200 (ncu: 85 % issue-slot utilisation at 36 % DRAM, profiles/r1_baseline_ncu.md).  At 4 bytes per
+// B200 (ncu: 85 % issue-slot utilisation at 36 % DRAM, profiles/r1a_generic_kernels_ncu.txt).  At 4 bytes per
 // element the HBM roofline leaves ~20 issue slots per element, so this path is written for
 // instruction count (~8 per element):
 //   * two elements per instruction wherever the ISA allows it: FMUL2 / FFMA2 (packed fp32,

@@ -175,7 +175,7 @@ FPQ_API int fpq_score_formats(const void *x, size_t n_rows, size_t row_len, int 
 
 /*
  * Exhaustive self-check used by the GPU test-suite: for ALL 2^32 fp32 bit patterns compare the
- * closed-form rounding of `format` (FPQ_FMT_* or 16+half-grid id, see fpq_kernels.cu) under
+ * closed-form rounding of `format` (FPQ_FMT_* or 16+half-grid id, 16 = int_neg, 17 = e2m3_pos, 18 = e1m2_neg, 19 = e2m1_pos, 20 = e2m1_neg; fpq_grid.cu) under
  * `tie_mode` with the literal reference scan over the same grid.  result[0] = mismatch count,
  * result[1] = bit pattern of the first mismatch found (device memory, 2 x uint64).
  */
