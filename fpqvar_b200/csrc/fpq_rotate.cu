@@ -11,6 +11,7 @@
 // chunk, so the seven index bits split as k (2 bits, in registers), l (3 bits, across lanes:
 // shfl.xor 1,2,4) and j (2 bits, in registers).  A Sylvester Hadamard transform is the tensor
 // product of a 2-point butterfly over every index bit, in any order (here: 0, 1, 4, 5, 6, 2, 3, in both layouts).
+#include <cstdlib>
 #include "fpq_h16.cuh"
 
 #ifndef FPQ_ROT_V2
@@ -21,6 +22,9 @@ namespace fpq {
 
 struct SignMask { uint32_t w[4]; };    // bit e of the 128-bit mask set  <=>  sigma[e] = +1
 
+// adaLN modulate operands (fpq_modulate_transform_rotate_quant): t = (x * (scale[b, c] + 1) + shift[b, c]) * smooth[c]
+struct Modulate { const float* scale; const float* shift; size_t rows_per_batch; };
+
 // 1 / fl32(sqrt(128)), rounded to fp32 (0x3DB504F3)
 __device__ __forceinline__ float inv_sqrt128() { return __uint_as_float(0x3DB504F3u); }
 
@@ -28,10 +32,13 @@ __device__ __forceinline__ float inv_sqrt128() { return __uint_as_float(0x3DB504
 // smooth*sign multipliers are loaded once and live in registers) and walks down the rows
 // k, k+K, k+2K, ... of that chunk column.  Arithmetic is two elements per instruction where the
 // ISA allows (FMUL2/FFMA2/FADD2 packed fp32, sm_100): P[2j] = (v[4j], v[4j+1]), P[2j+1] = (v[4j+2], v[4j+3]).
-template <int FMT, bool QUANT>
+// MOD (adaLN modulate fused in): a lane set walks CONTIGUOUS rows (k0*R .. k0*R + R - 1) instead of strided ones, so the
+// (scale+1) and shift values of its column change only when the batch index does and live in registers in between --
+// read from L2 once per (batch, column, row range) instead of once per chunk.
+template <int FMT, bool QUANT, bool MOD>
 __global__ void __launch_bounds__(256) transform_rotate_quant_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
                                                                      SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
-                                                                     size_t n_rows, int cpr, size_t sets_per_col) {
+                                                                     size_t n_rows, int cpr, size_t sets_per_col, Modulate mod) {
     constexpr int LPG = 8;
     pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
@@ -63,9 +70,11 @@ __global__ void __launch_bounds__(256) transform_rotate_quant_kernel(const float
 
     // uniform trip count across the warp (the shuffles need every lane)
     const size_t trips = (n_rows + sets_per_col - 1) / sets_per_col;
+    uint64_t A[MOD ? 8 : 1], SH[MOD ? 8 : 1];         // (scale + 1) and shift of this lane's 16 columns for batch cur_b
+    size_t cur_b = ~size_t(0);
     pdl_wait();                                       // smooth / sign mask are parameters; x may come from the previous kernel
     for (size_t t = 0; t < trips; ++t) {
-        const size_t row = k0 + t * sets_per_col;
+        const size_t row = MOD ? k0 * trips + t : k0 + t * sets_per_col;
         const bool valid = active && row < n_rows;
         const size_t off = row * row_stride + size_t(cc) * 128;
         uint64_t P[8];
@@ -79,6 +88,30 @@ __global__ void __launch_bounds__(256) transform_rotate_quant_kernel(const float
         } else {
 #pragma unroll
             for (int i = 0; i < 8; ++i) P[i] = 0ull;
+        }
+        if constexpr (MOD) {
+            const size_t b = valid ? row / mod.rows_per_batch : cur_b;
+            if (b != cur_b) {
+                cur_b = b;
+                const size_t mo = b * row_stride + size_t(cc) * 128;
+                const uint64_t one2 = pk(1.0f, 1.0f);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 sc = __ldg(reinterpret_cast<const float4*>(mod.scale + mo + (j * LPG + lig) * 4));
+                    const float4 sh = __ldg(reinterpret_cast<const float4*>(mod.shift + mo + (j * LPG + lig) * 4));
+                    A[2 * j] = fadd2(pk(sc.x, sc.y), one2);               // scale.add(1)
+                    A[2 * j + 1] = fadd2(pk(sc.z, sc.w), one2);
+                    SH[2 * j] = pk(sh.x, sh.y);
+                    SH[2 * j + 1] = pk(sh.z, sh.w);
+                }
+            }
+            // .mul(scale.add(1)).add_(shift): the product with the SCALAR mul.rn.f32 (never contracted; ptxas fuses
+            // mul.rn.f32x2 + add.rn.f32x2 into one FFMA2, which would skip the rounding of the product)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const F2 xv = unpk(P[i]), av = unpk(A[i]);
+                P[i] = fadd2(pk(__fmul_rn(xv.lo, av.lo), __fmul_rn(xv.hi, av.hi)), SH[i]);
+            }
         }
         // x * (s * sigma): basic_var.py:263 `.mul(s)` in fp32, then the sign row of Q
 #pragma unroll
@@ -147,7 +180,6 @@ __global__ void __launch_bounds__(256) transform_rotate_quant_kernel(const float
 // MOD: the adaLN modulate in front of it is fused as well (basic_var.py:263,266):
 //     t = (x * (scale[b, c] + 1) + shift[b, c]) * smooth[c]        b = row / rows_per_batch
 // as four separately rounded fp32 operations, exactly the reference's `.mul(scale.add(1)).add_(shift).mul(s)`.
-struct Modulate { const float* scale; const float* shift; size_t rows_per_batch; };
 
 template <int FMT, bool QUANT, bool MOD>
 __global__ void __launch_bounds__(256) transform_rotate_quant_v2_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
@@ -331,8 +363,11 @@ static int launch_rotate_quant(const float* x, const Modulate* mod, const float*
     // Small launches (the first four stages of a VAR pass) are latency-bound: the first layout has no
     // shared-memory table to build and twice as many lane sets per chunk, and is 5-35 % faster there
     // (profiles/r1_stagebench.txt); from ~25 k chunks on the second layout wins (fewer instructions).
-    const bool small = mod == nullptr && n_rows * size_t(cpr) <= 24576;
-    if (!small && size_t(cpr) * 144 * sizeof(float) <= 48 * 1024) {
+    const bool small = n_rows * size_t(cpr) <= 24576;
+    // FPQ_ROT_MOD_V2=1 keeps the second layout for the modulate variant too (it re-reads scale/shift per chunk through L1:
+    // 3.6 TB/s-equivalent against the register-table variant of the first layout, see profiles/r1_kbench.txt)
+    static const bool mod_v2 = getenv("FPQ_ROT_MOD_V2") != nullptr;
+    if (!small && (mod == nullptr || mod_v2) && size_t(cpr) * 144 * sizeof(float) <= 48 * 1024) {
         const size_t n_chunks = n_rows * size_t(cpr);
         const unsigned grid = grid_for(n_chunks, 64, 4);              // 8 warps x 8 chunks per block and trip
         const size_t smem = size_t(cpr) * 144 * sizeof(float);
@@ -352,9 +387,9 @@ static int launch_rotate_quant(const float* x, const Modulate* mod, const float*
         return finish_launch();
     }
 #endif
-    if (mod != nullptr) return FPQ_ERR_UNSUPPORTED;                  // rows wider than 10 922 columns: first layout has no modulate variant
-    // first layout: lane sets, one per (chunk column, row phase); enough to fill every SM's 2048 thread slots
-    const size_t max_sets = size_t(sm_count()) * 2048 / 8;
+    // first layout: lane sets, one per (chunk column, row phase); enough to fill every SM's thread slots (the
+    // modulate variant holds three operand tables in registers: 2 resident CTAs instead of 4)
+    const size_t max_sets = size_t(sm_count()) * (mod ? 1024 : 2048) / 8;
     size_t sets_per_col = max_sets / size_t(cpr);
     if (sets_per_col < 1) sets_per_col = 1;
     if (sets_per_col > n_rows) sets_per_col = n_rows;
@@ -364,7 +399,10 @@ static int launch_rotate_quant(const float* x, const Modulate* mod, const float*
     sets_per_col = (n_rows + trips - 1) / trips;
     const size_t n_sets = sets_per_col * size_t(cpr);
     const unsigned grid = unsigned((n_sets + 31) / 32);            // 32 lane sets per 256-thread block
-#define FPQ_TRQ(F, Q) launch_pdl(transform_rotate_quant_kernel<F, Q>, grid, 256, 0, st, x, smooth, sm, o, rot, n_rows, cpr, sets_per_col)
+    const Modulate m1 = mod ? *mod : Modulate{nullptr, nullptr, 1};
+#define FPQ_TRQ(F, Q)                                                                                                                     \
+    if (mod) launch_pdl(transform_rotate_quant_kernel<F, Q, true>, grid, 256, 0, st, x, smooth, sm, o, rot, n_rows, cpr, sets_per_col, m1); \
+    else launch_pdl(transform_rotate_quant_kernel<F, Q, false>, grid, 256, 0, st, x, smooth, sm, o, rot, n_rows, cpr, sets_per_col, m1)
     switch (format) {
         case -1: FPQ_TRQ(0, false); break;
         case FPQ_FMT_E2M1: FPQ_TRQ(FPQ_FMT_E2M1, true); break;
