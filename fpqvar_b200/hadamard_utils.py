@@ -1,7 +1,7 @@
 """Drop-in mirror of the parts of rotate_utils/hadamard_utils.py the block rotation uses (power-of-two sizes).
 
-`matmul_hadU` is the reference's butterfly (hadamard_utils.py:63-85) -- host-side torch code used to BUILD
-matrices offline, not a hot-path kernel; the K != 1 Kronecker tables (had12 ... had172, lines 164-4204) belong to
+`matmul_hadU` / `random_hadamard_matrix` are host-side torch code used to BUILD matrices offline, not hot-path
+kernels; the K != 1 Kronecker tables (had12 ... had172, lines 164-4204) belong to
 the full-width rotation, which is out of scope, and raise NotImplementedError here."""
 from __future__ import annotations
 
@@ -22,19 +22,15 @@ def get_hadK(n, transpose=False):
 
 
 def matmul_hadU(X, transpose=False):
-    """X @ H_n / fl32(sqrt(n)) along the last dim by repeated (a+b, a-b) stages (hadamard_utils.py:63-85)."""
+    """X @ H_n / fl32(sqrt(n)) along the last dim, H_n the Sylvester matrix (what hadamard_utils.py:63-85 computes with
+    in-place butterflies; H_n is symmetric, so `transpose` changes nothing).  Written as one fp64 product: for the
+    +-1 diagonal inputs the rotation code feeds it, every partial sum is a small integer and the result is exact
+    either way (the block matrix equals the reference's bit for bit, tests/test_host_logic.py)."""
+    from .rotation_utils import _sylvester
     n = X.shape[-1]
     get_hadK(n, transpose)
-    inp = X.clone().reshape(-1, n, 1)
-    out = inp.clone()
-    while inp.shape[1] > 1:
-        inp = inp.view(inp.shape[0], inp.shape[1] // 2, 2, inp.shape[2])
-        out = out.view(inp.shape)
-        out[:, :, 0, :] = inp[:, :, 0, :] + inp[:, :, 1, :]
-        out[:, :, 1, :] = inp[:, :, 0, :] - inp[:, :, 1, :]
-        out = out.view(inp.shape[0], inp.shape[1], -1)
-        inp, out = out, inp
-    return inp.view(X.shape) / torch.tensor(n).sqrt()
+    h = _sylvester(n).to(device=X.device, dtype=X.dtype)
+    return (X.reshape(-1, n) @ h).view(X.shape) / torch.tensor(n).sqrt()
 
 
 def matmul_hadUt(X):

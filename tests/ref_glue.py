@@ -23,39 +23,36 @@ def load_ref_ext():
     return mod
 
 
+def _absmax_scale(t, grid):
+    return t.abs().max(dim=-1, keepdim=True)[0] / grid.abs().max()
+
+
+def _kernel_round(quant, t, grid):
+    """`.view(-1).to(float32)` -> quant_cuda.quant -> back to the group shape (quant_utils.py:323-327)."""
+    flat, _unused = quant(t.view(-1).to(torch.float32), grid.type_as(t.view(-1).to(torch.float32)))
+    return flat.view(t.shape)
+
+
 def sym_group_cuda(quant, x, grid, group_size=128, out_dtype=None):
-    quant_grid = grid.to(x.device)
-    x_shape = x.shape
-    x = x.reshape(-1, group_size)
-    x_shape_1 = x.shape
-    scale = x.abs().max(dim=-1, keepdim=True)[0] / quant_grid.abs().max()
-    x = x / scale
-    quant_array = x.view(-1).to(torch.float32)
-    quant_grid = quant_grid.type_as(quant_array)
-    quant_array, _ = quant(quant_array, quant_grid)
-    quant_array = quant_array.view(x_shape_1)
-    output = quant_array * scale
-    return output.view(x_shape).to(x.dtype if out_dtype is None else out_dtype)
+    """fp_quant_e2_per_group_cuda & friends (quant_utils.py:313-330): scale = absmax/max|grid|; x/scale; kernel; *scale."""
+    grid = grid.to(x.device)
+    groups = x.reshape(-1, group_size)
+    scale = _absmax_scale(groups, grid)
+    q = _kernel_round(quant, groups / scale, grid)
+    return (q * scale).view(x.shape).to(x.dtype if out_dtype is None else out_dtype)
 
 
 def signsplit_group_cuda(quant, x, grid_neg, grid_pos, group_size=128, clipping_strength=1.0):
-    grid_neg = grid_neg.to(x.device)
-    grid_pos = grid_pos.to(x.device)
+    """fp_quant_e1m2_neg_e2m1_pos_per_group_cuda (quant_utils.py:415-452) / fp6_quant_int_neg_e2m3_pos_per_group_cuda
+    (:577-611, clipping_strength=None): whole-tensor clip, where()-split, one scale and one kernel call per side, sum."""
+    grid_neg, grid_pos = grid_neg.to(x.device), grid_pos.to(x.device)
     if clipping_strength is not None:
-        clip_value = clipping_strength * x.abs().max()
-        x = torch.clamp(x, -clip_value, clip_value)
-    x_shape = x.shape
-    x = x.reshape(-1, group_size)
-    x_shape_1 = x.shape
-    x_neg = torch.where(x <= 0, x, torch.zeros_like(x))
-    x_pos = torch.where(x > 0, x, torch.zeros_like(x))
-    scale_neg = x_neg.abs().max(dim=-1, keepdim=True)[0] / grid_neg.abs().max()
-    scale_pos = x_pos.abs().max(dim=-1, keepdim=True)[0] / grid_pos.abs().max()
-    x_neg_normalized = (x_neg / scale_neg).view(-1).to(torch.float32)
-    x_pos_normalized = (x_pos / scale_pos).view(-1).to(torch.float32)
-    quantized_neg, _ = quant(x_neg_normalized, grid_neg)
-    quantized_pos, _ = quant(x_pos_normalized, grid_pos)
-    quantized_neg = quantized_neg.view(x_shape_1)
-    quantized_pos = quantized_pos.view(x_shape_1)
-    output = quantized_neg * scale_neg + quantized_pos * scale_pos
-    return output.view(x_shape).to(x.dtype)
+        bound = clipping_strength * x.abs().max()
+        x = torch.clamp(x, -bound, bound)
+    groups = x.reshape(-1, group_size)
+    zeros = torch.zeros_like(groups)
+    neg, pos = torch.where(groups <= 0, groups, zeros), torch.where(groups > 0, groups, zeros)
+    s_neg, s_pos = _absmax_scale(neg, grid_neg), _absmax_scale(pos, grid_pos)
+    q_neg = _kernel_round(quant, neg / s_neg, grid_neg)
+    q_pos = _kernel_round(quant, pos / s_pos, grid_pos)
+    return (q_neg * s_neg + q_pos * s_pos).view(x.shape).to(x.dtype)
