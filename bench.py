@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-generation", action="store_true",
+                    help="skip the images/sec leg (tools/var_generate.py: a full VAR generation pass around the hot path)")
+    ap.add_argument("--gen-iters", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--sample-stages", type=int, default=0,
                     help="CPU legs only: restrict the bounded sample to the first N stages (0 = all; used by the CPU unit test)")
@@ -260,6 +263,41 @@ def config1_extra(torch, lib, dev, side):
     return out
 
 
+def generation_leg(torch, dist, dev, hot, iters, rank, world):
+    """BASELINE.json's second metric: images/sec of a whole class-conditional generation pass (autoregressive pass +
+    VQVAE decode) of the workload's VAR, random-init weights, with the hot path in place — `fused` = level (c) of
+    INTEGRATION.md — next to the unquantized fp16 model.  The model around the hot path is tools/var_generate.py (a
+    measurement harness; its GEMMs / attention / convolutions are torch library calls).  Every rank runs its own
+    batches (classes sharded, no collective on the path); times are CUDA events, max over ranks."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("var_generate", os.path.join(ROOT, "tools", "var_generate.py"))
+    vg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vg)
+    res = 512 if hot.patch_nums[-1] == 32 else 256
+    bits = 6 if hot.act_fmt in ("e2m3", "e3m2") else 4
+    out = {"unit": "images/s", "model": f"VAR-d{hot.depth} {res}x{res}, B={hot.batch}/GPU, W{bits}A{bits}, random init",
+           "harness": "tools/var_generate.py", "iters": iters, "warmup": 1}
+    for mode in (("fused" if hot.rotate_transform else "modules"), "fp16"):
+        ms, err = float("nan"), None
+        try:
+            r = vg.measure(dev, hot.depth, hot.batch, res, bits, mode, iters, 1, rank, world, rotate=hot.rotate_transform)
+            ms = r["ms_per_batch"]
+            if not r["finite"]:
+                err = "non-finite image"
+        except Exception as e:  # noqa: BLE001  (reported in the JSON line; the hot-path numbers above stand on their own)
+            err = f"{type(e).__name__}: {e}"
+        t = torch.tensor([ms if err is None else float("inf")], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        worst = float(t.item())
+        if worst == float("inf"):
+            out[mode] = {"error": err or "failed on another rank"}
+        else:
+            out[mode] = {"images_per_sec": world * hot.batch / (worst / 1e3), "ms_per_batch": worst,
+                         "decode_ms_per_batch": r["decode_ms_per_batch"], "fpq_launches_per_batch": r["fpq_launches_per_batch"]}
+    return out
+
+
 def main():
     args = parse_args()
     from fpqvar_b200.var_workload import WORKLOADS
@@ -416,6 +454,11 @@ def main():
                "launches": e2e_launches}
         del pipe
 
+    # ---- images/sec: the caller around the hot path --------------------
+    generation = None
+    if not args.no_generation:
+        generation = generation_leg(torch, dist, dev, hot, args.gen_iters, rank, world)
+
     # ---- gather (the only collective) --------------------------------------------------------
     if world > 1:
         keys = sorted(fam)
@@ -468,6 +511,8 @@ def main():
         }
         if e2e is not None:
             line["e2e"] = e2e
+        if generation is not None:
+            line["generation"] = generation
         if world == 1 and not args.no_cpu:
             base, _, _ = cpu_baseline(hot, args.cpu_seconds)
             line["cpu_baseline"] = base

@@ -19,6 +19,7 @@ FMT = {"e2m1": 0, "e1m2": 1, "e3m0": 2, "e2m3": 3, "e3m2": 4}
 SPLIT = {"e1m2_neg_e2m1_pos": 0, "int_neg_e2m3_pos": 1, "afpq_e2m1": 2}
 TIE = {"kernel": 0, "argmin": 1}
 FLAG_CLAMP3, FLAG_GLOBAL_CLIP = 1, 2
+MOD_GAIN = 1                                # FPQ_MOD_GAIN (fpq_modulate_transform_rotate_quant flags)
 
 _c = ctypes
 SIGNATURES = {
@@ -33,7 +34,8 @@ SIGNATURES = {
     "fpq_transform_rotate_quant": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t,
                                               _c.c_size_t, _c.c_int, _c.c_void_p]),
     "fpq_modulate_transform_rotate_quant": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p,
-                                                       _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_void_p]),
+                                                       _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_int,
+                                                       _c.c_void_p]),
     "fpq_transform_rotate_weight": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t,
                                                _c.c_void_p]),
     "fpq_score_formats": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int,

@@ -23,7 +23,7 @@ namespace fpq {
 struct SignMask { uint32_t w[4]; };    // bit e of the 128-bit mask set  <=>  sigma[e] = +1
 
 // adaLN modulate operands (fpq_modulate_transform_rotate_quant): t = (x * (scale[b, c] + 1) + shift[b, c]) * smooth[c]
-struct Modulate { const float* scale; const float* shift; size_t rows_per_batch; };
+struct Modulate { const float* scale; const float* shift; size_t rows_per_batch; float one; };   // one: 1.0f, or -0.0f (the exact additive identity) under FPQ_MOD_GAIN
 
 // 1 / fl32(sqrt(128)), rounded to fp32 (0x3DB504F3)
 __device__ __forceinline__ float inv_sqrt128() { return __uint_as_float(0x3DB504F3u); }
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) transform_rotate_quant_kernel(const float
             if (b != cur_b) {
                 cur_b = b;
                 const size_t mo = b * row_stride + size_t(cc) * 128;
-                const uint64_t one2 = pk(1.0f, 1.0f);
+                const uint64_t one2 = pk(mod.one, mod.one);
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const float4 sc = __ldg(reinterpret_cast<const float4*>(mod.scale + mo + (j * LPG + lig) * 4));
@@ -231,7 +231,7 @@ __global__ void __launch_bounds__(256) transform_rotate_quant_v2_kernel(const fl
                 const size_t mo = moff + (j * LPG + lig) * 4;
                 const float4 sc = __ldg(reinterpret_cast<const float4*>(mod.scale + mo));
                 const float4 sh = __ldg(reinterpret_cast<const float4*>(mod.shift + mo));
-                const uint64_t one2 = pk(1.0f, 1.0f);
+                const uint64_t one2 = pk(mod.one, mod.one);
                 // .mul(scale.add(1)).add_(shift).  The product uses the SCALAR mul.rn.f32 (never contracted):
                 // ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 -- even through a *1 -- which would skip
                 // the rounding of the product that the reference's separate ATen kernels perform.
@@ -371,7 +371,7 @@ static int launch_rotate_quant(const float* x, const Modulate* mod, const float*
         const size_t n_chunks = n_rows * size_t(cpr);
         const unsigned grid = grid_for(n_chunks, 64, 4);              // 8 warps x 8 chunks per block and trip
         const size_t smem = size_t(cpr) * 144 * sizeof(float);
-        const Modulate m = mod ? *mod : Modulate{nullptr, nullptr, 1};
+        const Modulate m = mod ? *mod : Modulate{nullptr, nullptr, 1, 1.0f};
 #define FPQ_TRQ2(F, Q)                                                                                                                     \
     if (mod) launch_pdl(transform_rotate_quant_v2_kernel<F, Q, true>, grid, 256, smem, st, x, smooth, sm, o, rot, n_chunks, cpr, m);       \
     else launch_pdl(transform_rotate_quant_v2_kernel<F, Q, false>, grid, 256, smem, st, x, smooth, sm, o, rot, n_chunks, cpr, m)
@@ -399,7 +399,7 @@ static int launch_rotate_quant(const float* x, const Modulate* mod, const float*
     sets_per_col = (n_rows + trips - 1) / trips;
     const size_t n_sets = sets_per_col * size_t(cpr);
     const unsigned grid = unsigned((n_sets + 31) / 32);            // 32 lane sets per 256-thread block
-    const Modulate m1 = mod ? *mod : Modulate{nullptr, nullptr, 1};
+    const Modulate m1 = mod ? *mod : Modulate{nullptr, nullptr, 1, 1.0f};
 #define FPQ_TRQ(F, Q)                                                                                                                     \
     if (mod) launch_pdl(transform_rotate_quant_kernel<F, Q, true>, grid, 256, 0, st, x, smooth, sm, o, rot, n_rows, cpr, sets_per_col, m1); \
     else launch_pdl(transform_rotate_quant_kernel<F, Q, false>, grid, 256, 0, st, x, smooth, sm, o, rot, n_rows, cpr, sets_per_col, m1)
@@ -422,8 +422,9 @@ extern "C" int fpq_transform_rotate_quant(const float* x, const float* smooth, c
 
 extern "C" int fpq_modulate_transform_rotate_quant(const float* x, const float* scale, const float* shift, size_t rows_per_batch,
                                                    const float* smooth, const uint32_t* sign_bits_host, void* out, void* rotated,
-                                                   size_t n_rows, size_t n_cols, int format, void* stream) {
-    const Modulate m{scale, shift, rows_per_batch};
+                                                   size_t n_rows, size_t n_cols, int format, int flags, void* stream) {
+    if (flags & ~FPQ_MOD_GAIN) return FPQ_ERR_ARG;
+    const Modulate m{scale, shift, rows_per_batch, (flags & FPQ_MOD_GAIN) ? -0.0f : 1.0f};
     return launch_rotate_quant(x, &m, smooth, sign_bits_host, out, rotated, n_rows, n_cols, format, stream);
 }
 

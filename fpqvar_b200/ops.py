@@ -178,20 +178,29 @@ def transform_rotate_quant(x: torch.Tensor, smooth: Optional[torch.Tensor], sign
 def modulate_transform_rotate_quant(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, smooth: Optional[torch.Tensor], sign_bits,
                                     fmt: Optional[str], return_rotated: bool = False):
     """Fused ``((x * (scale + 1) + shift) * smooth) @ Q_block128`` -> fp16 -> per-group fake quant
-    (fpq_modulate_transform_rotate_quant).  x: fp32 [B, L, C] (LayerNorm output); scale, shift: fp32
-    broadcastable [B, 1, C] (the adaLN tensors of basic_var.py:258)."""
+    (fpq_modulate_transform_rotate_quant).  x: fp32 [B, L, C] (LayerNorm output); scale, shift:
+    broadcastable [B, 1, C] (the adaLN tensors of basic_var.py:258), fp32 or fp16.
+
+    fp16 scale / shift is what the call site sees under the reference's fp16 autocast
+    (evaluate_fp_quant_transform_rotate.py:195: ada_lin is an autocast Linear): there `scale.add(1)` is an
+    fp16 add and only its rounded result meets the fp32 LayerNorm output.  That add is done here with the
+    same ATen op on the tiny [B, 1, C] tensor and handed to the kernel as a gain (FPQ_MOD_GAIN)."""
     _require_cuda(x, "modulate_transform_rotate_quant")
     if x.dtype != torch.float32 or x.dim() < 2:
         raise L.FpqError("modulate_transform_rotate_quant: x must be float32 [B, ..., C]")
     x = x.contiguous()
     b, c = x.shape[0], x.shape[-1]
     rows_per_batch = x.numel() // (b * c) if b * c else 0
-    mods = []
     for name, t in (("scale", scale), ("shift", shift)):
         _require_cuda(t, f"modulate_transform_rotate_quant({name})")
         if t.numel() != b * c or t.shape[0] != b or t.shape[-1] != c:
             raise L.FpqError(f"{name} must be [B, 1, C] = [{b}, 1, {c}], got {tuple(t.shape)}")
-        mods.append(t.detach().to(torch.float32).contiguous())
+        if t.dtype not in (torch.float32, torch.float16):
+            raise L.FpqError(f"{name} must be float32 or float16, got {t.dtype}")
+    flags = 0
+    if scale.dtype == torch.float16:
+        scale, flags = scale.detach().add(1), L.MOD_GAIN
+    mods = [t.detach().to(torch.float32).contiguous() for t in (scale, shift)]
     if smooth is not None:
         smooth = smooth.detach().to(torch.float32).contiguous()
         if smooth.numel() != c:
@@ -202,7 +211,7 @@ def modulate_transform_rotate_quant(x: torch.Tensor, scale: torch.Tensor, shift:
         rc = L.lib().fpq_modulate_transform_rotate_quant(x.data_ptr(), mods[0].data_ptr(), mods[1].data_ptr(), rows_per_batch,
                                                          smooth.data_ptr() if smooth is not None else None, sign_bits, out.data_ptr(),
                                                          rot.data_ptr() if rot is not None else None, b * rows_per_batch, c,
-                                                         -1 if fmt is None else L.FMT[fmt], _stream(_di))
+                                                         -1 if fmt is None else L.FMT[fmt], flags, _stream(_di))
     L.check(rc, "fpq_modulate_transform_rotate_quant")
     return (out, rot) if return_rotated else out
 

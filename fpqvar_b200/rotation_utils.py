@@ -118,7 +118,8 @@ def adaln_transform_rotate_quant_activation(ln_out: torch.Tensor, scale: torch.T
                                             act_fp_type: Optional[str] = "fp_e2", sign_bits=None) -> torch.Tensor:
     """basic_var.py:263,266 in ONE kernel, adaLN modulate included:
         act_quant( matmul( ln_out.mul(scale.add(1)).add_(shift).mul(smooth), Q_block ) )
-    ln_out: fp32 [B, L, C] (`self.ln_wo_grad(x)`); scale, shift: fp32 [B, 1, C] (scale1/shift1 or scale2/shift2)."""
+    ln_out: fp32 [B, L, C] (`self.ln_wo_grad(x)`); scale, shift: [B, 1, C] (scale1/shift1 or scale2/shift2), fp32, or fp16 as
+    under the reference's fp16 autocast, where `scale.add(1)` is an fp16 add (reproduced bit for bit, see ops)."""
     fmt = {None: None, "fp_e1": "e1m2", "fp_e2": "e2m1", "fp_e3": "e3m0", "fp6_e2m3": "e2m3", "fp6_e3m2": "e3m2"}.get(act_fp_type, "?")
     if fmt == "?":
         raise ValueError("Unsupported fp_type.")

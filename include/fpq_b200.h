@@ -149,10 +149,15 @@ FPQ_API int fpq_transform_rotate_quant(const float *x, const float *smooth, cons
  * computed as the reference's four separately rounded fp32 operations, then rotated and quantized as above.
  *   x            : fp32 [n_rows, n_cols], the LayerNorm output; n_rows % rows_per_batch == 0
  *   scale, shift : fp32 [n_rows / rows_per_batch, n_cols] (the [B, 1, C] adaLN tensors), 16-byte aligned
+ *   flags        : 0, or FPQ_MOD_GAIN: `scale` already holds the gain (scale + 1).  The reference's evaluation runs
+ *                  under fp16 autocast (evaluate_fp_quant_transform_rotate.py:195), where scale1/shift1 are fp16 and
+ *                  `scale1.add(1)` is rounded to fp16 before the fp32 multiply; such a caller passes
+ *                  float(half(scale + 1)) and float(shift), both exact, and the kernel skips its own fp32 `+ 1`.
  */
+#define FPQ_MOD_GAIN 1
 FPQ_API int fpq_modulate_transform_rotate_quant(const float *x, const float *scale, const float *shift, size_t rows_per_batch,
                                         const float *smooth, const uint32_t *sign_bits_host, void *out, void *rotated,
-                                        size_t n_rows, size_t n_cols, int format, void *stream);
+                                        size_t n_rows, size_t n_cols, int format, int flags, void *stream);
 
 /*
  * Weight side of the same transform (transform_model_utils.py:8-28, rotation_utils.py:129-154):

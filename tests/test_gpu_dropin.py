@@ -242,3 +242,41 @@ def test_fpquant_autograd_functions():
     assert torch.equal(h.grad, torch.full_like(h, 2.0))
     with pytest.raises(ValueError):
         search.FPQuant.apply(x, 4, 128, "e5m2", 1.0)
+
+
+def test_var_generation_harness_modes():
+    """tools/var_generate.py: the three quantized modes run the hot path (launch counts: 4 quantizer calls per block
+    per scale) and the fused mode agrees with the module-level mode up to the fp16-GEMM vs fp32-FWHT rotation."""
+    import importlib.util
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("var_generate", os.path.join(root, "tools", "var_generate.py"))
+    vg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vg)
+    from fpqvar_b200 import ops
+    dev = torch.device("cuda")
+    outs = {}
+    for mode in ("fp16", "modules", "fused"):
+        with torch.device(dev):
+            model = vg.Var(2, (1, 2, 3, 4), False).eval()
+        model.init_weights(0)
+        vg.prepare(model, mode, 4)
+        n0 = ops.launch_count()
+        f_hat = model.generate(3, torch.tensor([1, 2, 3], device=dev), torch.Generator(device=dev).manual_seed(0))
+        assert f_hat.shape == (3, 32, 4, 4) and bool(torch.isfinite(f_hat).all())
+        assert ops.launch_count() - n0 == (0 if mode == "fp16" else 4 * 2 * 4)
+        outs[mode] = model
+    # same quantized weights in both quantized modes (transform + rotate + quantize happen offline, identically)
+    for a, b in zip(outs["modules"].blocks, outs["fused"].blocks):
+        assert torch.equal(a.attn.mat_qkv.weight, b.attn.mat_qkv.weight) and torch.equal(a.ffn.fc2.weight, b.ffn.fc2.weight)
+    # one block, same input: fused == modules up to the rotation's precision (fp16 GEMM vs fp32 butterflies)
+    x = torch.randn(6, 9, 128, device=dev)
+    cond = torch.randn(6, 128, device=dev).half()
+    ys = []
+    for mode in ("modules", "fused"):
+        m = outs[mode]
+        for blk in m.blocks:
+            blk.attn.reset_cache(6, 30, dev)
+        with torch.no_grad():
+            ys.append(m._block(0, m.blocks[0], x, cond, None))
+    assert torch.allclose(ys[0], ys[1], atol=2e-2, rtol=0)

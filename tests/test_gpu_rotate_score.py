@@ -111,6 +111,33 @@ def test_modulate_transform_rotate_quant(ops, sign_bits, B, Lr, C, fmt):
         assert bits_equal(host(fused), O.fake_quant(host(frot), fmt, 128, "kernel"))
 
 
+@pytest.mark.parametrize("B,Lr,C", [(3, 7, 256), (100, 16, 1920), (4, 33, 2304)])
+def test_modulate_with_fp16_adaln_tensors_matches_the_autocast_call_site(ops, sign_bits, B, Lr, C):
+    """Under the reference's fp16 autocast (evaluate_fp_quant_transform_rotate.py:195) scale1 / shift1 come out of an
+    autocast Linear as fp16 and `scale1.add(1)` is an fp16 add (basic_var.py:263): the fused call must reproduce
+    that rounding (FPQ_MOD_GAIN), bit for bit, including scale == -1, tiny scales (1 + s rounds to 1) and -0."""
+    g = torch.Generator(device="cuda").manual_seed(B + C)
+    x = torch.randn(B, Lr, C, device="cuda", generator=g)
+    scale = (torch.randn(B, 1, C, device="cuda", generator=g) * 0.3).half()
+    shift = (torch.randn(B, 1, C, device="cuda", generator=g) * 0.5).half()
+    scale[0, 0, :8] = torch.tensor([-1.0, 2.0 ** -12, -(2.0 ** -12), 6e-8, -6e-8, 0.0, -0.0, -1.0005], device="cuda").half()
+    shift[0, 0, :8] = torch.tensor([0.0, -0.0, 0.0, -0.0, 1.0, 0.0, -0.0, 0.0], device="cuda").half()
+    s = torch.exp(torch.rand(C, device="cuda", generator=g) * 2 - 1)
+    fused, frot = ops.modulate_transform_rotate_quant(x, scale, shift, s, sign_bits, "e2m1", return_rotated=True)
+    mod = x.mul(scale.add(1)).add_(shift)                                 # fp32 * fp16 -> fp32, as ATen promotes it
+    assert mod.dtype == torch.float32
+    two, trot = ops.transform_rotate_quant(mod, s, sign_bits, "e2m1", return_rotated=True)
+    assert torch.equal(frot.view(torch.int16), trot.view(torch.int16))
+    assert torch.equal(fused.view(torch.int16), two.view(torch.int16))
+    # and it is NOT what an fp32 `+ 1` gives wherever the fp16 add rounds: the flag matters
+    wide = ops.modulate_transform_rotate_quant(x, scale.float(), shift.float(), s, sign_bits, None)
+    assert not torch.equal(wide.view(torch.int16), frot.view(torch.int16))
+    # oracle: numpy restatement with the fp16 add
+    gain = (host(scale).astype(np.float16) + np.float16(1)).astype(np.float16).astype(np.float32)
+    mo = (host(x) * gain).astype(np.float32) + host(shift).astype(np.float32)
+    assert bits_equal(mo.astype(np.float32), host(mod))
+
+
 def test_modulate_argument_checks(ops, sign_bits):
     from fpqvar_b200._lib import FpqError
     x = torch.randn(4, 3, 256, device="cuda")

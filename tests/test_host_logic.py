@@ -263,3 +263,22 @@ def test_bench_reference_arm_json_contract():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
     assert line["config"]["workload"] == "var_d16_w4a4"
+
+
+def test_var_generation_harness_runs_on_cpu_in_fp16_mode():
+    """tools/var_generate.py (the images/sec harness): the caller-side model steps through all
+    ten scales with a KV cache and produces a finite f_hat of the right shape.  The quantized modes need the GPU
+    (tests/test_gpu_dropin.py); here only the unquantized plumbing runs."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("var_generate", os.path.join(ROOT, "tools", "var_generate.py"))
+    vg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vg)
+    import torch
+    model = vg.Var(2, (1, 2, 3, 4), False).eval()
+    model.init_weights(0)
+    for b in model.blocks:
+        for lin in (b.attn.mat_qkv, b.attn.proj, b.ffn.fc1, b.ffn.fc2, b.ada_lin):
+            lin.half()
+    f_hat = model.generate(2, torch.tensor([1, 2]), torch.Generator().manual_seed(0))
+    assert f_hat.shape == (2, 32, 4, 4) and bool(torch.isfinite(f_hat).all())
+    assert model.blocks[0].attn.cur == 1 + 4 + 9 + 16

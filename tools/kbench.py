@@ -103,7 +103,7 @@ def main():
         sc = torch.randn(B, C, device=dev) * 0.3
         sh = torch.randn(B, C, device=dev) * 0.5
         res["adaLN+rotate+quant f32->f16"] = timeit(lambda i: lib.fpq_modulate_transform_rotate_quant(
-            xf[i].data_ptr(), sc.data_ptr(), sh.data_ptr(), r4 // B, smooth.data_ptr(), sb, of[i].data_ptr(), None, r4, C, 0, st), n * 6)
+            xf[i].data_ptr(), sc.data_ptr(), sh.data_ptr(), r4 // B, smooth.data_ptr(), sb, of[i].data_ptr(), None, r4, C, 0, 0, st), n * 6)
     # generic fp32 -> fp32 group kernel (config 1 / weights)
     o32 = [torch.empty_like(t) for t in xf]
     if want("group e2m1 f32->f32"):
