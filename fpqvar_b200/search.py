@@ -5,7 +5,8 @@ Two scoring levels, as in the reference:
     loops :840-893) -- `score_tensor_formats`: ONE kernel reads x once and scores every candidate.
   * output level  mean((x W^T - x_q W_q^T)^2) over the calibration activations per (weight format,
     activation format) pair (loop :781-836) -- `search_layer`: fused quantizers + library GEMMs; y_fp is
-    computed once per activation instead of once per pair.
+    computed once per activation instead of once per pair; `search_layer_batched`: the whole calibration
+    set of a layer as one row-stacked matrix (large GEMMs, a handful of quantizer launches).
 Candidates are independent, so `search_layers` shards (layer, weight-format) units over ranks and
 gathers the small loss table at the end -- the only collective.
 """
@@ -101,6 +102,40 @@ def search_layer(weight: torch.Tensor, activations: Sequence[torch.Tensor], weig
             for wi in range(len(weight_formats)):
                 loss[wi, ai] += compute_quant_error(y_fp, torch.matmul(xq, wq[wi].T)).double()
     return loss / max(1, len(activations))
+
+
+def search_layer_batched(weight: torch.Tensor, activations: Sequence[torch.Tensor], weight_formats: Sequence[str] = FP4_FORMATS,
+                         act_formats: Sequence[str] = FP4_FORMATS, per: str = "group", max_rows: int = 32768) -> torch.Tensor:
+    """The same loss table as `search_layer`, computed on the calibration set as ONE row-stacked matrix.
+
+    Scales are shared only along the last dim (groups of 128 or whole rows), so quantizing the stacked
+    [sum_j rows_j, C_in] matrix gives every row exactly the values it gets inside its own tensor.  The
+    reference's 1000 small tensors per layer ([2, pn^2, C_in], search_fp4_format.py:781-836) then cost
+    len(act_formats) fused quantizer launches and (1 + W*A) large library GEMMs per `max_rows` slab instead
+    of ~25 launch-bound kernels per tensor.  Per-tensor means are recovered with a segment sum of per-row
+    squared errors, accumulated in float64:
+        loss[w, a] = (1/J) sum_j  SSE_rows(j) / (rows_j * C_out).
+    Differs from `search_layer` only in floating-point summation order."""
+    if not activations:
+        return torch.zeros(len(weight_formats), len(act_formats), dtype=torch.float64, device=weight.device)
+    c_in = weight.shape[1]
+    flat = [x.reshape(-1, c_in) for x in activations]
+    rows = torch.tensor([f.shape[0] for f in flat], device=weight.device)
+    X = torch.cat(flat)
+    # weight of every row in the final mean: 1 / (rows_j * C_out * J)
+    row_w = torch.repeat_interleave(1.0 / (rows.double() * weight.shape[0] * len(flat)), rows)
+    wq = [quantize(weight, wf, per).to(weight.dtype) for wf in weight_formats]
+    loss = torch.zeros(len(weight_formats), len(act_formats), dtype=torch.float64, device=weight.device)
+    for r0 in range(0, X.shape[0], max_rows):
+        xs = X[r0:r0 + max_rows]
+        ws = row_w[r0:r0 + max_rows]
+        y_fp = torch.matmul(xs, weight.T)
+        for ai, af in enumerate(act_formats):
+            xq = quantize(xs, af, per).to(xs.dtype)
+            for wi in range(len(weight_formats)):
+                d = torch.matmul(xq, wq[wi].T).sub_(y_fp)
+                loss[wi, ai] += torch.dot(d.float().square_().sum(dim=1, dtype=torch.float64), ws)
+    return loss
 
 
 def best_formats(loss: torch.Tensor, weight_formats: Sequence[str], act_formats: Sequence[str]) -> Dict[str, object]:

@@ -223,6 +223,30 @@ def test_search_layer_and_tensor_scores():
         search.fp4_quant(w, "e5m9")
 
 
+@pytest.mark.parametrize("dtype,fmts", [(torch.float32, "FP4"), (torch.float16, "FP4"), (torch.float16, "FP6")])
+def test_search_layer_batched_matches_the_per_tensor_loop(dtype, fmts):
+    """Row-stacking the calibration tensors leaves every row's quantized values unchanged (scales live on the last dim), so the
+    batched table equals the reference-order loop up to summation order; the ragged [2, pn^2, C] shapes of the reference's
+    calibration set exercise the segment means."""
+    from fpqvar_b200 import search
+    g = torch.Generator(device="cuda").manual_seed(11)
+    formats = search.FP4_FORMATS if fmts == "FP4" else search.FP6_FORMATS
+    per = "group" if fmts == "FP4" else "token"
+    w = (torch.randn(384, 256, device="cuda", generator=g) * 0.05).to(dtype)
+    acts = [torch.randn(2, pn * pn, 256, device="cuda", generator=g).to(dtype) for pn in (1, 2, 3, 4, 5, 6, 8, 10, 13, 16, 1, 3)]
+    ref = search.search_layer(w, acts, formats, formats, per)
+    for max_rows in (32768, 100):                                          # one slab / slabs that cut through tensors
+        got = search.search_layer_batched(w, acts, formats, formats, per, max_rows=max_rows)
+        assert torch.allclose(got, ref, rtol=2e-3 if dtype == torch.float16 else 1e-4, atol=0)
+        assert search.best_formats(got, formats, formats)["weight_format"] == search.best_formats(ref, formats, formats)["weight_format"]
+    # quantized rows are bit-identical whether a tensor is quantized alone or inside the stack
+    X = torch.cat([a.reshape(-1, 256) for a in acts])
+    q_stack = search.quantize(X, formats[0], per)
+    q_each = torch.cat([search.quantize(a, formats[0], per).reshape(-1, 256) for a in acts])
+    assert torch.equal(q_stack.view(torch.int16 if q_stack.dtype == torch.float16 else torch.int32),
+                       q_each.view(torch.int16 if q_each.dtype == torch.float16 else torch.int32))
+
+
 def test_fpquant_autograd_functions():
     """search_fp4_format.py:340-422 FPQuant / FPQuant_e1m2_neg_e2m1_pos: argmin rounding forward, straight-through backward."""
     from fpqvar_b200 import search

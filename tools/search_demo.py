@@ -47,6 +47,36 @@ def main():
     res = search.search_layers(layers, rank=rank, world=world)
     torch.cuda.synchronize()
     dt_s = time.perf_counter() - t0
+    # the same table with each layer's calibration set row-stacked into one matrix (large GEMMs, few launches)
+    t0 = time.perf_counter()
+    res_b = search.search_layers(layers, rank=rank, world=world, layer_fn=search.search_layer_batched)
+    torch.cuda.synchronize()
+    dt_b = time.perf_counter() - t0
+    agree = sum(a["weight_format"] == b["weight_format"] and a["activation_format"] == b["activation_format"] for a, b in zip(res, res_b))
+    rel = max(abs(a["loss"] - b["loss"]) / a["loss"] for a, b in zip(res, res_b))
+    # the reference's loop (search_fp4_format.py:798-816) with the reference's quantizer path (its glue, restated in
+    # tests/ref_glue.py, around its unmodified extension): every pair re-quantizes x and recomputes y_fp
+    dt_r = None
+    if os.environ.get("SEARCH_REF", "1") == "1" and rank == 0:
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+        import ref_glue
+        from fpqvar_b200 import quant_utils as Q
+        ext = ref_glue.load_ref_ext()
+        if ext is not None:
+            grids = {"e1m2": Q.fp4_e1m2_grid, "e2m1": Q.fp4_e2m1_grid, "e3m0": Q.fp4_e3m0_grid}
+            t0 = time.perf_counter()
+            for ly in layers:
+                w = ly["weight"]
+                for wf in search.FP4_FORMATS:
+                    wq = ref_glue.sym_group_cuda(ext.quant, w, grids[wf])
+                    for af in search.FP4_FORMATS:
+                        loss = 0.0
+                        for x in ly["activations"]:
+                            xq = ref_glue.sym_group_cuda(ext.quant, x, grids[af])
+                            loss += search.compute_quant_error(torch.matmul(x, w.T), torch.matmul(xq, wq.T))
+                        loss = float(loss / len(ly["activations"]))
+            torch.cuda.synchronize()
+            dt_r = time.perf_counter() - t0
     # tensor-level scores of the same activations (one kernel per tensor scores all three candidates)
     t1 = time.perf_counter()
     for ly in layers:
@@ -63,6 +93,8 @@ def main():
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps({"layers": len(layers), "activations_per_layer": n_act, "world": world, "output_level_search_s": round(dt_s, 3),
+                          "output_level_search_batched_s": round(dt_b, 3), "batched_same_optimum": f"{agree}/{len(res)}",
+                          "batched_max_rel_loss_diff": rel, "reference_loop_reference_quantizers_s": None if dt_r is None else round(dt_r, 3),
                           "tensor_level_scoring_s": round(dt_t, 3), "first": res[:4]}))
 
 
