@@ -10,6 +10,7 @@
 #include <cuda_fp16.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <stdlib.h>
 
 #include "../../include/fpq_b200.h"
 #include "fpq_round.cuh"
@@ -66,6 +67,39 @@ static inline unsigned grid_for(size_t work_items, size_t items_per_block, int b
     size_t cap = size_t(sm_count()) * blocks_per_sm;
     if (need < 1) need = 1;
     return unsigned(need < cap ? need : cap);
+}
+
+// Row-per-CTA persistent kernels (per_token / per_channel): how many values each thread keeps of its row (V uint4
+// vectors) and how many CTAs are REALLY resident per SM.  The grid must not exceed the resident CTAs: a persistent
+// CTA that only starts when another one has finished all of its rows runs a second, half-empty wave.
+// FPQ_ROW_V=1|2|4 overrides the choice (measurement aid; read per launch).
+static inline int row_reg_vectors(size_t row_vecs) {
+    // Small CTAs win (more rows in flight per SM, cheaper barriers): measured at equal lane use, V = 1 / 2 / 4 run at
+    // 0.67 / 0.90 / 1.00 (rows of 1920 fp16, tools/rowbench.py); weigh that against the lanes the last warp wastes.
+    int v = 1;
+    float best = 0.0f;
+    for (int c = 1; c <= 4; c *= 2) {
+        const size_t thr = (row_vecs + c - 1) / c;
+        if (thr > 1024) continue;
+        const float score = (c == 1 ? 0.67f : c == 2 ? 0.90f : 1.0f) * float(thr) / float((thr + 31) / 32 * 32);
+        if (score > best) { best = score; v = c; }
+    }
+    if (const char* e = getenv("FPQ_ROW_V")) {
+        const int f = atoi(e);
+        if ((f == 1 || f == 2 || f == 4) && (row_vecs + f - 1) / f <= 1024) v = f;
+    }
+    while ((row_vecs + v - 1) / v > 1024) v *= 2;
+    return v;
+}
+template <typename KernelT>
+static inline unsigned resident_row_grid(KernelT kernel, int threads, size_t n_rows, int* cache) {
+    int per_sm = cache[threads / 32];
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+        cache[threads / 32] = per_sm;
+    }
+    const size_t cap = size_t(sm_count()) * per_sm;
+    return unsigned(n_rows < cap ? n_rows : cap);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -311,5 +345,7 @@ __device__ __forceinline__ float block_max_nan(float a, float* smem) {
     return r;
 }
 
+// (Measured and rejected: one-barrier reductions with parity-double-buffered scratch for the persistent row kernels ran
+// 5-10 % SLOWER than the two-barrier form -- rows of 1920 / 7680 fp16, sym 5302 -> 5030, sign-split 4093 -> 3764 GB/s.)
 
 }  // namespace fpq

@@ -279,15 +279,20 @@ static bool launch_split_row_reg(const InT* xi, OutT* oo, size_t n_rows, size_t 
     if ((reinterpret_cast<uintptr_t>(xi) & 15) || (reinterpret_cast<uintptr_t>(oo) & 15)) return false;
     const size_t row_vecs = row_len / VEC;
     if (row_vecs > 4096) return false;
-    const int v = row_vecs <= 1024 ? 1 : (row_vecs <= 2048 ? 2 : 4);
+    const int v = row_reg_vectors(row_vecs);
     int threads = int((row_vecs + v - 1) / v);
     threads = (threads + 31) / 32 * 32;
-    const int ctas_per_sm = 2048 / threads > 0 ? 2048 / threads : 1;
-    const size_t cap = size_t(sm_count()) * ctas_per_sm;
-    const unsigned grid = unsigned(n_rows < cap ? n_rows : cap);
-    if (v == 1) signsplit_row_reg_kernel<InT, OutT, SPLIT, TIE, 1><<<grid, threads, 0, st>>>(xi, oo, n_rows, int(row_vecs), flag);
-    else if (v == 2) signsplit_row_reg_kernel<InT, OutT, SPLIT, TIE, 2><<<grid, threads, 0, st>>>(xi, oo, n_rows, int(row_vecs), flag);
-    else signsplit_row_reg_kernel<InT, OutT, SPLIT, TIE, 4><<<grid, threads, 0, st>>>(xi, oo, n_rows, int(row_vecs), flag);
+    static int occ[3][33];                            // resident CTAs per SM, per (V, threads / 32); 0 = not asked yet
+    if (v == 1) {
+        auto k = signsplit_row_reg_kernel<InT, OutT, SPLIT, TIE, 1>;
+        k<<<resident_row_grid(k, threads, n_rows, occ[0]), threads, 0, st>>>(xi, oo, n_rows, int(row_vecs), flag);
+    } else if (v == 2) {
+        auto k = signsplit_row_reg_kernel<InT, OutT, SPLIT, TIE, 2>;
+        k<<<resident_row_grid(k, threads, n_rows, occ[1]), threads, 0, st>>>(xi, oo, n_rows, int(row_vecs), flag);
+    } else {
+        auto k = signsplit_row_reg_kernel<InT, OutT, SPLIT, TIE, 4>;
+        k<<<resident_row_grid(k, threads, n_rows, occ[2]), threads, 0, st>>>(xi, oo, n_rows, int(row_vecs), flag);
+    }
     return true;
 }
 

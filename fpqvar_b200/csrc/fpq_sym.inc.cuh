@@ -194,7 +194,6 @@ __global__ void __launch_bounds__(1024) fake_quant_row_reg_kernel(const InT* __r
                 }
             }
         }
-        // `red` is reused by the next row's reduction: block_max_nan starts with a __syncthreads
     }
 }
 
@@ -208,15 +207,20 @@ static bool launch_row_reg(const InT* xi, OutT* oo, size_t n_rows, size_t row_le
     }
     const size_t row_vecs = row_len / VEC;
     if (row_vecs > 4096) return false;
-    const int v = row_vecs <= 1024 ? 1 : (row_vecs <= 2048 ? 2 : 4);
+    const int v = row_reg_vectors(row_vecs);
     int threads = int((row_vecs + v - 1) / v);
     threads = (threads + 31) / 32 * 32;
-    const int ctas_per_sm = 2048 / threads > 0 ? 2048 / threads : 1;
-    const size_t cap = size_t(sm_count()) * ctas_per_sm;
-    const unsigned grid = unsigned(n_rows < cap ? n_rows : cap);
-    if (v == 1) fake_quant_row_reg_kernel<InT, OutT, FMT, TIE, 1><<<grid, threads, 0, st>>>(xi, oo, n_rows, int(row_vecs), clamp3);
-    else if (v == 2) fake_quant_row_reg_kernel<InT, OutT, FMT, TIE, 2><<<grid, threads, 0, st>>>(xi, oo, n_rows, int(row_vecs), clamp3);
-    else fake_quant_row_reg_kernel<InT, OutT, FMT, TIE, 4><<<grid, threads, 0, st>>>(xi, oo, n_rows, int(row_vecs), clamp3);
+    static int occ[3][33];                            // resident CTAs per SM, per (V, threads / 32); 0 = not asked yet
+    if (v == 1) {
+        auto k = fake_quant_row_reg_kernel<InT, OutT, FMT, TIE, 1>;
+        k<<<resident_row_grid(k, threads, n_rows, occ[0]), threads, 0, st>>>(xi, oo, n_rows, int(row_vecs), clamp3);
+    } else if (v == 2) {
+        auto k = fake_quant_row_reg_kernel<InT, OutT, FMT, TIE, 2>;
+        k<<<resident_row_grid(k, threads, n_rows, occ[1]), threads, 0, st>>>(xi, oo, n_rows, int(row_vecs), clamp3);
+    } else {
+        auto k = fake_quant_row_reg_kernel<InT, OutT, FMT, TIE, 4>;
+        k<<<resident_row_grid(k, threads, n_rows, occ[2]), threads, 0, st>>>(xi, oo, n_rows, int(row_vecs), clamp3);
+    }
     return true;
 }
 
