@@ -11,6 +11,7 @@
 #include <stdint.h>
 #include <stddef.h>
 #include <stdlib.h>
+#include <math.h>
 
 #include "../../include/fpq_b200.h"
 #include "fpq_round.cuh"
@@ -73,16 +74,20 @@ static inline unsigned grid_for(size_t work_items, size_t items_per_block, int b
 // vectors) and how many CTAs are REALLY resident per SM.  The grid must not exceed the resident CTAs: a persistent
 // CTA that only starts when another one has finished all of its rows runs a second, half-empty wave.
 // FPQ_ROW_V=1|2|4 overrides the choice (measurement aid; read per launch).
-static inline int row_reg_vectors(size_t row_vecs) {
-    // Small CTAs win (more rows in flight per SM, cheaper barriers): measured at equal lane use, V = 1 / 2 / 4 run at
-    // 0.67 / 0.90 / 1.00 (rows of 1920 fp16, tools/rowbench.py); weigh that against the lanes the last warp wastes.
+static inline int row_reg_vectors(size_t row_vecs, bool heavy_loop) {
+    // Measured with tools/rowbench.py (profiles/r1_rowbench.txt).  Sign-split (heavy_loop): the smallest CTA wins at every
+    // row length (V = 1 / 2 / 4 at 0.6 / 0.8 / 1.0), weighed against the lanes the last warp wastes.  Symmetric: CTAs of
+    // 128-288 threads win (rows of 1920: V=2, 7680 / 9216: V=4); larger V on ties.
     int v = 1;
     float best = 0.0f;
     for (int c = 1; c <= 4; c *= 2) {
         const size_t thr = (row_vecs + c - 1) / c;
         if (thr > 1024) continue;
-        const float score = (c == 1 ? 0.67f : c == 2 ? 0.90f : 1.0f) * float(thr) / float((thr + 31) / 32 * 32);
-        if (score > best) { best = score; v = c; }
+        const float padded = float((thr + 31) / 32 * 32);
+        float score = float(thr) / padded;
+        if (heavy_loop) score *= (c == 1 ? 0.6f : c == 2 ? 0.8f : 1.0f);
+        else score /= 1.0f + fabsf(log2f(padded / 181.0f));
+        if (score >= best) { best = score; v = c; }
     }
     if (const char* e = getenv("FPQ_ROW_V")) {
         const int f = atoi(e);

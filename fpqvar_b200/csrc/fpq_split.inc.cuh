@@ -26,6 +26,19 @@ __device__ __forceinline__ float signsplit_elem_literal(float x, float sn, float
     return __fmul_rn(__fadd_rn(qn, qp), (x <= 0.0f) ? sn : sp);
 }
 
+// Eight fp16 elements, literal sequence under the kernel tie rule, out of line (cold path of the row kernel).
+template <int SPLIT>
+static __device__ __noinline__ uint4 signsplit_vec_literal_h16(uint4 v, float sn, float sp) {
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
+        w[q] = pack_h2(signsplit_elem_literal<__half, __half, SPLIT, TIE_KERNEL>(t.x, sn, sp),
+                       signsplit_elem_literal<__half, __half, SPLIT, TIE_KERNEL>(t.y, sn, sp));
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // Fast element: only the side the element lives on does any work; the other side
 // contributes R(0/s)*s = +0 (s regular or zero) which leaves the sum unchanged.
 template <typename InT, int SPLIT, int TIE>
@@ -136,7 +149,12 @@ __global__ void __launch_bounds__(256) signsplit_row_kernel(const InT* __restric
 // fp6_quant_int_neg_e2m3_pos_per_token_cuda qu.py:614-646): one CTA per row, V 16-byte vectors per
 // thread, one HBM pass, the next row's loads in flight during the block reduction.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void block_max2(float& a, float& b, float (&red)[64]) {
+// FPQ_ROW_BCAST=1: row scalars derived once per row by warp 0 (measured: rows of 7680 / 9216 fp16 4.59 / 4.34 -> 5.25 / 5.01 TB/s,
+// rows of 1920 unchanged); 0 keeps the every-thread form.
+#ifndef FPQ_ROW_BCAST
+#define FPQ_ROW_BCAST 1
+#endif
+__device__ __forceinline__ void block_max2(float& a, float& b, float (&red)[104]) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
@@ -155,7 +173,7 @@ __global__ void __launch_bounds__(1024) signsplit_row_reg_kernel(const InT* __re
                                                                  int row_vecs, unsigned* __restrict__ nan_flag) {
     using SF = SplitFmt<SPLIT>;
     constexpr int VEC = 16 / sizeof(InT);
-    __shared__ float red[64];
+    __shared__ float red[104];                        // warp partials (an, ap, NaN flag) + the five row scalars
     const int tid = threadIdx.x, nt = blockDim.x;
     const float delta = tie_delta_kernel(uint32_t((size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 40));
     auto load_row = [&](size_t row, uint4 (&dst)[V]) {
@@ -217,32 +235,70 @@ __global__ void __launch_bounds__(1024) signsplit_row_reg_kernel(const InT* __re
         } else {
             float_maxima();
         }
+        if (nan_flag != nullptr && has_nan) atomicOr(nan_flag, 1u);
+#if FPQ_ROW_BCAST
+        // Row scalars once per row: warp partials -> shared, warp 0 finishes the reduction and derives the scales, everybody
+        // reads five floats back (instead of every thread redoing the reduction, two IEEE divisions and two reciprocals).
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            an = fmaxf(an, __shfl_xor_sync(0xffffffffu, an, o));
+            ap = fmaxf(ap, __shfl_xor_sync(0xffffffffu, ap, o));
+        }
+        const bool warp_nan = __any_sync(0xffffffffu, has_nan);
+        const int wid = tid >> 5, lane = tid & 31, nw = (nt + 31) >> 5;
+        __syncthreads();                                   // the previous row's readers of red[] are done
+        if (lane == 0) { red[wid] = an; red[32 + wid] = ap; red[64 + wid] = warp_nan ? 1.0f : 0.0f; }
+        __syncthreads();
+        if (wid == 0) {
+            float a = lane < nw ? red[lane] : 0.0f, b = lane < nw ? red[32 + lane] : 0.0f;
+            const bool any_nan = __any_sync(0xffffffffu, lane < nw && red[64 + lane] != 0.0f);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
+                b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
+            }
+            if (lane == 0) {
+                const float sn0 = rnd_in<InT>(__fdiv_rn(a, SF::NEG::VMAX));
+                const float sp0 = rnd_in<InT>(__fdiv_rn(b, SF::POS::VMAX));
+                const bool fast0 = split_fast_ok<InT, TIE>(sn0, sp0) && !any_nan;      // rows holding a NaN take the literal sequence
+                red[96] = sn0; red[97] = sp0;
+                red[98] = (fast0 && sn0 != 0.0f) ? __frcp_rn(sn0) : 0.0f;
+                red[99] = (fast0 && sp0 != 0.0f) ? __frcp_rn(sp0) : 0.0f;
+                red[100] = fast0 ? 1.0f : 0.0f;
+            }
+        }
+        __syncthreads();
+        const float sn = red[96], sp = red[97], rn = red[98], rp = red[99];
+        const bool fast = red[100] != 0.0f;
+#else
         block_max2(an, ap, red);
         const bool row_nan = __syncthreads_or(has_nan ? 1 : 0) != 0;
-        if (nan_flag != nullptr && has_nan) atomicOr(nan_flag, 1u);
         const float sn = rnd_in<InT>(__fdiv_rn(an, SF::NEG::VMAX));
         const float sp = rnd_in<InT>(__fdiv_rn(ap, SF::POS::VMAX));
         const bool fast = split_fast_ok<InT, TIE>(sn, sp) && !row_nan;      // rows holding a NaN take the literal sequence
         const float rn = (fast && sn != 0.0f) ? __frcp_rn(sn) : 0.0f;
         const float rp = (fast && sp != 0.0f) ? __frcp_rn(sp) : 0.0f;
+#endif
         constexpr float K = SplitScale<typename SF::NEG, typename SF::POS>::K;
+        const float rnk = rn * K, snk = sn * (1.0f / K);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
             const int vi = tid + k * nt;
             if (vi >= row_vecs) continue;
             const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
             if constexpr (sizeof(InT) == 2 && sizeof(OutT) == 2 && TIE == TIE_KERNEL) {
-                uint32_t o[4];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[q]));
-                    if (fast) {
-                        o[q] = split_pair_h16_w<typename SF::NEG, typename SF::POS>(t, rn * K, sn * (1.0f / K), rp, sp, delta);
-                    } else {
-                        o[q] = pack_h2(signsplit_elem_literal<InT, OutT, SPLIT, TIE>(t.x, sn, sp), signsplit_elem_literal<InT, OutT, SPLIT, TIE>(t.y, sn, sp));
-                    }
+                // packed path; rows with an irregular scale or a NaN go through the out-of-line literal sequence (by value:
+                // registers are not addressable), so the loop the hardware fetches stays small
+                uint4 o;
+                if (fast) {
+                    o.x = split_pair_h16<typename SF::NEG, typename SF::POS>(w[0], rnk, snk, rp, sp, delta);
+                    o.y = split_pair_h16<typename SF::NEG, typename SF::POS>(w[1], rnk, snk, rp, sp, delta);
+                    o.z = split_pair_h16<typename SF::NEG, typename SF::POS>(w[2], rnk, snk, rp, sp, delta);
+                    o.w = split_pair_h16<typename SF::NEG, typename SF::POS>(w[3], rnk, snk, rp, sp, delta);
+                } else {
+                    o = signsplit_vec_literal_h16<SPLIT>(u[k], sn, sp);
                 }
-                stg_stream(orow + size_t(vi) * VEC, make_uint4(o[0], o[1], o[2], o[3]));
+                stg_stream(orow + size_t(vi) * VEC, o);
             } else {
                 float f[VEC];
 #pragma unroll
@@ -279,7 +335,7 @@ static bool launch_split_row_reg(const InT* xi, OutT* oo, size_t n_rows, size_t 
     if ((reinterpret_cast<uintptr_t>(xi) & 15) || (reinterpret_cast<uintptr_t>(oo) & 15)) return false;
     const size_t row_vecs = row_len / VEC;
     if (row_vecs > 4096) return false;
-    const int v = row_reg_vectors(row_vecs);
+    const int v = row_reg_vectors(row_vecs, true);
     int threads = int((row_vecs + v - 1) / v);
     threads = (threads + 31) / 32 * 32;
     static int occ[3][33];                            // resident CTAs per SM, per (V, threads / 32); 0 = not asked yet

@@ -97,12 +97,17 @@ __global__ void __launch_bounds__(256) fake_quant_row_kernel(const InT* __restri
 // per_channel shapes of the FP6 README configs (rows of 1920 .. 9216) when the row is 16-byte
 // aligned and fits V <= 4 vectors x 1024 threads.
 // ------------------------------------------------------------------------------------------
+// FPQ_ROW_BCAST_SYM=1: row scalars derived once per row by warp 0 (measured, rows of 2304 / 7680 / 9216 fp16:
+// 4.77 / 5.00 / 4.80 -> 5.66 / 5.59 / 5.32 TB/s); 0 keeps the every-thread form.
+#ifndef FPQ_ROW_BCAST_SYM
+#define FPQ_ROW_BCAST_SYM 1
+#endif
 template <typename InT, typename OutT, int FMT, int TIE, int V>
 __global__ void __launch_bounds__(1024) fake_quant_row_reg_kernel(const InT* __restrict__ x, OutT* __restrict__ out, size_t n_rows,
                                                                   int row_vecs, int clamp3) {
     using HG = typename SymFmt<FMT>::HG;
     constexpr int VEC = 16 / sizeof(InT);
-    __shared__ float red[32];
+    __shared__ float red[36];
     const int tid = threadIdx.x, nt = blockDim.x;
     const float delta = tie_delta_kernel(uint32_t((size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 40));
     auto load_row = [&](size_t row, uint4 (&dst)[V]) {
@@ -138,10 +143,33 @@ __global__ void __launch_bounds__(1024) fake_quant_row_reg_kernel(const InT* __r
                 }
             }
         }
+#if FPQ_ROW_BCAST_SYM
+        // row scalars once per row (see signsplit_row_reg_kernel)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a = fmax_nan(a, __shfl_xor_sync(0xffffffffu, a, o));
+        __syncthreads();
+        if ((tid & 31) == 0) red[tid >> 5] = a;
+        __syncthreads();
+        if (tid < 32) {
+            const int nw = (nt + 31) >> 5;
+            float m = tid < nw ? red[tid] : 0.0f;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) m = fmax_nan(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (tid == 0) {
+                const float s0 = rnd_in<InT>(__fdiv_rn(m, HG::VMAX));
+                const bool reg0 = scale_regular<InT>(s0);
+                red[32] = s0; red[33] = reg0 ? __frcp_rn(s0) : 0.0f; red[34] = reg0 ? 1.0f : 0.0f;
+            }
+        }
+        __syncthreads();
+        const float s = red[32], r = red[33];
+        const bool regular = red[34] != 0.0f;
+#else
         a = block_max_nan(a, red);
         const float s = rnd_in<InT>(__fdiv_rn(a, HG::VMAX));                     // quant_utils.py:505 / :239
         const bool regular = scale_regular<InT>(s);
         const float r = regular ? __frcp_rn(s) : 0.0f;
+#endif
         const GridTable& gt = c_grids[SymFmt<FMT>::GT];
 #pragma unroll
         for (int k = 0; k < V; ++k) {
@@ -207,7 +235,7 @@ static bool launch_row_reg(const InT* xi, OutT* oo, size_t n_rows, size_t row_le
     }
     const size_t row_vecs = row_len / VEC;
     if (row_vecs > 4096) return false;
-    const int v = row_reg_vectors(row_vecs);
+    const int v = row_reg_vectors(row_vecs, false);
     int threads = int((row_vecs + v - 1) / v);
     threads = (threads + 31) / 32 * 32;
     static int occ[3][33];                            // resident CTAs per SM, per (V, threads / 32); 0 = not asked yet

@@ -56,6 +56,42 @@ def test_row_kernels_every_dtype_pair(ops, row_len, din, dout):
         assert bits_equal(got, want), f"rows {row_len} {din}->{dout} {fmt}\n" + mismatch_report(got, want)
 
 
+@pytest.mark.parametrize("row_len", [256, 264, 1000, 1920, 2304, 4096, 7680, 9216, 16384, 40000])
+@pytest.mark.parametrize("din", [torch.float16, torch.float32])
+@pytest.mark.parametrize("tie", ["kernel", "argmin"])
+def test_signsplit_row_kernels(ops, row_len, din, tie):
+    """Per-token sign-split (fp6_quant_int_neg_e2m3_pos_per_token_cuda qu.py:614-646 and friends) through the
+    row-in-registers kernel (every values-per-thread choice) and the two-pass fallback: one-sided rows (a zero scale on
+    the other side), zero / NaN / +-inf rows, rows whose scales are fp16-subnormal."""
+    torch.manual_seed(row_len + 1)
+    x = (torch.randn(23, row_len, device="cuda") * torch.exp(torch.randn(23, 1, device="cuda") * 2)).to(din)
+    x[3] = 0
+    x[4] = x[4].abs()                                        # no negative element: sn = 0
+    x[5] = -x[5].abs()                                       # no positive element: sp = 0
+    x[6, 7] = float("nan")
+    x[7, 1] = float("inf")
+    x[8, row_len - 1] = float("-inf")
+    x[9] = x[9] * 1e-6                                       # scales in the fp16 subnormal range
+    x[10] = torch.where(x[10] > 0, x[10], x[10] * 0.02)      # GELU-like skew
+    for fmt in ("int_neg_e2m3_pos", "e1m2_neg_e2m1_pos"):
+        want = O.fake_quant_signsplit(host(x), fmt, None, tie, clipping_strength=None)
+        got = host(ops.fake_quant_signsplit(x, fmt, None, tie))
+        assert bits_equal(got, want), f"split rows {row_len} {din} {fmt} {tie}\n" + mismatch_report(got, want)
+
+
+@pytest.mark.parametrize("v", ["1", "2", "4"])
+def test_row_kernels_values_per_thread_override(ops, v, monkeypatch):
+    """FPQ_ROW_V (measurement aid, read per launch) must not change results."""
+    monkeypatch.setenv("FPQ_ROW_V", v)
+    torch.manual_seed(int(v))
+    for row_len in (520, 1920, 7680):
+        x = (torch.randn(9, row_len, device="cuda") * 3).half()
+        x[2, 5] = float("nan")
+        assert bits_equal(host(ops.fake_quant(x, "e2m3", None, "kernel")), O.fake_quant(host(x), "e2m3", None, "kernel"))
+        assert bits_equal(host(ops.fake_quant_signsplit(x, "int_neg_e2m3_pos", None, "kernel")),
+                          O.fake_quant_signsplit(host(x), "int_neg_e2m3_pos", None, "kernel", clipping_strength=None))
+
+
 @pytest.mark.parametrize("dt", [torch.float32, torch.float16])
 def test_unaligned_and_noncontiguous_inputs(ops, dt):
     torch.manual_seed(1)

@@ -11,6 +11,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from fpqvar_b200 import _lib as L  # noqa: E402
 
+if os.environ.get("FPQ_LIB_PATH"):                     # an alternative build (fpqvar_b200/csrc: make VARIANT=... EXTRA=...)
+    L.LIB_PATH = os.environ["FPQ_LIB_PATH"]
 lib = L.lib()
 dev = torch.device("cuda")
 st = torch.cuda.current_stream().cuda_stream
