@@ -94,3 +94,38 @@ def test_rotation_matrix(golden):
     # entries are +-1/fl32(sqrt(128)) and every block is identical
     assert np.allclose(np.abs(blk), 1.0 / float(np.sqrt(np.float32(128))), rtol=0, atol=0)
     assert np.array_equal(q[128:, 128:], blk)
+
+
+def _requantize_row_family(fmt, ai):
+    """Every fp16 x with |x| <= a (a = the ai-th positive fp16) quantized with the scale of absmax a, then quantized again
+    with the scale re-derived from the quantized absmax element.  Returns (first pass, second pass)."""
+    allpos = np.arange(0, 0x7C00, dtype=np.uint16).view(np.float16)
+    grid, vmax = O.GRIDS[fmt], np.float32(O.grid_absmax(fmt))
+
+    def q(x, s):
+        with np.errstate(all="ignore"):
+            v = (x.astype(np.float32) / np.float32(s)).astype(np.float16)
+            return (O.scan_quant(v.astype(np.float32), grid) * np.float32(s)).astype(np.float16)
+
+    a = allpos[ai]
+    x = allpos[:ai + 1]
+    with np.errstate(all="ignore"):
+        y = q(x, (np.float32(a) / vmax).astype(np.float16))
+        a2 = np.max(np.abs(y))
+        y2 = q(y, (np.float32(a2) / vmax).astype(np.float16))
+    return y, y2
+
+
+@pytest.mark.parametrize("fmt", ["e2m3", "e2m1"])
+def test_requantization_is_idempotent(fmt):
+    """Why the KV cache may be quantized incrementally (fpqvar_b200/kv_cache.py): the reference re-quantizes the whole
+    cache at every scale (basic_var.py:192-200), and a second pass over quantized rows is the identity.  The exhaustive
+    run over every (absmax, x) pair is tools/idempotence_check.py; this is every 61st absmax plus the known exceptions."""
+    for ai in list(range(128, 0x7BFF, 61)) + [0x7BFE]:
+        y, y2 = _requantize_row_family(fmt, ai)
+        assert bits_equal(y, y2), f"{fmt}: absmax index {ai}"
+    # the exceptions: deep-subnormal scales and the overflowing absmax 65504
+    for ai in {"e2m3": (57, 64, 65, 72, 79, 94, 0x7BFF), "e2m1": (9, 0x7BFF)}[fmt]:
+        y, y2 = _requantize_row_family(fmt, ai)
+        assert not bits_equal(y, y2), f"{fmt}: absmax index {ai} was expected to drift"
+    assert float(np.arange(0, 0x7C00, dtype=np.uint16).view(np.float16)[94]) < 2.0 ** -17      # the guard of kv_cache.py covers them
