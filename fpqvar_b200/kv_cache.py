@@ -11,8 +11,10 @@ schedule, where 424 suffice if each row is quantized once.  That is bit-identica
 quantizer is IDEMPOTENT: a second pass re-derives the same scale from the quantized absmax element and maps every value to
 itself.  Checked exhaustively against the oracle for every fp16 (absmax, x) pair (tools/idempotence_check.py); the only
 exceptions are rows whose absmax is below 2^-17 (scales in the deep fp16-subnormal range) or equal to 65504 (the quantized
-absmax overflows to inf).  `IncrementalKVQuant` watches for those rows on the device and, if one ever appears, `exact` turns
-False: the caller can then redo the pass with `incremental=False`, which is the reference's schedule verbatim.
+absmax overflows to inf).  Such rows are recognisable afterwards (a quantized row with 0 < absmax < 2^-16, or a non-finite
+value): `IncrementalKVQuant.exact` scans the finished cache once and reports them, and the caller can redo the pass with
+`incremental=False`, which is the reference's schedule verbatim.  Nothing is checked inside `append` (a per-append check
+costs more launches than the quantizer itself on the launch-bound early scales).
 
 Layout: the appended dimension must be the outermost after the batch ("BLHc", what the reference's flash-attention path
 uses, dim_cat=1): then per-token rows of 64 (kv_bit=6) and groups of 128 along the flattened head dims (kv_bit=4) never
@@ -26,8 +28,7 @@ import torch
 
 from . import quant_utils
 
-_TINY = 2.0 ** -17          # below this absmax a row is not idempotent under e2m3 (5.6e-6) / e2m1 (5.4e-7)
-_HUGE = 65504.0
+_TINY = 2.0 ** -16          # rows that drift have absmax <= 5.6e-6 (e2m3) / 5.4e-7 (e2m1) before AND after quantization: < 2^-17
 
 
 def _quant(t: torch.Tensor, kv_bit: int) -> torch.Tensor:
@@ -56,26 +57,22 @@ class IncrementalKVQuant:
         self.v: Optional[torch.Tensor] = None
         self.cur = 0            # tokens in the cache
         self.done = 0           # tokens already quantized
-        self._suspect: Optional[torch.Tensor] = None      # device flag: a row outside the idempotent range was quantized
 
     def reset(self):
         self.cur = self.done = 0
-        if self._suspect is not None:
-            self._suspect.zero_()
 
     @property
     def exact(self) -> bool:
-        """False if a row outside the proven-idempotent range went through the incremental schedule (reads a device flag:
-        call it once, after the pass)."""
-        return self._suspect is None or not bool(self._suspect.item())
-
-    def _watch(self, t: torch.Tensor):
-        if self.kv_bit == 6:
-            amax = t.abs().amax(dim=-1)
-        else:
-            amax = t.reshape(-1, 128).abs().amax(dim=-1)
-        bad = ((amax < _TINY) & (amax > 0)) | (amax >= _HUGE) | torch.isnan(amax)
-        self._suspect |= bad.any()
+        """True if every row quantized so far lies in the range where one pass equals the reference's repeated passes.
+        Scans the quantized part of the cache (a few reductions and one host read): call it once, after the pass."""
+        if not self.incremental or self.k is None or self.done == 0:
+            return True
+        bad = False
+        for buf in (self.k, self.v):
+            part = buf[:, :self.done]
+            amax = (part.abs().amax(dim=-1) if self.kv_bit == 6 else part.reshape(-1, 128).abs().amax(dim=-1)).float()
+            bad = bad | (((amax < _TINY) & (amax > 0)) | ~torch.isfinite(amax)).any()
+        return not bool(bad)
 
     def append(self, k: torch.Tensor, v: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         if k.shape != v.shape or k.dim() != 4 or k.dtype != torch.float16:
@@ -86,7 +83,6 @@ class IncrementalKVQuant:
         if self.k is None or self.k.shape[0] != B or self.k.shape[2:] != (H, hd) or self.k.device != k.device:
             self.k = torch.empty(B, self.max_len, H, hd, dtype=torch.float16, device=k.device)
             self.v = torch.empty_like(self.k)
-            self._suspect = torch.zeros((), dtype=torch.bool, device=k.device)
             self.cur = self.done = 0
         if self.cur + l > self.max_len:
             raise ValueError(f"cache overflow: {self.cur} + {l} > {self.max_len}")
@@ -94,8 +90,6 @@ class IncrementalKVQuant:
             lo = self.done if self.incremental else 0
             for buf in (self.k, self.v):
                 part = buf[:, lo:self.cur]
-                if self.incremental:
-                    self._watch(part)
                 part.copy_(_quant(part, self.kv_bit))
             self.done = self.cur
         self.k[:, self.cur:self.cur + l] = k

@@ -40,7 +40,7 @@ import torch.nn.functional as F
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-from fpqvar_b200 import ops, quant_utils, rotation_utils, transform_model_utils  # noqa: E402
+from fpqvar_b200 import kv_cache, ops, quant_utils, rotation_utils, transform_model_utils  # noqa: E402
 
 PATCH_256 = (1, 2, 3, 4, 5, 6, 8, 10, 13, 16)
 PATCH_512 = (1, 2, 3, 4, 6, 9, 13, 18, 24, 32)
@@ -57,8 +57,15 @@ class SelfAttention(nn.Module):                      # class NAME is what quanti
         self.log_scale_mul = nn.Parameter(torch.full((1, 1, heads, 1), 4.0).log())
         self.k_cache = self.v_cache = None
         self.cur = 0
+        self.kv = None                                               # IncrementalKVQuant when --quant-kv is on
 
-    def reset_cache(self, rows, L, device):
+    def reset_cache(self, rows, L, device, kv_bit=0, kv_incremental=True):
+        if kv_bit:
+            if self.kv is None or self.kv.max_len != L or self.kv.kv_bit != kv_bit or self.kv.incremental != kv_incremental:
+                self.kv = kv_cache.IncrementalKVQuant(kv_bit, L, incremental=kv_incremental)
+            self.kv.reset()
+            return
+        self.kv = None
         if self.k_cache is None or self.k_cache.shape[0] != rows or self.k_cache.shape[1] != L:
             self.k_cache = torch.empty(rows, L, self.H, self.hd, dtype=torch.float16, device=device)
             self.v_cache = torch.empty_like(self.k_cache)
@@ -69,10 +76,13 @@ class SelfAttention(nn.Module):                      # class NAME is what quanti
         q, k, v = qkv.view(B, l, 3, self.H, self.hd).unbind(2)
         q = F.normalize(q, dim=-1).mul(self.log_scale_mul.clamp_max(math.log(100)).exp().to(q.dtype))
         k = F.normalize(k, dim=-1)
-        self.k_cache[:, self.cur:self.cur + l] = k
-        self.v_cache[:, self.cur:self.cur + l] = v
-        self.cur += l
-        kk, vv = self.k_cache[:, :self.cur], self.v_cache[:, :self.cur]
+        if self.kv is not None:                                       # basic_var.py:188-203 with --quant_kv
+            kk, vv = self.kv.append(k, v)
+        else:
+            self.k_cache[:, self.cur:self.cur + l] = k
+            self.v_cache[:, self.cur:self.cur + l] = v
+            self.cur += l
+            kk, vv = self.k_cache[:, :self.cur], self.v_cache[:, :self.cur]
         o = F.scaled_dot_product_attention(q.transpose(1, 2), kk.transpose(1, 2), vv.transpose(1, 2), scale=1.0)
         return o.transpose(1, 2).reshape(B, l, self.C)
 
@@ -124,6 +134,7 @@ class Var(nn.Module):
         self.codebook = nn.Embedding(V, Cvae)
         self.phi = nn.ModuleList(nn.Conv2d(Cvae, Cvae, 3, padding=1) for _ in range(4))
         self.mode = "fp16"
+        self.kv_bit, self.kv_incremental = 0, True
         self.smooth_qkv = self.smooth_fc1 = None
         self.Q = None
 
@@ -188,7 +199,7 @@ class Var(nn.Module):
         x = cond.unsqueeze(1) + self.pos_start + lvl_pos[:, :pn[0] ** 2]
         f_hat = cond.new_zeros(B, self.Cvae, pn[-1], pn[-1])
         for b in self.blocks:
-            b.attn.reset_cache(2 * B, self.L, dev)
+            b.attn.reset_cache(2 * B, self.L, dev, self.kv_bit, self.kv_incremental)
         cur = 0
         for si, p in enumerate(pn):
             cur += p * p
@@ -337,7 +348,8 @@ def prepare(model: Var, mode: str, bits: int, seed=0, rotate=True):
     return model
 
 
-def measure(dev, depth, batch, res=256, bits=4, mode="fused", iters=3, warmup=1, rank=0, world=1, decode=True, rotate=True, dec=None):
+def measure(dev, depth, batch, res=256, bits=4, mode="fused", iters=3, warmup=1, rank=0, world=1, decode=True, rotate=True, dec=None,
+            quant_kv=""):
     """Build the model for `mode`, run `warmup` + `iters` generation passes; returns the JSON-able result (times are
     CUDA-event ms per batch on this rank; the caller takes the max over ranks)."""
     patch = PATCH_256 if res == 256 else PATCH_512
@@ -353,6 +365,8 @@ def measure(dev, depth, batch, res=256, bits=4, mode="fused", iters=3, warmup=1,
         model = Var(depth, patch, shared_aln=(depth == 36)).eval()
     model.init_weights(0)
     prepare(model, mode, bits, rotate=rotate)
+    if quant_kv and mode != "fp16":                                   # --quant_kv: kv_bit follows the activation bits
+        model.kv_bit, model.kv_incremental = bits, quant_kv == "incremental"
     rng = torch.Generator(device=dev)
     marks = []
     torch.cuda.reset_peak_memory_stats(dev)
@@ -387,7 +401,7 @@ def measure(dev, depth, batch, res=256, bits=4, mode="fused", iters=3, warmup=1,
     res_d = {"mode": mode, "ms_per_batch": ms, "decode_ms_per_batch": sum(a.elapsed_time(b) for a, b in marks) / iters,
              "wall_ms_per_batch": wall / iters * 1e3, "fpq_launches_per_batch": (ops.launch_count() - n1) // max(1, iters),
              "finite": bool(torch.isfinite(img).all()), "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 1),
-             "config": {"depth": depth, "width": 64 * depth, "res": res, "batch_per_gpu": batch, "bits": bits, "rotate_transform": rotate,
+             "config": {"depth": depth, "width": 64 * depth, "res": res, "batch_per_gpu": batch, "bits": bits, "rotate_transform": rotate, "quant_kv": quant_kv or None,
                         "patch_nums": list(patch), "decode": decode, "iters": iters, "warmup": warmup}}
     del model
     torch.cuda.empty_cache()
@@ -405,6 +419,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--no-decode", action="store_true")
     ap.add_argument("--no-rotate", action="store_true", help="plain models_fp_quant configuration (BASELINE config 2)")
+    ap.add_argument("--quant-kv", default="", choices=("", "incremental", "reference"),
+                    help="fake-quantize the KV cache (kv_bit = --bits): each row once, or the reference's schedule (whole cache every scale)")
     args = ap.parse_args()
 
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -426,7 +442,7 @@ def main():
         if world > 1:
             dist.barrier()
         r = measure(dev, args.depth, args.batch, args.res, args.bits, mode, args.iters, args.warmup, rank, world,
-                    decode=not args.no_decode, rotate=not args.no_rotate, dec=dec)
+                    decode=not args.no_decode, rotate=not args.no_rotate, dec=dec, quant_kv=args.quant_kv)
         ms = torch.tensor([r["ms_per_batch"]], device=dev)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
