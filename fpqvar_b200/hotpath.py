@@ -11,8 +11,7 @@ No arithmetic happens here; there is no CPU fallback.
 """
 from __future__ import annotations
 
-import ctypes
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import torch
 
