@@ -187,3 +187,46 @@ def test_randomized_differential_against_oracle(ops):
             want = O.fake_quant(xh, fmt, group, tie, clamp3=clamp3)
             got = host(ops.fake_quant(xt, fmt, group, tie, clamp3=clamp3))
         assert bits_equal(got, want), f"case {case}: {shape} {dt} group={group} {fmt} {tie}\n" + mismatch_report(got, want)
+
+
+def test_concurrent_host_threads_and_streams(ops):
+    """The C ABI is called from several host threads at once (ctypes drops the GIL), each on its own stream: per-thread
+    error / launch bookkeeping, per-(device, stream) clip workspaces, benign static caches.  Results must equal the
+    serial ones and every thread must see its own launch count."""
+    import threading
+    from fpqvar_b200.hotpath import seed42_sign_bits
+    bits = seed42_sign_bits()
+    n_threads, iters = 4, 40
+    torch.manual_seed(5)
+    xs = [torch.randn(300 + 7 * t, 1920, device="cuda") for t in range(n_threads)]
+    hs = [torch.nn.functional.gelu(x).half() for x in xs]
+    s = torch.exp(torch.rand(1920, device="cuda") - 0.5)
+    want = [(ops.transform_rotate_quant(x, s, bits, "e2m1"), ops.fake_quant_signsplit(h, "e1m2_neg_e2m1_pos", 128, "kernel", global_clip=True),
+             ops.fake_quant(h, "e2m3", None, "kernel")) for x, h in zip(xs, hs)]
+    torch.cuda.synchronize()
+    errors, counts = [], [0] * n_threads
+
+    def worker(t):
+        try:
+            st = torch.cuda.Stream()
+            with torch.cuda.stream(st):
+                n0 = ops.launch_count()
+                for _ in range(iters):
+                    got = (ops.transform_rotate_quant(xs[t], s, bits, "e2m1"),
+                           ops.fake_quant_signsplit(hs[t], "e1m2_neg_e2m1_pos", 128, "kernel", global_clip=True),
+                           ops.fake_quant(hs[t], "e2m3", None, "kernel"))
+                st.synchronize()
+                counts[t] = ops.launch_count() - n0
+                for g, w in zip(got, want[t]):
+                    if not torch.equal(g.view(torch.int16), w.view(torch.int16)):
+                        errors.append(f"thread {t}: result differs")
+        except Exception as e:  # noqa: BLE001
+            errors.append(f"thread {t}: {type(e).__name__}: {e}")
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+    assert counts == [3 * iters] * n_threads
