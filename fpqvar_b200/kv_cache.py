@@ -9,7 +9,7 @@ The reference, with `--quant_kv`, re-quantizes the WHOLE cache at every scale be
 so a row appended at scale t is quantized at scales t+1, t+2, ...: sum_t cur_L(t) = 1030 token rows per block for the 256x256
 schedule, where 424 suffice if each row is quantized once.  That is bit-identical to the reference because the fp16 fake
 quantizer is IDEMPOTENT: a second pass re-derives the same scale from the quantized absmax element and maps every value to
-itself.  Checked exhaustively against the oracle for every fp16 (absmax, x) pair (tools/idempotence_check.py); the only
+itself.  Checked exhaustively against the oracle for every fp16 (absmax, x) pair (tests/idempotence_exhaustive.py); the only
 exceptions are rows whose absmax is below 2^-17 (scales in the deep fp16-subnormal range) or equal to 65504 (the quantized
 absmax overflows to inf).  Such rows are recognisable afterwards (a quantized row with 0 < absmax < 2^-16, or a non-finite
 value): `IncrementalKVQuant.exact` scans the finished cache once and reports them, and the caller can redo the pass with

@@ -8,7 +8,7 @@ from the quantized row, quantize again, compare bits.  ~4 min on one core.  Resu
   e2m1 per_group: idempotent except absmax 5.36e-7 and 65504 (half(6 * s) overflows)
 """
 import numpy as np, sys, time
-sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))
+sys.path.insert(0, __import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__))))  # TEST INFRASTRUCTURE: runs the oracle, not the product
 from oracle import oracle as O
 allpos=np.arange(0x0000,0x7C00,dtype=np.uint16).view(np.float16)   # +0 .. max finite
 def Q(x, s, grid, vmaxf):

@@ -50,7 +50,7 @@ def test_incremental_kv_quant_equals_the_reference_schedule(kv_bit):
         assert same(fk, rk) and same(fv, rv)
     assert inc.exact and full.exact
     assert n_inc == 2 * (len(PATCH) - 1)                             # one quantizer launch per tensor and scale, on the new rows only
-    # the history really is quantized: a further pass changes nothing (idempotence, tools/idempotence_check.py)
+    # the history really is quantized: a further pass changes nothing (idempotence, tests/idempotence_exhaustive.py)
     from fpqvar_b200 import quant_utils as Q
     hist = inc.k[:, :inc.done].contiguous()
     again = Q.fp6_quant_e2m3_per_token_cuda(hist, 6) if kv_bit == 6 else Q.fp_quant_e2_per_group_cuda(hist, 4)

@@ -120,7 +120,7 @@ def _requantize_row_family(fmt, ai):
 def test_requantization_is_idempotent(fmt):
     """Why the KV cache may be quantized incrementally (fpqvar_b200/kv_cache.py): the reference re-quantizes the whole
     cache at every scale (basic_var.py:192-200), and a second pass over quantized rows is the identity.  The exhaustive
-    run over every (absmax, x) pair is tools/idempotence_check.py; this is every 61st absmax plus the known exceptions."""
+    run over every (absmax, x) pair is tests/idempotence_exhaustive.py; this is every 61st absmax plus the known exceptions."""
     for ai in list(range(128, 0x7BFF, 61)) + [0x7BFE]:
         y, y2 = _requantize_row_family(fmt, ai)
         assert bits_equal(y, y2), f"{fmt}: absmax index {ai}"
