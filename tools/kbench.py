@@ -19,7 +19,7 @@ from fpqvar_b200.hotpath import seed42_sign_bits  # noqa: E402
 lib = L.lib()
 dev = torch.device("cuda")
 st = torch.cuda.current_stream().cuda_stream
-NBUF = 6
+NBUF = int(os.environ.get("KB_NBUF", "6"))
 ITERS = int(os.environ.get("KB_ITERS", "30"))
 ONLY = os.environ.get("KB_ONLY")
 
@@ -110,6 +110,12 @@ def main():
         res["group e2m1 f32->f32"] = timeit(lambda i: lib.fpq_fake_quant(xf[i].data_ptr(), o32[i].data_ptr(), n // 128, 128, 0, 0, 0, 0, 0, st), n * 8)
     if want("score 3 fmts f32 (read-only)"):
         res["score 3 fmts f32 (read-only)"] = timeit(lambda i: ops.score_formats(xf[i], ["e2m1", "e1m2", "e3m0"]), n * 4)
+    if want("quant_grid f32 (quant_cuda.quant compat)"):
+        grid = torch.tensor([-6, -4, -3, -2, -1.5, -1, -0.5, 0, 0.5, 1, 1.5, 2, 3, 4, 6.0], device=dev)
+        res["quant_grid f32 (quant_cuda.quant compat)"] = timeit(lambda i: lib.fpq_quant_grid(xf[i].data_ptr(), grid.data_ptr(), 15, n, o32[i].data_ptr(), 0, st), n * 8)
+    if want("weight transform+rotate f32 (fp64 butterflies)"):
+        res["weight transform+rotate f32 (fp64 butterflies)"] = timeit(lambda i: lib.fpq_transform_rotate_weight(
+            xf[i].data_ptr(), smooth.data_ptr(), sb, o32[i].data_ptr(), r4, C, st), n * 8)
     # plain copy for reference
     if want("torch copy f32 (d2d)"):
         res["torch copy f32 (d2d)"] = timeit(lambda i: o32[i].copy_(xf[i]), n * 8)
