@@ -62,6 +62,7 @@ int signsplit_kernel_tie(int in_dtype, int out_dtype, int split, const void* x, 
 int signsplit_argmin_tie(int in_dtype, int out_dtype, int split, const void* x, void* out, size_t n_rows, size_t row_len, unsigned* flag, cudaStream_t st);
 // packed fp16 -> fp16 group-of-128 kernels, kernel tie rule (fpq_h16.cu)
 int launch_sym_h16(int format, const void* x, void* out, size_t n_groups, cudaStream_t st);
+int launch_sym_h16_g64(int format, const void* x, void* out, size_t n_groups, cudaStream_t st);   // groups / rows of 64 (KV cache)
 int launch_split_h16(int split, const void* x, void* out, size_t n_groups, unsigned* nan_flag, cudaStream_t st);
 static inline unsigned grid_for(size_t work_items, size_t items_per_block, int blocks_per_sm) {
     size_t need = (work_items + items_per_block - 1) / items_per_block;

@@ -92,6 +92,54 @@ __global__ void __launch_bounds__(256) fake_quant_group_h16_kernel(const __half*
 }
 
 // ------------------------------------------------------------------------------------------
+// Groups / rows of 64 (the KV cache: fp6_quant_e2m3_per_token_cuda on [B, L, H, 64], basic_var.py:193-194).
+// Same packed element path; 4 lanes x 2 vectors x 8 halves per group, so a warp-wide 128-bit load still touches
+// 8 groups x 64 contiguous bytes.  Two independent tiles per trip keep four loads in flight per lane.  (The generic
+// kernel these rows used to take ran at 20.4 instructions per element, 81 % issue utilisation: profiles/r1e.)
+// ------------------------------------------------------------------------------------------
+template <int FMT>
+__global__ void __launch_bounds__(256) fake_quant_group64_h16_kernel(const __half* __restrict__ x, __half* __restrict__ out, size_t n_groups) {
+    constexpr int LPG = 4, NV = 2, NW = 4 * NV, GPW = 32 / LPG;
+    pdl_launch_dependents();
+    const int lane = threadIdx.x & 31;
+    const int lig = lane % LPG;
+    const size_t warp_global = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
+    const float delta = tie_delta_kernel(uint32_t(warp_global >> 33));
+    const size_t stride = n_warps * GPW;
+    pdl_wait();
+    auto load = [&](size_t g, uint32_t (&p)[NW]) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            uint4 u = make_uint4(0u, 0u, 0u, 0u);
+            if (g < n_groups) u = ldg_stream(x + g * 64 + (j * LPG + lig) * 8);
+            p[4 * j] = u.x; p[4 * j + 1] = u.y; p[4 * j + 2] = u.z; p[4 * j + 3] = u.w;
+        }
+    };
+    auto finish = [&](size_t g, uint32_t (&p)[NW]) {
+        float s;
+        const bool ok = sym_quant_tile_h16<FMT, LPG, NW>(p, s, delta);
+        if (g < n_groups) {
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < NV; ++j)
+                    stg_stream(out + g * 64 + (j * LPG + lig) * 8, make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]));
+            } else {
+                literal_sym_h16(x + g * 64, out + g * 64, lig, LPG, 8, NV, s, SymFmt<FMT>::GT);
+            }
+        }
+    };
+    for (size_t g0 = warp_global * GPW; g0 < n_groups; g0 += 2 * stride) {
+        const size_t ga = g0 + lane / LPG, gb = ga + stride;
+        uint32_t A[NW], B[NW];
+        load(ga, A);
+        load(gb, B);
+        finish(ga, A);
+        finish(gb, B);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // sign-split
 // ------------------------------------------------------------------------------------------
 template <int SPLIT> struct SplitH16;
@@ -369,6 +417,21 @@ int launch_sym_h16(int format, const void* x, void* out, size_t n_groups, cudaSt
         case FPQ_FMT_E3M0: launch_pdl(fake_quant_group_h16_kernel<FPQ_FMT_E3M0>, grid, 256, 0, st, xi, oo, n_groups); break;
         case FPQ_FMT_E2M3: launch_pdl(fake_quant_group_h16_kernel<FPQ_FMT_E2M3>, grid, 256, 0, st, xi, oo, n_groups); break;
         case FPQ_FMT_E3M2: launch_pdl(fake_quant_group_h16_kernel<FPQ_FMT_E3M2>, grid, 256, 0, st, xi, oo, n_groups); break;
+        default: return FPQ_ERR_ARG;
+    }
+    return finish_launch();
+}
+
+int launch_sym_h16_g64(int format, const void* x, void* out, size_t n_groups, cudaStream_t st) {
+    const __half* xi = static_cast<const __half*>(x);
+    __half* oo = static_cast<__half*>(out);
+    const unsigned grid = grid_for(n_groups, 8 * 8 * 2, 8);       // 8 warps x 8 groups x 2 tiles per block and trip
+    switch (format) {
+        case FPQ_FMT_E2M1: launch_pdl(fake_quant_group64_h16_kernel<FPQ_FMT_E2M1>, grid, 256, 0, st, xi, oo, n_groups); break;
+        case FPQ_FMT_E1M2: launch_pdl(fake_quant_group64_h16_kernel<FPQ_FMT_E1M2>, grid, 256, 0, st, xi, oo, n_groups); break;
+        case FPQ_FMT_E3M0: launch_pdl(fake_quant_group64_h16_kernel<FPQ_FMT_E3M0>, grid, 256, 0, st, xi, oo, n_groups); break;
+        case FPQ_FMT_E2M3: launch_pdl(fake_quant_group64_h16_kernel<FPQ_FMT_E2M3>, grid, 256, 0, st, xi, oo, n_groups); break;
+        case FPQ_FMT_E3M2: launch_pdl(fake_quant_group64_h16_kernel<FPQ_FMT_E3M2>, grid, 256, 0, st, xi, oo, n_groups); break;
         default: return FPQ_ERR_ARG;
     }
     return finish_launch();

@@ -260,6 +260,7 @@ static int launch_sym(const void* x, void* out, size_t n_rows, size_t row_len, i
                             ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
     if constexpr (sizeof(InT) == 2 && sizeof(OutT) == 2 && TIE == TIE_KERNEL) {
         if (pow2_group && row_len == 128 && !clamp3) return launch_sym_h16(FMT, x, out, n_rows, st);
+        if (pow2_group && row_len == 64 && !clamp3 && getenv("FPQ_NO_G64") == nullptr) return launch_sym_h16_g64(FMT, x, out, n_rows, st);
     }
     if (pow2_group) {
         const int lpg = int(row_len / 16);
