@@ -6,7 +6,7 @@
 namespace fpq {
 
 // Software pipelining (two register tiles in ping-pong).  Measured on B200 (tools/kbench.py,
-// profiles/r1_kbench_variants.txt): +3 % for the symmetric kernel (42 -> 70 registers), -8 % for the
+// profiles/r1_kbench.txt, the "variant" sections): +3 % for the symmetric kernel (42 -> 70 registers), -8 % for the
 // sign-split kernel (52 -> 84 registers, occupancy drops to 3 CTAs), so only the former uses it.
 #ifndef FPQ_SYM_PREFETCH
 #define FPQ_SYM_PREFETCH 1
