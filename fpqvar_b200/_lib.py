@@ -10,7 +10,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfpq_b200.so")
+LIB_PATH = os.environ.get("FPQ_LIB_PATH") or os.path.join(_HERE, "libfpq_b200.so")     # FPQ_LIB_PATH: an alternative BUILD of the same library (csrc: make VARIANT=...)
 
 # mirrors include/fpq_b200.h
 FPQ_OK, FPQ_ERR_ARG, FPQ_ERR_UNSUPPORTED, FPQ_ERR_CUDA = 0, -1, -2, -3

@@ -35,8 +35,14 @@ __device__ __forceinline__ float inv_sqrt128() { return __uint_as_float(0x3DB504
 // MOD (adaLN modulate fused in): a lane set walks CONTIGUOUS rows (k0*R .. k0*R + R - 1) instead of strided ones, so the
 // (scale+1) and shift values of its column change only when the batch index does and live in registers in between --
 // read from L2 once per (batch, column, row range) instead of once per chunk.
+// Resident CTAs per SM the adaLN-fused variant is compiled for.  As compiled freely it takes 100 registers = 2 CTAs per SM
+// and is latency-bound (ncu r1e: 24 % warps active, long_scoreboard 2.5 per issue).  Measured (tools/kbench.py, 102400 x 1920):
+// free 4526 GB/s; forced to 3 CTAs (80 registers, 48 B of spills) 3917; 4 CTAs (64 registers, 120 B) 4338 -- so it stays free.
+#ifndef FPQ_ROT_MOD_CTAS
+#define FPQ_ROT_MOD_CTAS 1
+#endif
 template <int FMT, bool QUANT, bool MOD>
-__global__ void __launch_bounds__(256) transform_rotate_quant_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
+__global__ void __launch_bounds__(256, MOD ? FPQ_ROT_MOD_CTAS : 1) transform_rotate_quant_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
                                                                      SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
                                                                      size_t n_rows, int cpr, size_t sets_per_col, Modulate mod) {
     constexpr int LPG = 8;
