@@ -37,12 +37,17 @@ __device__ __forceinline__ float inv_sqrt128() { return __uint_as_float(0x3DB504
 // read from L2 once per (batch, column, row range) instead of once per chunk.
 // Resident CTAs per SM the adaLN-fused variant is compiled for.  As compiled freely it takes 100 registers = 2 CTAs per SM
 // and is latency-bound (ncu r1e: 24 % warps active, long_scoreboard 2.5 per issue).  Measured (tools/kbench.py, 102400 x 1920):
-// free 4526 GB/s; forced to 3 CTAs (80 registers, 48 B of spills) 3917; 4 CTAs (64 registers, 120 B) 4338 -- so it stays free.
+// free 4123-4526 GB/s (100 or, declared as (256, 1), 114 registers); forced to 3 CTAs (80 registers, 48 B of spills) 3917; 4 CTAs (64 registers, 120 B) 4338 -- so it stays free.
 #ifndef FPQ_ROT_MOD_CTAS
-#define FPQ_ROT_MOD_CTAS 1
+#define FPQ_ROT_MOD_CTAS 0
+#endif
+#if FPQ_ROT_MOD_CTAS > 1
+#define FPQ_ROT_BOUNDS __launch_bounds__(256, MOD ? FPQ_ROT_MOD_CTAS : 1)
+#else
+#define FPQ_ROT_BOUNDS __launch_bounds__(256)       // NOT (256, 1): that form relaxes the register heuristics (100 -> 114, 67 -> 76)
 #endif
 template <int FMT, bool QUANT, bool MOD>
-__global__ void __launch_bounds__(256, MOD ? FPQ_ROT_MOD_CTAS : 1) transform_rotate_quant_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
+__global__ void FPQ_ROT_BOUNDS transform_rotate_quant_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
                                                                      SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
                                                                      size_t n_rows, int cpr, size_t sets_per_col, Modulate mod) {
     constexpr int LPG = 8;
