@@ -41,8 +41,8 @@ __device__ __forceinline__ float inv_sqrt128() { return __uint_as_float(0x3DB504
 #ifndef FPQ_ROT_MOD_CTAS
 #define FPQ_ROT_MOD_CTAS 0
 #endif
-#if FPQ_ROT_MOD_CTAS > 1
-#define FPQ_ROT_BOUNDS __launch_bounds__(256, MOD ? FPQ_ROT_MOD_CTAS : 1)
+#if FPQ_ROT_MOD_CTAS >= 1
+#define FPQ_ROT_BOUNDS __launch_bounds__(256, MOD ? FPQ_ROT_MOD_CTAS : 0)      // 0 = no occupancy hint
 #else
 #define FPQ_ROT_BOUNDS __launch_bounds__(256)       // NOT (256, 1): that form relaxes the register heuristics (100 -> 114, 67 -> 76)
 #endif
