@@ -35,16 +35,19 @@ __device__ __forceinline__ float inv_sqrt128() { return __uint_as_float(0x3DB504
 // MOD (adaLN modulate fused in): a lane set walks CONTIGUOUS rows (k0*R .. k0*R + R - 1) instead of strided ones, so the
 // (scale+1) and shift values of its column change only when the batch index does and live in registers in between --
 // read from L2 once per (batch, column, row range) instead of once per chunk.
-// Resident CTAs per SM the adaLN-fused variant is compiled for.  As compiled freely it takes 100 registers = 2 CTAs per SM
-// and is latency-bound (ncu r1e: 24 % warps active, long_scoreboard 2.5 per issue).  Measured (tools/kbench.py, 102400 x 1920):
-// free 4123-4526 GB/s (100 or, declared as (256, 1), 114 registers); forced to 3 CTAs (80 registers, 48 B of spills) 3917; 4 CTAs (64 registers, 120 B) 4338 -- so it stays free.
+// Occupancy hint of the adaLN-fused variant (MOD).  Compiled freely it takes 100 registers = 2 CTAs per SM and is latency-bound
+// (ncu r1e: 24 % warps active, long_scoreboard 2.5 per issue).  Measured (tools/kbench.py, 102400 x 1920, same run A/B,
+// profiles/r1_kbench.txt): plain bounds 4314 / 4317 GB/s; declared (256, 1) -- still 2 CTAs, but the compiler spends 114
+// registers and spills nothing -- 4526 / 4530; forced to 3 CTAs (80 registers, 48 B of spills) 3917; 4 CTAs (64 registers,
+// 120 B) 4338.  So MOD is declared (256, 1).  The plain variants keep the plain bounds: the (256, 1) form costs them
+// registers (67 -> 76) for nothing measured.
 #ifndef FPQ_ROT_MOD_CTAS
-#define FPQ_ROT_MOD_CTAS 0
+#define FPQ_ROT_MOD_CTAS 1
 #endif
 #if FPQ_ROT_MOD_CTAS >= 1
 #define FPQ_ROT_BOUNDS __launch_bounds__(256, MOD ? FPQ_ROT_MOD_CTAS : 0)      // 0 = no occupancy hint
 #else
-#define FPQ_ROT_BOUNDS __launch_bounds__(256)       // NOT (256, 1): that form relaxes the register heuristics (100 -> 114, 67 -> 76)
+#define FPQ_ROT_BOUNDS __launch_bounds__(256)
 #endif
 template <int FMT, bool QUANT, bool MOD>
 __global__ void FPQ_ROT_BOUNDS transform_rotate_quant_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
