@@ -282,3 +282,24 @@ def test_var_generation_harness_runs_on_cpu_in_fp16_mode():
     f_hat = model.generate(2, torch.tensor([1, 2]), torch.Generator().manual_seed(0))
     assert f_hat.shape == (2, 32, 4, 4) and bool(torch.isfinite(f_hat).all())
     assert model.blocks[0].attn.cur == 1 + 4 + 9 + 16
+
+
+def test_kv_cache_host_checks_without_a_gpu():
+    """fpqvar_b200.kv_cache: argument errors surface before anything touches the device; a CPU tensor reaches the
+    quantizer's own 'no CPU fallback' error only when there is history to quantize."""
+    import torch
+    from fpqvar_b200.kv_cache import IncrementalKVQuant
+    from fpqvar_b200._lib import FpqError
+    with pytest.raises(NotImplementedError):
+        IncrementalKVQuant(8, 16)                                         # basic_var.py:199: only kv_bit 4 and 6 exist
+    c = IncrementalKVQuant(6, 16)
+    with pytest.raises(ValueError):
+        c.append(torch.zeros(1, 2, 2, 64), torch.zeros(1, 2, 2, 64))      # fp32: the cache is fp16 (autocast attention)
+    k = torch.zeros(1, 2, 2, 64, dtype=torch.float16)
+    kk, vv = c.append(k, k)                                               # first scale: nothing to quantize yet
+    assert kk.shape == (1, 2, 2, 64) and c.cur == 2 and c.done == 0 and c.exact
+    with pytest.raises(FpqError):
+        c.append(k, k)                                                    # history on the CPU: the quantizer refuses
+    c4 = IncrementalKVQuant(4, 16)
+    with pytest.raises(ValueError):
+        c4.append(torch.zeros(1, 2, 3, 64, dtype=torch.float16), torch.zeros(1, 2, 3, 64, dtype=torch.float16))
