@@ -426,4 +426,92 @@ def quantize_VAR(model, weight_quant=None, act_quant=None, quantize_bmm_input=Fa
     return model
 
 
+# ---- per-layer ("mixed datatype") variants ---------------------------------------------------------------------
+# evaluate_fp_quant.py:18 imports quantize_VAR_mixed_fp4_datatype / quantize_VAR_mixed_fp6_datatype next to quantize_VAR
+# (models_fp_quant/quant_utils.py:1256-1432); models_fp_quant_rotate/quant_utils.py:982-1067 has
+# quantize_VAR_use_different_datatype.  They differ from quantize_VAR in two ways: the (activation, weight) format of a
+# linear depends on its block index (tables taken from the format search), and the adaLN projection `ada_lin[1]` of every
+# block is quantized as well.  A plan maps (site, block) to formats; `None` entries fall back to the caller's arguments.
+_FC1_E2_BLOCKS = frozenset(range(6, 21))                     # fc1 activations on fp_e2 in blocks 6..20, fp_e3 elsewhere
+
+
+def _plan_mixed_fp4(qkv_e2_blocks):
+    def plan(site, block):
+        if site == "fc1":
+            return ("fp_e2" if block in _FC1_E2_BLOCKS else "fp_e3", "fp_e2")
+        if site == "mat_qkv":
+            return ("fp_e2" if block in qkv_e2_blocks else "fp_e3", "fp_e2")
+        return (None, None)                                     # proj, fc2, ada_lin: the caller's act_fp_type / fc2_fp_type / weight_fp_type
+    return plan
+
+
+def _plan_mixed_fp6(site, block):
+    if site in ("fc1", "mat_qkv"):
+        return ("fp6_e3m2", "fp6_e2m3")
+    if site == "fc2":
+        return ("fp6_e2m3" if block in (0, 23) else "fp6_e3m2", "fp6_e2m3")
+    if site == "proj":
+        return ("fp6_e2m3" if block >= 2 else "fp6_e3m2", "fp6_e2m3")
+    return ("fp6_e2m3", "fp6_e2m3")                             # ada_lin
+
+
+def _quantize_VAR_planned(model, plan, weight_quant, act_quant, w_bit, a_bit, act_quant_sym, fc2_act_log2_quant,
+                          activation_fp_quant, weight_fp_quant, act_fp_type, weight_fp_type, fc2_fp_type):
+    common = dict(weight_quant=weight_quant, act_quant=act_quant, w_bit=w_bit, a_bit=a_bit,
+                  activation_fp_quant=activation_fp_quant, weight_fp_quant=weight_fp_quant)
+
+    def swap(owner, attr, site, block, fc2=False):
+        a, w = plan(site, block)
+        a = a if a is not None else (fc2_fp_type if fc2 else act_fp_type)
+        w = w if w is not None else weight_fp_type
+        target = owner[attr] if isinstance(attr, int) else getattr(owner, attr)
+        if fc2:
+            new = QuantizedLinear_fc2.from_float(target, act_quant_sym=False, fc2_act_log2_quant=fc2_act_log2_quant,
+                                                 act_fp_type=a, weight_fp_type=w, **common)
+        else:
+            new = QuantizedLinear.from_float(target, act_quant_sym=act_quant_sym, act_fp_type=a, weight_fp_type=w, **common)
+        if isinstance(attr, int):
+            owner[attr] = new
+        else:
+            setattr(owner, attr, new)
+
+    for name, m in list(model.named_modules()):             # parents come before their children, as in the reference's walk
+        if not (_is_ffn(m) or _is_self_attention(m) or type(m).__name__ == "AdaLNSelfAttn"):
+            continue
+        block = int(name.split(".")[1])                        # "blocks.<i>...." (qu0.py:1270)
+        if _is_ffn(m):
+            swap(m, "fc1", "fc1", block)
+            swap(m, "fc2", "fc2", block, fc2=True)
+        elif _is_self_attention(m):
+            swap(m, "mat_qkv", "mat_qkv", block)
+            swap(m, "proj", "proj", block)
+        else:
+            swap(m.ada_lin, 1, "ada_lin", block)               # AttributeError with shared_aln=True, as in the reference
+    return model
+
+
+def quantize_VAR_mixed_fp4_datatype(model, weight_quant=None, act_quant=None, quantize_bmm_input=False, w_bit=8, a_bit=8, kv_bit=8,
+                                    act_quant_sym=None, fc2_act_log2_quant=None, quant_kv=None, activation_fp_quant=False,
+                                    weight_fp_quant=False, act_fp_type=None, weight_fp_type=None, fc2_fp_type=None):
+    """models_fp_quant/quant_utils.py:1256-1341."""
+    return _quantize_VAR_planned(model, _plan_mixed_fp4(frozenset((0, 24, 25))), weight_quant, act_quant, w_bit, a_bit, act_quant_sym,
+                                 fc2_act_log2_quant, activation_fp_quant, weight_fp_quant, act_fp_type, weight_fp_type, fc2_fp_type)
+
+
+def quantize_VAR_mixed_fp6_datatype(model, weight_quant=None, act_quant=None, quantize_bmm_input=False, w_bit=8, a_bit=8, kv_bit=8,
+                                    act_quant_sym=None, fc2_act_log2_quant=None, quant_kv=None, activation_fp_quant=False,
+                                    weight_fp_quant=False, act_fp_type=None, weight_fp_type=None, fc2_fp_type=None):
+    """models_fp_quant/quant_utils.py:1344-1432 (every format comes from the table; the *_fp_type arguments are unused there too)."""
+    return _quantize_VAR_planned(model, _plan_mixed_fp6, weight_quant, act_quant, w_bit, a_bit, act_quant_sym,
+                                 fc2_act_log2_quant, activation_fp_quant, weight_fp_quant, act_fp_type, weight_fp_type, fc2_fp_type)
+
+
+def quantize_VAR_use_different_datatype(model, weight_quant=None, act_quant=None, quantize_bmm_input=False, w_bit=8, a_bit=8, kv_bit=8,
+                                        act_quant_sym=None, fc2_act_log2_quant=None, quant_kv=None, activation_fp_quant=False,
+                                        weight_fp_quant=False, act_fp_type=None, weight_fp_type=None, fc2_fp_type=None):
+    """models_fp_quant_rotate/quant_utils.py:982-1067 (the FP4 table without block 0 in the mat_qkv list)."""
+    return _quantize_VAR_planned(model, _plan_mixed_fp4(frozenset((24, 25))), weight_quant, act_quant, w_bit, a_bit, act_quant_sym,
+                                 fc2_act_log2_quant, activation_fp_quant, weight_fp_quant, act_fp_type, weight_fp_type, fc2_fp_type)
+
+
 assert FpqError  # re-exported for callers that want to catch it

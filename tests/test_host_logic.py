@@ -303,3 +303,58 @@ def test_kv_cache_host_checks_without_a_gpu():
     c4 = IncrementalKVQuant(4, 16)
     with pytest.raises(ValueError):
         c4.append(torch.zeros(1, 2, 3, 64, dtype=torch.float16), torch.zeros(1, 2, 3, 64, dtype=torch.float16))
+
+
+def test_mixed_datatype_variants_issue_the_reference_call_sequence(monkeypatch):
+    """quantize_VAR_mixed_fp4_datatype / _mixed_fp6_datatype (imported by evaluate_fp_quant.py:18) and
+    quantize_VAR_use_different_datatype: the same (module, class, keyword arguments) sequence as the reference's own
+    functions on a 30-block model (tests/golden/make_golden_mixed.py recorded them with `from_float` patched out)."""
+    import json
+    import torch
+    from torch import nn
+    from fpqvar_b200 import quant_utils as Q
+    plans = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_mixed_plans.json")))
+
+    class SelfAttention(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.mat_qkv, self.proj = nn.Linear(128, 384, bias=False), nn.Linear(128, 128)
+
+    class FFN(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.fc1, self.fc2 = nn.Linear(128, 128), nn.Linear(128, 128)
+
+    class AdaLNSelfAttn(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.attn, self.ffn = SelfAttention(), FFN()
+            self.ada_lin = nn.Sequential(nn.SiLU(), nn.Linear(128, 768))
+
+    class Model(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.blocks = nn.ModuleList(AdaLNSelfAttn() for _ in range(30))
+
+    for fn_name in ("quantize_VAR_mixed_fp4_datatype", "quantize_VAR_mixed_fp6_datatype", "quantize_VAR_use_different_datatype"):
+        model = Model()
+        paths = {id(m): n for n, m in model.named_modules()}
+        calls = []
+
+        def recorder(cls_name):
+            def from_float(module, **kwargs):
+                calls.append({"module": paths[id(module)], "class": cls_name, "kwargs": {k: kwargs[k] for k in sorted(kwargs)}})
+                return module
+            return staticmethod(from_float)
+
+        monkeypatch.setattr(Q.QuantizedLinear, "from_float", recorder("QuantizedLinear"))
+        monkeypatch.setattr(Q.QuantizedLinear_fc2, "from_float", recorder("QuantizedLinear_fc2"))
+        kw = dict(plans["kwargs"])
+        if "fp6" in fn_name:
+            kw.update(w_bit=6, a_bit=6, act_fp_type="fp6_e2m3", weight_fp_type="fp6_e2m3", fc2_fp_type="fp6_int_neg_e2m3_pos")
+        out = getattr(Q, fn_name)(model, **kw)
+        assert out is model
+        want = plans[fn_name]
+        assert len(calls) == len(want) == 150
+        for got, ref in zip(calls, want):
+            assert got == ref, (fn_name, got, ref)
