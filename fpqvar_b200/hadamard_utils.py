@@ -35,3 +35,17 @@ def matmul_hadU(X, transpose=False):
 
 def matmul_hadUt(X):
     return matmul_hadU(X, transpose=True)
+
+
+def apply_exact_had_to_linear(module, had_dim=-1, output=False):
+    """hadamard_utils.py:119-154 (imported by rotation_utils.py:7, used only by the full-width rotation of fc2 / proj
+    outputs, which the reference's own rotate_model leaves commented out): W <- W @ H / sqrt(n) on the input side, or
+    H @ W on the output side, for power-of-two sizes, in float64 on the weight's device.  `had_dim != -1` needs the
+    external fast_hadamard_transform package in the reference and is not provided."""
+    assert isinstance(module, torch.nn.Linear)
+    if had_dim != -1:
+        raise NotImplementedError("apply_exact_had_to_linear(had_dim != -1): the chunked fast_hadamard_transform path is out of scope")
+    w = module.weight.data
+    w64 = w.double()
+    w64 = matmul_hadU(w64.t(), False).t() if output else matmul_hadU(w64, False)
+    module.weight.data = w64.to(device=w.device, dtype=w.dtype)

@@ -52,6 +52,36 @@ def block_random_hadamard_matrix(total_size=1920, block_size=128, device="cuda",
     return torch.block_diag(*([blk] * n_blocks)).to(device)
 
 
+def random_orthogonal_matrix(size, device):
+    """rotation_utils.py:38-55: QR of a standard normal fp64 matrix with the signs of diag(R) folded in (draws from the
+    global CPU RNG, like the reference)."""
+    random_matrix = torch.randn(size, size, dtype=torch.float64).to(device)
+    q, r = torch.linalg.qr(random_matrix)
+    q *= torch.sign(torch.diag(r)).unsqueeze(0)
+    return q
+
+
+def get_orthogonal_matrix(size, mode="hadamard", device=None, seed=42):
+    """rotation_utils.py:58-64.  mode="hadamard" is the full-width randomized Hadamard of `--rotate` without
+    `--block_rotate`: available for power-of-two sizes; the reference's K = 60 / 36 factor tables for C = 1920 / 2304
+    (hadamard_utils.py:28-39) are outside the hot path, so those sizes raise FpqError (use `--block_rotate`)."""
+    if mode == "random":
+        return random_orthogonal_matrix(size, device)
+    if mode == "hadamard":
+        return random_hadamard_matrix(size, device, seed)
+    raise ValueError(f"Unknown mode {mode}")
+
+
+def cleanup_memory() -> None:
+    """rotation_utils.py:11-35 (called by evaluate_fp_quant_transform_rotate.py:105 after rotate_model): run the garbage
+    collector and hand cached GPU memory back.  The fused weight kernels build no dense C x C temporaries, so there is
+    little to free; the call is kept so the reference's scripts run unchanged."""
+    import gc
+    gc.collect()
+    if torch.cuda.is_available():
+        torch.cuda.empty_cache()
+
+
 def block_sign_bits(block_size: int = 128, seed: int = 42):
     """The packed sign mask the kernels take (bit set = +1) for the reference's seed."""
     if block_size != 128:

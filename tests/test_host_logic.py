@@ -358,3 +358,34 @@ def test_mixed_datatype_variants_issue_the_reference_call_sequence(monkeypatch):
         assert len(calls) == len(want) == 150
         for got, ref in zip(calls, want):
             assert got == ref, (fn_name, got, ref)
+
+
+def test_rotation_module_exports_what_the_reference_scripts_use():
+    """evaluate_fp_quant_transform_rotate.py calls rotation_utils.cleanup_memory() / get_orthogonal_matrix(...), and
+    rotation_utils.py:7 imports apply_exact_had_to_linear / is_pow2 from hadamard_utils: a drop-in must carry the names."""
+    import torch
+    from fpqvar_b200 import hadamard_utils as H, rotation_utils as R
+    from fpqvar_b200._lib import FpqError
+    R.cleanup_memory()                                                    # no GPU here: gc only
+    q = R.get_orthogonal_matrix(128, "hadamard", "cpu")
+    assert torch.equal(q, R.random_hadamard_matrix(128, "cpu", 42))
+    assert torch.allclose(q @ q.T, torch.eye(128, dtype=torch.float64), atol=1e-12)
+    torch.manual_seed(0)
+    r = R.get_orthogonal_matrix(64, "random", "cpu")
+    assert r.dtype == torch.float64 and torch.allclose(r @ r.T, torch.eye(64, dtype=torch.float64), atol=1e-10)
+    with pytest.raises(ValueError):
+        R.get_orthogonal_matrix(64, "givens", "cpu")
+    with pytest.raises(FpqError):
+        R.get_orthogonal_matrix(1920, "hadamard", "cpu")                  # the K = 60 tables of the full-width rotation: out of scope
+    lin = torch.nn.Linear(64, 32, bias=False)
+    w0 = lin.weight.data.clone()
+    H.apply_exact_had_to_linear(lin)                                       # W @ H_64 / 8
+    assert torch.allclose(lin.weight.data.double(), w0.double() @ (R._sylvester(64) / 8.0), atol=1e-6)
+    H.apply_exact_had_to_linear(lin)                                       # H is an involution up to the scale: back to W
+    assert torch.allclose(lin.weight.data, w0, atol=1e-5)
+    lin2 = torch.nn.Linear(16, 64, bias=False)
+    w1 = lin2.weight.data.clone()
+    H.apply_exact_had_to_linear(lin2, output=True)
+    assert torch.allclose(lin2.weight.data.double(), (R._sylvester(64) / 8.0) @ w1.double(), atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        H.apply_exact_had_to_linear(lin, had_dim=16)
