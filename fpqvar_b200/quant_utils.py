@@ -223,6 +223,7 @@ quantize_activation_per_tensor_asymmetric = _out_of_scope("quantize_activation_p
 quantize_activation_per_group_sym = _out_of_scope("quantize_activation_per_group_sym")
 quantize_activation_per_group_asymmetric = _out_of_scope("quantize_activation_per_group_asymmetric")
 log2_quant_per_group_asym = _out_of_scope("log2_quant_per_group_asym")
+log2_quant_per_token_asym = _out_of_scope("log2_quant_per_token_asym")
 quantize_weight_per_channel_sym = _out_of_scope("quantize_weight_per_channel_sym")
 quantize_weight_per_tensor_sym = _out_of_scope("quantize_weight_per_tensor_sym")
 quantize_weight_per_group_sym = _out_of_scope("quantize_weight_per_group_sym")

@@ -115,6 +115,32 @@ def rotate_fc1(layer, Q=None, sign_bits=None):
     layer.ffn.fc1.weight.data = rotate_weight(w.contiguous(), None, sign_bits)
 
 
+def rotate_fc2(layer, Q):
+    """rotation_utils.py:155-163 (defined by the reference, its call in rotate_model is commented out): W_fc2 @ Q in fp64.
+    Q is a dense [4C, 4C] matrix here -- this path is offline, rarely used host code, not a hot-path kernel."""
+    w = layer.ffn.fc2.weight.data
+    layer.ffn.fc2.weight.data = torch.matmul(w.to(torch.float64), Q.to(w.device)).to(w.dtype)
+
+
+def rotate_ada_lin(layer, Q):
+    """rotation_utils.py:166-208 (also unused by the reference's rotate_model): the shift rows of the adaLN projection are
+    rotated (Q^T W for the weight rows, b Q for the bias); gamma and scale rows stay as they are -- the reference computes
+    rotated scale rows and then discards them (:191-192, :206-207), which is reproduced by leaving them untouched."""
+    lin = layer.ada_lin[1]
+    w, b = lin.weight.data, lin.bias.data
+    C = w.shape[1]
+    Q = Q.to(device=w.device, dtype=torch.float64)
+    w64, b64 = w.to(torch.float64), b.to(torch.float64)
+    w64 = torch.cat([w64[:4 * C], Q.T @ w64[4 * C:5 * C], Q.T @ w64[5 * C:6 * C]], dim=0)
+    b64 = torch.cat([b64[:4 * C], b64[4 * C:5 * C] @ Q, b64[5 * C:6 * C] @ Q], dim=0)
+    lin.weight.data, lin.bias.data = w64.to(w.dtype), b64.to(b.dtype)
+
+
+def block_diag(blocks):
+    """rotation_utils.py (helper of block_random_hadamard_matrix): equally sized square blocks on the diagonal."""
+    return torch.block_diag(*[b.to(device=blocks[0].device, dtype=blocks[0].dtype) for b in blocks])
+
+
 def rotate_model(model, device, block_rotate):
     """rotation_utils.py:211-240.  Only the block rotation of the README commands is implemented; the
     full-width randomized Hadamard (`block_rotate=False`, K = 60 / 36 Kronecker tables) is not on the

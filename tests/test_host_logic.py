@@ -389,3 +389,32 @@ def test_rotation_module_exports_what_the_reference_scripts_use():
     assert torch.allclose(lin2.weight.data.double(), (R._sylvester(64) / 8.0) @ w1.double(), atol=1e-6)
     with pytest.raises(NotImplementedError):
         H.apply_exact_had_to_linear(lin, had_dim=16)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/rotate_utils"), reason="needs the reference checkout (build container only)")
+def test_rotate_fc2_and_ada_lin_match_the_reference_functions():
+    """rotation_utils.rotate_fc2 / rotate_ada_lin (defined by the reference, unused by its rotate_model): bit-identical to
+    the reference's own functions, imported here with the shims of tests/golden/make_golden.py."""
+    import subprocess
+    import sys
+    code = r'''
+import sys, torch
+sys.path.insert(0, "%s/tests/golden"); sys.path.insert(0, "%s")
+import make_golden as MG
+MG._install_shims()
+from rotate_utils import rotation_utils as RR
+from fpqvar_b200 import rotation_utils as R
+torch.manual_seed(0)
+class L(torch.nn.Module):
+    def __init__(s):
+        super().__init__(); s.ffn = torch.nn.Module(); s.ffn.fc2 = torch.nn.Linear(64, 16)
+        s.ada_lin = torch.nn.Sequential(torch.nn.SiLU(), torch.nn.Linear(16, 96))
+a, b = L(), L(); b.load_state_dict(a.state_dict())
+Q64, Q16 = R.get_orthogonal_matrix(64, "hadamard", "cpu"), R.get_orthogonal_matrix(16, "hadamard", "cpu")
+RR.rotate_fc2(a, Q64); R.rotate_fc2(b, Q64); RR.rotate_ada_lin(a, Q16); R.rotate_ada_lin(b, Q16)
+assert all(torch.equal(p, q) for p, q in zip(a.state_dict().values(), b.state_dict().values()))
+assert torch.equal(RR.block_diag([Q16, Q16]), R.block_diag([Q16, Q16]))
+print("IDENTICAL")
+''' % (ROOT, ROOT)
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)   # own process: the shims patch sys.modules
+    assert "IDENTICAL" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
