@@ -49,3 +49,16 @@ def apply_exact_had_to_linear(module, had_dim=-1, output=False):
     w64 = w.double()
     w64 = matmul_hadU(w64.t(), False).t() if output else matmul_hadU(w64, False)
     module.weight.data = w64.to(device=w.device, dtype=w.dtype)
+
+
+def matmul_hadU_cuda(X, hadK=None, K=1, transpose=False):
+    """hadamard_utils.py:88-113 calls the external fast_hadamard_transform CUDA package for the power-of-two part and a
+    dense product with the K-table otherwise.  Only K == 1 (power-of-two sizes) exists here, computed by `matmul_hadU`
+    on X's device -- same value up to the summation order of the fp32 butterflies the external package uses."""
+    if K != 1 or hadK is not None:
+        raise NotImplementedError("matmul_hadU_cuda: the Kronecker-factor tables of the full-width rotation are out of scope")
+    return matmul_hadU(X, transpose)
+
+
+def matmul_hadUt_cuda(X, hadK=None, K=1):
+    return matmul_hadU_cuda(X, hadK, K, transpose=True)
