@@ -491,6 +491,16 @@ def _quantize_VAR_planned(model, plan, weight_quant, act_quant, w_bit, a_bit, ac
     return model
 
 
+def quantize_VAR_with_ada_lin(model, weight_quant=None, act_quant=None, quantize_bmm_input=False, w_bit=8, a_bit=8, kv_bit=8,
+                              act_quant_sym=None, fc2_act_log2_quant=None, quant_kv=None, activation_fp_quant=False,
+                              weight_fp_quant=False, act_fp_type=None, weight_fp_type=None, fc2_fp_type=None):
+    """`quantize_VAR` as the `models_fp_quant_rotate` package defines it (models_fp_quant_rotate/quant_utils.py:894-979):
+    the four linears of every block as in `quantize_VAR`, plus the adaLN projection `ada_lin[1]` of every block, which
+    the other packages leave in floating point (their branch is commented out, qu.py:1147-1155)."""
+    return _quantize_VAR_planned(model, lambda site, block: (None, None), weight_quant, act_quant, w_bit, a_bit, act_quant_sym,
+                                 fc2_act_log2_quant, activation_fp_quant, weight_fp_quant, act_fp_type, weight_fp_type, fc2_fp_type)
+
+
 def quantize_VAR_mixed_fp4_datatype(model, weight_quant=None, act_quant=None, quantize_bmm_input=False, w_bit=8, a_bit=8, kv_bit=8,
                                     act_quant_sym=None, fc2_act_log2_quant=None, quant_kv=None, activation_fp_quant=False,
                                     weight_fp_quant=False, act_fp_type=None, weight_fp_type=None, fc2_fp_type=None):

@@ -63,7 +63,11 @@ def main():
            "quantize_VAR_mixed_fp6_datatype": run("models_fp_quant", "quantize_VAR_mixed_fp6_datatype",
                                                   dict(KW, w_bit=6, a_bit=6, act_fp_type="fp6_e2m3", weight_fp_type="fp6_e2m3",
                                                        fc2_fp_type="fp6_int_neg_e2m3_pos")),
-           "quantize_VAR_use_different_datatype": run("models_fp_quant_rotate", "quantize_VAR_use_different_datatype", KW)}
+           "quantize_VAR_use_different_datatype": run("models_fp_quant_rotate", "quantize_VAR_use_different_datatype", KW),
+           # models_fp_quant_rotate/quant_utils.py:894-979: this package's quantize_VAR also quantizes every block's ada_lin[1]
+           "models_fp_quant_rotate.quantize_VAR": run("models_fp_quant_rotate", "quantize_VAR", KW),
+           # the README package: ada_lin stays FP (the branch is commented out, qu.py:1147-1155)
+           "models_fp_quant_transform_rotate.quantize_VAR": run("models_fp_quant_transform_rotate", "quantize_VAR", KW)}
     path = os.path.join(HERE, "reference_mixed_plans.json")
     with open(path, "w") as f:
         json.dump(out, f, indent=0, sort_keys=True)

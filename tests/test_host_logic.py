@@ -336,7 +336,9 @@ def test_mixed_datatype_variants_issue_the_reference_call_sequence(monkeypatch):
             super().__init__()
             self.blocks = nn.ModuleList(AdaLNSelfAttn() for _ in range(30))
 
-    for fn_name in ("quantize_VAR_mixed_fp4_datatype", "quantize_VAR_mixed_fp6_datatype", "quantize_VAR_use_different_datatype"):
+    fixture_key = {"quantize_VAR_with_ada_lin": "models_fp_quant_rotate.quantize_VAR", "quantize_VAR": "models_fp_quant_transform_rotate.quantize_VAR"}
+    for fn_name in ("quantize_VAR_mixed_fp4_datatype", "quantize_VAR_mixed_fp6_datatype", "quantize_VAR_use_different_datatype",
+                    "quantize_VAR_with_ada_lin", "quantize_VAR"):
         model = Model()
         paths = {id(m): n for n, m in model.named_modules()}
         calls = []
@@ -354,8 +356,11 @@ def test_mixed_datatype_variants_issue_the_reference_call_sequence(monkeypatch):
             kw.update(w_bit=6, a_bit=6, act_fp_type="fp6_e2m3", weight_fp_type="fp6_e2m3", fc2_fp_type="fp6_int_neg_e2m3_pos")
         out = getattr(Q, fn_name)(model, **kw)
         assert out is model
-        want = plans[fn_name]
-        assert len(calls) == len(want) == 150
+        want = plans[fixture_key.get(fn_name, fn_name)]
+        assert len(calls) == len(want) == (120 if fn_name == "quantize_VAR" else 150)
+        if fn_name == "quantize_VAR":                          # same calls; this repo's walk visits ffn / attn in registration order too
+            key = lambda c: (c["module"],)  # noqa: E731
+            assert sorted(calls, key=key) == sorted(want, key=key)
         for got, ref in zip(calls, want):
             assert got == ref, (fn_name, got, ref)
 
