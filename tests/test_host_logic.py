@@ -423,3 +423,17 @@ print("IDENTICAL")
 ''' % (ROOT, ROOT)
     out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)   # own process: the shims patch sys.modules
     assert "IDENTICAL" in out.stdout, out.stdout[-2000:] + out.stderr[-2000:]
+
+
+def test_bench_b200_arm_refuses_to_run_without_a_gpu():
+    """The product arm of bench.py has no CPU path: without a CUDA device it exits with an explicit message instead of
+    timing anything (the CPU numbers come only from `--impl reference`)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "1"], capture_output=True, text=True, timeout=300)
+    assert out.returncode != 0
+    assert "no CUDA device" in (out.stderr + out.stdout) and "no CPU fallback" in (out.stderr + out.stdout)
+    assert not any(line.startswith("{") for line in out.stdout.splitlines())
