@@ -140,8 +140,16 @@ def cpu_run_sample(calls, data, smooth, P):
             P.fake_quant(x, c.fmt, 128, "kernel", out_dtype={"f32": "float32", "f16": "float16"}[c.out_dtype])
         elif c.op == "signsplit":
             P.fake_quant_signsplit(x, c.fmt, 128, "kernel")
+        elif c.op == "mod_rotate_quant":
+            # the adaLN modulate in front of it (basic_var.py:263): numpy on the [B, rows_per_batch, C] view
+            b = c.rows // c.rows_per_batch
+            xm = x.reshape(b, c.rows_per_batch, c.cols) * MOD_GAIN[:b, None, :c.cols] + MOD_SHIFT[:b, None, :c.cols]
+            P.transform_rotate_quant(xm.reshape(c.rows, c.cols), smooth, c.fmt)
         else:
             P.transform_rotate_quant(x, smooth, c.fmt)
+
+
+MOD_GAIN = MOD_SHIFT = None
 
 
 def cpu_baseline(hot, seconds, steps=None, warmup=1, stages=0):
@@ -149,6 +157,10 @@ def cpu_baseline(hot, seconds, steps=None, warmup=1, stages=0):
     from oracle import port as P       # test infrastructure, used here as the timed CPU baseline only
     calls, data = cpu_sample_inputs(hot, np, stages=stages)
     smooth = np.exp(np.random.default_rng(1).uniform(-1, 1, hot.width)).astype(np.float32)
+    global MOD_GAIN, MOD_SHIFT
+    rng = np.random.default_rng(2)
+    MOD_GAIN = (1.0 + 0.3 * rng.standard_normal((2 * hot.batch, hot.width))).astype(np.float32)
+    MOD_SHIFT = (0.5 * rng.standard_normal((2 * hot.batch, hot.width))).astype(np.float32)
     nbytes = sum(c.bytes for c in calls)
     for _ in range(warmup):
         cpu_run_sample(calls, data, smooth, P)
@@ -181,6 +193,9 @@ def run_reference(args, hot):
         n_st = len(hot.patch_nums)
         calls, data = cpu_sample_inputs(hot, np, stages=n_st // 2)
         smooth = np.ones(hot.width, np.float32)
+        global MOD_GAIN, MOD_SHIFT
+        MOD_GAIN = np.ones((2 * hot.batch, hot.width), np.float32)
+        MOD_SHIFT = np.zeros((2 * hot.batch, hot.width), np.float32)
         t0 = time.perf_counter()
         cpu_run_sample(calls, data, smooth, P)
         t_half = time.perf_counter() - t0
@@ -339,7 +354,10 @@ def main():
     arenas = {"f32": Arena(a_f32), "f16": Arena(a_f16), "gelu": Arena(a_gelu), "out": Arena(a_out)}
     gs = torch.Generator(device="cpu"); gs.manual_seed(7)
     smooth = {site: torch.exp(torch.rand(C, generator=gs) * 2 - 1).to(dev) for site in ("mat_qkv", "fc1")} if hot.rotate_transform else {}
-    replay = DeviceReplay(dev, smooth)
+    modulate = {site: (1.0 + 0.3 * torch.randn(2 * hot.batch, C, generator=gs), 0.5 * torch.randn(2 * hot.batch, C, generator=gs))
+                for site in ("mat_qkv", "fc1")} if hot.modulate else {}
+    modulate = {k: (a.to(dev), b.to(dev)) for k, (a, b) in modulate.items()}
+    replay = DeviceReplay(dev, smooth, modulate=modulate)
 
     def in_arena(c):
         if c.in_dtype == "f32":
@@ -425,7 +443,7 @@ def main():
     if not args.no_e2e:
         max_in = max(c.in_bytes for c in calls)
         max_out = max(c.out_bytes for c in calls)
-        pipe = HostPipeline(dev, max_in, max_out, smooth)
+        pipe = HostPipeline(dev, max_in, max_out, smooth, modulate=modulate)
         h_f32 = torch.randn(max(c.in_bytes for c in calls if c.in_dtype == "f32") // 4 if any(c.in_dtype == "f32" for c in calls) else 1).pin_memory()
         h_f16 = torch.nn.functional.gelu(torch.randn(max(c.in_bytes for c in calls if c.in_dtype == "f16") // 2), approximate="tanh").to(torch.float16).pin_memory()
         h_out = [torch.empty(max_out, dtype=torch.uint8).pin_memory() for _ in range(2)]
@@ -476,7 +494,9 @@ def main():
         def kernel_name(key):
             op, fmt, din, dout = key
             if op == "rotate_quant":
-                return f"transform_rotate_quant_v2_kernel<{fmt}> (f32->f16)"
+                return f"transform_rotate_quant_{{tma,small}}_kernel<{fmt}> (f32->f16)"
+            if op == "mod_rotate_quant":
+                return f"modulate_transform_rotate_quant_{{tma,small}}_kernel<{fmt}> (adaLN modulate fused, f32->f16)"
             packed = din == "f16" and dout == "f16"
             base = {"group": "fake_quant_group", "signsplit": "signsplit_group"}[op]
             return f"{base}_h16_kernel<{fmt}> (f16->f16)" if packed else f"{base}_kernel<{din}->{dout},{fmt}>"

@@ -26,6 +26,8 @@ SIGNATURES = {
     "fpq_version": (_c.c_char_p, []),
     "fpq_last_cuda_error": (_c.c_char_p, []),
     "fpq_launch_count": (_c.c_uint64, []),
+    "fpq_set_tunable": (_c.c_int, [_c.c_char_p, _c.c_longlong]),
+    "fpq_rotate_plan": (_c.c_int, [_c.c_int, _c.c_void_p]),
     "fpq_quant_grid": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_size_t, _c.c_void_p, _c.c_int, _c.c_void_p]),
     "fpq_fake_quant": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                   _c.c_uint, _c.c_void_p]),
@@ -61,11 +63,21 @@ def lib() -> ctypes.CDLL:
                 "`make -C fpqvar_b200/csrc` (or __graft_entry__.build()).")
         handle = ctypes.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
-            fn = getattr(handle, name)        # AttributeError here = header and library out of sync
+            try:
+                fn = getattr(handle, name)    # AttributeError here = header and library out of sync
+            except AttributeError:
+                if os.environ.get("FPQ_LIB_PATH") and name in ("fpq_set_tunable", "fpq_rotate_plan"):
+                    continue                  # an older build selected for an A/B measurement (tools/): it has no tunables
+                raise
             fn.restype = res
             fn.argtypes = args
         _lib = handle
     return _lib
+
+
+def set_tunable(name: str, value: int) -> None:
+    """fpq_set_tunable: move a measured launch-geometry choice at run time (measurement tools and tests only)."""
+    check(lib().fpq_set_tunable(name.encode(), int(value)), f"fpq_set_tunable({name!r}, {value})")
 
 
 def check(rc: int, what: str) -> None:

@@ -55,6 +55,14 @@ static __constant__ GridTable c_grids[GT_COUNT] = {
 // launch bookkeeping (defined in fpq_grid.cu)
 int finish_launch();
 int sm_count();
+// Launch-geometry choices that were made from measurements and that the measurement tools (tools/rowbench.py,
+// tools/abbench.py) and the GPU tests move at run time through fpq_set_tunable() -- not through the environment.
+struct Tunables {
+    int pdl = 1;                               // programmatic dependent launch on (0: plain stream-ordered launches)
+    int row_v = 0;                             // values-per-thread of the per-token kernels: 0 = chosen by row_reg_vectors, else 1 | 2 | 4
+    long long rot_small_max_chunks = 24576;    // rotate launches up to this many 128-chunks take the small-launch kernel
+};
+extern Tunables g_tun;
 // symmetric fake quant, one translation unit per tie rule (fpq_sym_k.cu / fpq_sym_a.cu)
 int fake_quant_kernel_tie(int in_dtype, int out_dtype, int format, const void* x, void* out, size_t n_rows, size_t row_len, int clamp3, cudaStream_t st);
 int fake_quant_argmin_tie(int in_dtype, int out_dtype, int format, const void* x, void* out, size_t n_rows, size_t row_len, int clamp3, cudaStream_t st);
@@ -74,7 +82,7 @@ static inline unsigned grid_for(size_t work_items, size_t items_per_block, int b
 // Row-per-CTA persistent kernels (per_token / per_channel): how many values each thread keeps of its row (V uint4
 // vectors) and how many CTAs are REALLY resident per SM.  The grid must not exceed the resident CTAs: a persistent
 // CTA that only starts when another one has finished all of its rows runs a second, half-empty wave.
-// FPQ_ROW_V=1|2|4 overrides the choice (measurement aid; read per launch).
+// The tunable row_v = 1|2|4 overrides the choice (measurement aid).
 static inline int row_reg_vectors(size_t row_vecs, bool heavy_loop) {
     // Measured with tools/rowbench.py (profiles/r1_rowbench.txt).  Sign-split (heavy_loop): the smallest CTA wins at every
     // row length (V = 1 / 2 / 4 at 0.6 / 0.8 / 1.0), weighed against the lanes the last warp wastes.  Symmetric: CTAs of
@@ -90,10 +98,7 @@ static inline int row_reg_vectors(size_t row_vecs, bool heavy_loop) {
         else score /= 1.0f + fabsf(log2f(padded / 181.0f));
         if (score >= best) { best = score; v = c; }
     }
-    if (const char* e = getenv("FPQ_ROW_V")) {
-        const int f = atoi(e);
-        if ((f == 1 || f == 2 || f == 4) && (row_vecs + f - 1) / f <= 1024) v = f;
-    }
+    if (const int f = g_tun.row_v; (f == 1 || f == 2 || f == 4) && (row_vecs + f - 1) / f <= 1024) v = f;
     while ((row_vecs + v - 1) / v > 1024) v *= 2;
     return v;
 }
@@ -119,7 +124,6 @@ static inline unsigned resident_row_grid(KernelT kernel, int threads, size_t n_r
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-bool pdl_enabled();      // fpq_grid.cu: on unless FPQ_NO_PDL is set in the environment
 
 template <typename... KArgs, typename... Args>
 static inline void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args... args) {
@@ -132,7 +136,7 @@ static inline void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned 
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = g_tun.pdl ? 1 : 0;
     cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 

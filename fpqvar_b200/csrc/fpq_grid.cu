@@ -1,6 +1,7 @@
 // libfpq_b200 -- quant_cuda.quant compatibility entry (row a1), the exhaustive rounding self-test, and launch bookkeeping
 // Part of the C ABI of include/fpq_b200.h; no torch types here.
 #include <cstdlib>
+#include <cstring>
 #include "fpq_common.cuh"
 
 namespace fpq {
@@ -92,10 +93,7 @@ int finish_launch() {
     return FPQ_OK;
 }
 
-bool pdl_enabled() {
-    static const bool on = (getenv("FPQ_NO_PDL") == nullptr);
-    return on;
-}
+Tunables g_tun;
 
 int sm_count() {
     static int n = 0;
@@ -114,6 +112,18 @@ using namespace fpq;
 extern "C" const char* fpq_version(void) { return "fpq_b200 0.1 (sm_100a)"; }
 extern "C" const char* fpq_last_cuda_error(void) { return cudaGetErrorString(t_last_err); }
 extern "C" uint64_t fpq_launch_count(void) { return t_launches; }
+
+extern "C" int fpq_set_tunable(const char* name, long long value) {
+    if (name == nullptr) return FPQ_ERR_ARG;
+    if (strcmp(name, "pdl") == 0) { g_tun.pdl = value != 0; return FPQ_OK; }
+    if (strcmp(name, "row_v") == 0) {
+        if (value != 0 && value != 1 && value != 2 && value != 4) return FPQ_ERR_ARG;
+        g_tun.row_v = int(value);
+        return FPQ_OK;
+    }
+    if (strcmp(name, "rot_small_max_chunks") == 0) { g_tun.rot_small_max_chunks = value; return FPQ_OK; }
+    return FPQ_ERR_ARG;
+}
 
 extern "C" int fpq_quant_grid(const float* x, const float* grid, int k, size_t n, float* z, int tie_mode, void* stream) {
     if (k < 1 || k > 256 || (n && (!x || !z)) || !grid) return FPQ_ERR_ARG;

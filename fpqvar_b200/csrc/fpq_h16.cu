@@ -1,28 +1,19 @@
 // libfpq_b200 -- packed fp16 -> fp16 kernels (kernel tie rule, groups of 128): the activation
 // quantizers of the hot path (reference rows a2, a3 of SURVEY.md section 8) at low instruction
 // count, see fpq_h16.cuh.  Part of the C ABI of include/fpq_b200.h; no torch types here.
-#include "fpq_stream.cuh"
+#include "fpq_h16.cuh"
 
 namespace fpq {
 
-// Software pipelining (two register tiles in ping-pong).  Measured on B200 (tools/kbench.py,
-// profiles/r1_kbench.txt, the "variant" sections): +3 % for the symmetric kernel (42 -> 70 registers), -8 % for the
-// sign-split kernel (52 -> 84 registers, occupancy drops to 3 CTAs), so only the former uses it.
-#ifndef FPQ_SYM_PREFETCH
-#define FPQ_SYM_PREFETCH 1
-#endif
+// Software pipelining (two register tiles in ping-pong).  Measured on B200 (tools/kbench.py, profiles/r1_kbench.txt, the
+// "variant" sections): +3 % for the symmetric kernel (42 -> 70 registers), -8 % for the sign-split kernel (52 -> 84
+// registers, occupancy drops to 3 CTAs), so only the former uses it.
 // Occupancy of the sign-split kernel, measured (profiles/r1_kbench.txt, kbench_11): as compiled (56 registers, 4 CTAs/SM)
 // 6.31 TB/s burst / 5.67 sustained; forced to 5 CTAs (48 registers, spills) 5.75 / 5.35; 6 CTAs (40 registers) 5.48 / 5.49;
 // 2 CTAs (90 registers) 5.26 / 5.20.  Plain __launch_bounds__(256) it stays.
-#ifndef FPQ_SPLIT_PREFETCH
-#define FPQ_SPLIT_PREFETCH 0
-#endif
 // lanes per 128-group.  Measured: 2 lanes x 64 halves is slower (sign-split 5.36 vs 6.40 TB/s burst, 5.30 vs 5.66 sustained;
 // symmetric 5.59 vs 6.34): a warp-wide load then touches 16 groups x 32 bytes instead of 8 x 64.
-#ifndef FPQ_H16_LPG
-#define FPQ_H16_LPG 4
-#endif
-constexpr int H16_LPG = FPQ_H16_LPG;          // lanes per 128-group
+constexpr int H16_LPG = 4;             // lanes per 128-group
 constexpr int H16_NV = 16 / H16_LPG;   // 16-byte vectors per lane and group (4 lanes: 32 halves = 16 packed words per lane)
 constexpr int H16_NW = 4 * H16_NV;
 constexpr int H16_GPW = 32 / H16_LPG;   // groups per warp and loop trip
@@ -70,7 +61,6 @@ __global__ void __launch_bounds__(256) fake_quant_group_h16_kernel(const __half*
             else literal_sym_h16(x + g * 128, out + g * 128, lig, H16_LPG, 8, H16_NV, s, SymFmt<FMT>::GT);
         }
     };
-#if FPQ_SYM_PREFETCH
     // two register tiles in ping-pong: the loads of the next trip are in flight while this one computes
     uint32_t A[H16_NW], B[H16_NW];
     size_t g0 = warp_global * H16_GPW;
@@ -82,13 +72,6 @@ __global__ void __launch_bounds__(256) fake_quant_group_h16_kernel(const __half*
         if (g2 < n_groups) load(g2, A);
         if (g1 < n_groups) work(g1, B);
     }
-#else
-    for (size_t gbase = warp_global * H16_GPW; gbase < n_groups; gbase += stride) {
-        uint32_t p[H16_NW];
-        load(gbase, p);
-        work(gbase, p);
-    }
-#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -181,12 +164,9 @@ __device__ __forceinline__ int split_quant_tile_h16(uint32_t (&p)[NW], float& sn
         sp = rnd_in<__half>(__fdiv_rn(ap, SF::POS::VMAX));
         return 1;
     }
-    constexpr float K = SplitScale<typename SF::NEG, typename SF::POS>::K;      // power of two: both products exact
-    const float rn = nbits == 0u ? 0.0f : rcp_rn_normal(sn) * K;
-    const float rp = pbits == 0u ? 0.0f : rcp_rn_normal(sp);
-    const float snk = sn * (1.0f / K);
+    const SplitK k = make_splitk(sn, nbits == 0u ? 0.0f : rcp_rn_normal(sn), sp, pbits == 0u ? 0.0f : rcp_rn_normal(sp));
 #pragma unroll
-    for (int i = 0; i < NW; ++i) p[i] = split_pair_h16<typename SF::NEG, typename SF::POS>(p[i], rn, snk, rp, sp, delta);
+    for (int i = 0; i < NW; ++i) p[i] = split_pair_h16<typename SF::NEG, typename SF::POS>(p[i], k, delta);
     return 0;
 }
 
@@ -244,144 +224,12 @@ __global__ void __launch_bounds__(256) signsplit_group_h16_kernel(const __half* 
             else literal_split_nan_group_h16(x + g * 128, out + g * 128, lig, H16_LPG, 8, H16_NV, SF::NEG::VMAX, SF::POS::VMAX, SF::GT_N, SF::GT_P);
         }
     };
-#if FPQ_SPLIT_PREFETCH
-    uint32_t A[H16_NW], B[H16_NW];
-    size_t g0 = warp_global * H16_GPW;
-    if (g0 < n_groups) load(g0, A);
-    for (; g0 < n_groups; g0 += 2 * stride) {
-        const size_t g1 = g0 + stride, g2 = g1 + stride;
-        if (g1 < n_groups) load(g1, B);
-        work(g0, A);
-        if (g2 < n_groups) load(g2, A);
-        if (g1 < n_groups) work(g1, B);
-    }
-#else
     for (size_t gbase = warp_global * H16_GPW; gbase < n_groups; gbase += stride) {
         uint32_t p[H16_NW];
         load(gbase, p);
         work(gbase, p);
     }
-#endif
     if (nan_flag != nullptr) poison_epilogue(out, n_groups * 128, nan_flag);
-}
-
-// ------------------------------------------------------------------------------------------
-// TMA-staged variants (fpq_stream.cuh): tiles of 64 groups (16 KB), 4 stages, 8 consumer warps x 8 groups
-// ------------------------------------------------------------------------------------------
-constexpr int ST_TILE_GROUPS = ST_CONSUMER_WARPS * H16_GPW;
-constexpr int ST_TILE_BYTES_H16 = ST_TILE_GROUPS * 256;
-using StreamSmemH16 = StreamSmem<ST_TILE_BYTES_H16, 4>;
-
-// Consumer side of one tile: lane set gi (of 8 in the warp) owns group warp*8+gi of the tile.  Vector
-// order is swizzled by the parity of gi so that the two lane sets of a quarter-warp (LDS.128 phase) read
-// different 64-byte halves of the 128-byte bank window: conflict-free.
-__device__ __forceinline__ int h16_vec(int j, int gi, int lig) { return ((j ^ (gi & 1)) * H16_LPG + lig); }
-
-__device__ __forceinline__ void lds_tile_h16(const unsigned char* gsm, int gi, int lig, bool valid, uint32_t (&p)[H16_NW]) {
-#pragma unroll
-    for (int j = 0; j < H16_NV; ++j) {
-        uint4 u = make_uint4(0u, 0u, 0u, 0u);
-        if (valid) u = *reinterpret_cast<const uint4*>(gsm + h16_vec(j, gi, lig) * 16);
-        p[4 * j] = u.x; p[4 * j + 1] = u.y; p[4 * j + 2] = u.z; p[4 * j + 3] = u.w;
-    }
-}
-__device__ __forceinline__ void stg_tile_h16_swz(__half* base, int gi, int lig, const uint32_t (&p)[H16_NW]) {
-#pragma unroll
-    for (int j = 0; j < H16_NV; ++j) stg_stream(base + h16_vec(j, gi, lig) * 8, make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]));
-}
-
-template <int FMT>
-__global__ void __launch_bounds__(ST_THREADS) fake_quant_group_h16_tma_kernel(const __half* __restrict__ x, __half* __restrict__ out, size_t n_groups) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    StreamSmemH16& sm = *reinterpret_cast<StreamSmemH16*>(smem_raw);
-    stream_init(sm);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t n_tiles = (n_groups + ST_TILE_GROUPS - 1) / ST_TILE_GROUPS;
-    if (warp == ST_CONSUMER_WARPS) {
-        if (lane == 0)
-            stream_producer(sm, n_tiles, [&](size_t t) { return x + t * ST_TILE_GROUPS * 128; },
-                            [&](size_t t) { const size_t g = n_groups - t * ST_TILE_GROUPS; return uint32_t((g < ST_TILE_GROUPS ? g : ST_TILE_GROUPS) * 256); });
-        return;
-    }
-    const int gi = lane / H16_LPG, lig = lane % H16_LPG;
-    const float delta = tie_delta_kernel(uint32_t((size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 38));
-    uint32_t k = 0;
-    for (size_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
-        const uint32_t s = k % StreamSmemH16::NSTAGES, ph = (k / StreamSmemH16::NSTAGES) & 1u;
-        const size_t g = t * ST_TILE_GROUPS + warp * H16_GPW + gi;
-        const bool valid = g < n_groups;
-        mbar_wait(&sm.full[s], ph);
-        uint32_t p[H16_NW];
-        lds_tile_h16(sm.tile[s] + (warp * H16_GPW + gi) * 256, gi, lig, valid, p);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[s]);                  // the stage can be refilled while we compute
-        float sc;
-        const bool ok = sym_quant_tile_h16<FMT, H16_LPG, H16_NW>(p, sc, delta);
-        if (valid) {
-            if (ok) stg_tile_h16_swz(out + g * 128, gi, lig, p);
-            else literal_sym_h16(x + g * 128, out + g * 128, lig, H16_LPG, 8, H16_NV, sc, SymFmt<FMT>::GT);
-        }
-    }
-}
-
-template <int SPLIT>
-__global__ void __launch_bounds__(ST_THREADS) signsplit_group_h16_tma_kernel(const __half* __restrict__ x, __half* __restrict__ out, size_t n_groups,
-                                                                             unsigned* __restrict__ nan_flag) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    StreamSmemH16& sm = *reinterpret_cast<StreamSmemH16*>(smem_raw);
-    stream_init(sm);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const size_t n_tiles = (n_groups + ST_TILE_GROUPS - 1) / ST_TILE_GROUPS;
-    if (warp == ST_CONSUMER_WARPS) {
-        if (lane == 0)
-            stream_producer(sm, n_tiles, [&](size_t t) { return x + t * ST_TILE_GROUPS * 128; },
-                            [&](size_t t) { const size_t g = n_groups - t * ST_TILE_GROUPS; return uint32_t((g < ST_TILE_GROUPS ? g : ST_TILE_GROUPS) * 256); });
-        return;
-    }
-    using SF = SplitH16<SPLIT>;
-    const int gi = lane / H16_LPG, lig = lane % H16_LPG;
-    const float delta = tie_delta_kernel(uint32_t((size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 38));
-    uint32_t k = 0;
-    for (size_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++k) {
-        const uint32_t s = k % StreamSmemH16::NSTAGES, ph = (k / StreamSmemH16::NSTAGES) & 1u;
-        const size_t g = t * ST_TILE_GROUPS + warp * H16_GPW + gi;
-        const bool valid = g < n_groups;
-        mbar_wait(&sm.full[s], ph);
-        uint32_t p[H16_NW];
-        lds_tile_h16(sm.tile[s] + (warp * H16_GPW + gi) * 256, gi, lig, valid, p);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[s]);
-        float sn, sp;
-        const int rc = split_quant_tile_h16<SPLIT, H16_LPG, H16_NW>(p, sn, sp, delta);
-        if (rc == 2 && nan_flag != nullptr) atomicOr(nan_flag, 1u);
-        if (valid) {
-            if (rc == 0) stg_tile_h16_swz(out + g * 128, gi, lig, p);
-            else if (rc == 1) literal_split_h16(x + g * 128, out + g * 128, lig, H16_LPG, 8, H16_NV, sn, sp, SF::GT_N, SF::GT_P);
-            else literal_split_nan_group_h16(x + g * 128, out + g * 128, lig, H16_LPG, 8, H16_NV, SF::NEG::VMAX, SF::POS::VMAX, SF::GT_N, SF::GT_P);
-        }
-    }
-}
-
-// Measured on B200 (tools/kbench.py, profiles/r1_kbench.txt, kbench_6): the TMA-staged variants are
-// parity-green but SLOWER than the LDG kernels back to back (sign-split 6.06 vs 6.29 TB/s burst, 5.32 vs
-// 5.66 sustained; symmetric 5.57 vs 6.30), although a single cold launch under ncu runs at the same
-// 6.2 TB/s (127 us): 3 CTAs x 8 consumer warps per SM and a static tile round-robin leave the SMs idle
-// 16 % of the cycles.  Kept behind this switch for the next round (dynamic tile scheduler, 2 CTAs x 16
-// warps); off by default.
-#ifndef FPQ_H16_TMA
-#define FPQ_H16_TMA 0
-#endif
-// below this many groups the plain LDG kernels are used (fewer than ~2 tiles per SM: nothing to pipeline)
-constexpr size_t ST_MIN_GROUPS = size_t(ST_TILE_GROUPS) * 148 * 2;
-
-template <class K>
-static bool tma_smem_ok(K kernel) {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(sizeof(StreamSmemH16))) == cudaSuccess;
-}
-static unsigned grid_tma(size_t n_groups) {
-    const size_t n_tiles = (n_groups + ST_TILE_GROUPS - 1) / ST_TILE_GROUPS;
-    const size_t cap = size_t(sm_count()) * 3;                    // 3 CTAs x 64 KB of stages per SM
-    return unsigned(n_tiles < cap ? n_tiles : cap);
 }
 
 static unsigned grid_h16(size_t n_groups) {
@@ -392,24 +240,6 @@ static unsigned grid_h16(size_t n_groups) {
 int launch_sym_h16(int format, const void* x, void* out, size_t n_groups, cudaStream_t st) {
     const __half* xi = static_cast<const __half*>(x);
     __half* oo = static_cast<__half*>(out);
-#if FPQ_H16_TMA
-    if (n_groups >= ST_MIN_GROUPS) {
-        const unsigned g = grid_tma(n_groups);
-        const size_t smem = sizeof(StreamSmemH16);
-#define FPQ_SYM_TMA(F) { static const bool ok = tma_smem_ok(fake_quant_group_h16_tma_kernel<F>); if (!ok) return FPQ_ERR_CUDA; \
-                         fake_quant_group_h16_tma_kernel<F><<<g, ST_THREADS, smem, st>>>(xi, oo, n_groups); }
-        switch (format) {
-            case FPQ_FMT_E2M1: FPQ_SYM_TMA(FPQ_FMT_E2M1) break;
-            case FPQ_FMT_E1M2: FPQ_SYM_TMA(FPQ_FMT_E1M2) break;
-            case FPQ_FMT_E3M0: FPQ_SYM_TMA(FPQ_FMT_E3M0) break;
-            case FPQ_FMT_E2M3: FPQ_SYM_TMA(FPQ_FMT_E2M3) break;
-            case FPQ_FMT_E3M2: FPQ_SYM_TMA(FPQ_FMT_E3M2) break;
-            default: return FPQ_ERR_ARG;
-        }
-#undef FPQ_SYM_TMA
-        return finish_launch();
-    }
-#endif
     const unsigned grid = grid_h16(n_groups);
     switch (format) {
         case FPQ_FMT_E2M1: launch_pdl(fake_quant_group_h16_kernel<FPQ_FMT_E2M1>, grid, 256, 0, st, xi, oo, n_groups); break;
@@ -440,22 +270,6 @@ int launch_sym_h16_g64(int format, const void* x, void* out, size_t n_groups, cu
 int launch_split_h16(int split, const void* x, void* out, size_t n_groups, unsigned* nan_flag, cudaStream_t st) {
     const __half* xi = static_cast<const __half*>(x);
     __half* oo = static_cast<__half*>(out);
-#if FPQ_H16_TMA
-    if (n_groups >= ST_MIN_GROUPS && nan_flag == nullptr) {       // the whole-tensor clip epilogue lives in the LDG kernel only
-        const unsigned g = grid_tma(n_groups);
-        const size_t smem = sizeof(StreamSmemH16);
-#define FPQ_SPLIT_TMA(F) { static const bool ok = tma_smem_ok(signsplit_group_h16_tma_kernel<F>); if (!ok) return FPQ_ERR_CUDA; \
-                           signsplit_group_h16_tma_kernel<F><<<g, ST_THREADS, smem, st>>>(xi, oo, n_groups, nan_flag); }
-        switch (split) {
-            case FPQ_SPLIT_E1M2NEG_E2M1POS: FPQ_SPLIT_TMA(FPQ_SPLIT_E1M2NEG_E2M1POS) break;
-            case FPQ_SPLIT_INTNEG_E2M3POS: FPQ_SPLIT_TMA(FPQ_SPLIT_INTNEG_E2M3POS) break;
-            case FPQ_SPLIT_AFPQ_E2M1: FPQ_SPLIT_TMA(FPQ_SPLIT_AFPQ_E2M1) break;
-            default: return FPQ_ERR_ARG;
-        }
-#undef FPQ_SPLIT_TMA
-        return finish_launch();
-    }
-#endif
     const unsigned grid = grid_h16(n_groups);
     switch (split) {
         case FPQ_SPLIT_E1M2NEG_E2M1POS: launch_pdl(signsplit_group_h16_kernel<FPQ_SPLIT_E1M2NEG_E2M1POS>, grid, 256, 0, st, xi, oo, n_groups, nan_flag); break;
@@ -491,25 +305,34 @@ __global__ void selftest_f16_flow_kernel(unsigned long long* result) {
         const float r = rcp_rn_normal(s);
         const float delta = tie_delta_kernel(0u);
         if (xb == 0 && __float_as_uint(r) != __float_as_uint(__frcp_rn(s))) { ++bad; if (idx < first) first = idx; }
-        uint32_t got, want;
+        // The pair under test holds x in its low half and -x in its high half (both halves and both signs of the packed
+        // instructions at once); a half whose value cannot occur next to this scale is not compared.
+        const uint32_t x2 = uint32_t(xb) | (uint32_t(xb ^ 0x8000u) << 16);
+        uint32_t got, want[2];
+        bool check[2];
         if constexpr (CODE < 16) {
             using HG = typename SymFmt<CODE>::HG;
-            if (!pair_possible<HG>(x, s)) continue;
-            got = sym_pair_h16<HG>(uint32_t(xb), pk(r, r), pk(s, s), delta) & 0xffffu;
-            want = f2h(quant_elem_literal<__half, TIE_KERNEL>(x, s, c_grids[SymFmt<CODE>::GT]) * s);
+            if (!scale_bits_regular_for<HG>(sb)) continue;      // scales the kernels send down the literal path
+            check[0] = check[1] = pair_possible<HG>(x, s);
+            got = sym_pair_h16<HG>(x2, make_symk<HG>(s, r), delta);
+            want[0] = f2h(quant_elem_literal<__half, TIE_KERNEL>(x, s, c_grids[SymFmt<CODE>::GT]) * s);
+            want[1] = f2h(quant_elem_literal<__half, TIE_KERNEL>(-x, s, c_grids[SymFmt<CODE>::GT]) * s);
         } else {
             using SF = SplitH16<CODE - 16>;
-            // the other side's scale does not influence this element: use the same s on both sides
-            const bool pos = x > 0.0f;
-            if (pos ? !pair_possible<typename SF::POS>(x, s) : !pair_possible<typename SF::NEG>(x, s)) continue;
-            constexpr float K = SplitScale<typename SF::NEG, typename SF::POS>::K;
-            got = split_pair_h16<typename SF::NEG, typename SF::POS>(uint32_t(xb), r * K, s * (1.0f / K), r, s, delta) & 0xffffu;
-            const float xn = (x <= 0.0f) ? x : 0.0f, xp = pos ? x : 0.0f;
-            const float qn = scan_kernel_rule(rnd_in<__half>(__fdiv_rn(xn, s)), c_grids[SF::GT_N].v, c_grids[SF::GT_N].k);
-            const float qp = scan_kernel_rule(rnd_in<__half>(__fdiv_rn(xp, s)), c_grids[SF::GT_P].v, c_grids[SF::GT_P].k);
-            want = f2h(__fadd_rn(__fmul_rn(qn, s), __fmul_rn(qp, s)));
+            // the other side's scale does not influence an element: use the same s on both sides
+            got = split_pair_h16<typename SF::NEG, typename SF::POS>(x2, make_splitk(s, r, s, r), delta);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const float xv = h ? -x : x;
+                const bool pos = xv > 0.0f;
+                check[h] = pos ? pair_possible<typename SF::POS>(xv, s) : pair_possible<typename SF::NEG>(xv, s);
+                const float xn = (xv <= 0.0f) ? xv : 0.0f, xp = pos ? xv : 0.0f;
+                const float qn = scan_kernel_rule(rnd_in<__half>(__fdiv_rn(xn, s)), c_grids[SF::GT_N].v, c_grids[SF::GT_N].k);
+                const float qp = scan_kernel_rule(rnd_in<__half>(__fdiv_rn(xp, s)), c_grids[SF::GT_P].v, c_grids[SF::GT_P].k);
+                want[h] = f2h(__fadd_rn(__fmul_rn(qn, s), __fmul_rn(qp, s)));
+            }
         }
-        if (got != want) { ++bad; if (idx < first) first = idx; }
+        if ((check[0] && (got & 0xffffu) != want[0]) || (check[1] && (got >> 16) != want[1])) { ++bad; if (idx < first) first = idx; }
     }
     // scale: half(a * RN(1/VMAX)) == half(a / VMAX) for every fp16 absmax a whose scale is regular by
     // either formula (irregular scales are recomputed with the true division)

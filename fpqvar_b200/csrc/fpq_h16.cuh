@@ -3,23 +3,25 @@
 //
 // The generic path (fpq_common.cuh) spends ~20-38 instructions per element and is issue-bound on
 // B200 (ncu: 85 % issue-slot utilisation at 36 % DRAM, profiles/r1a_generic_kernels_ncu.txt).  At 4 bytes per
-// element the HBM roofline leaves ~20 issue slots per element, so this path is written for
-// instruction count (~8 per element):
+// element the HBM roofline leaves ~20 issue slots per element at full clocks and ~16 under the 1000 W
+// cap, so this path is written for instruction count (~5 per element for the hardware formats):
 //   * two elements per instruction wherever the ISA allows it: FMUL2 / FFMA2 (packed fp32,
-//     sm_100), F2FP.PACK_AB, VIMNMX3 on 16x2 lanes;
-//   * grid rounding without a division, a directed-rounding add or integer masking per element:
-//       w = v + delta          v = half(x * RN(1/s)) == half(x/s) (proof: fpq_common.cuh), widened by the
-//                              mixed-precision add FHADD (add.f32.f16), which adds delta for free.
-//                              delta = +2^-17 moves exact midpoints to the side the kernel rule sends
-//                              them to (+inf) and is smaller than the distance from any other fp16
-//                              value to a midpoint, so nothing else changes side; v has 11
-//                              significant bits, so v + delta is exact in fp32.
-//       p = 2^max(exponent(w), EMIN)
-//       y = RN(p * 1.5*2^(23-M) + w)      the round-to-nearest-even of the FFMA does the grid rounding
-//                                         (w is never a tie any more): ulp(y) = 2^(E-M)
-//       q = y - p * 1.5*2^(23-M)          exact
-//     which handles the subnormal region of the target format (exponent clamp) and every binade
-//     with the same instructions;
+//     sm_100), F2FP.PACK_AB, HMNMX2 on |x| for the absmax, HFMA2 for the rescale;
+//   * grid rounding by the FP4 / FP6 CONVERSION HARDWARE of sm_100a for the formats it knows
+//     (e2m1, e2m3, e3m2 = F2FP.SATFINITE.E2M1 / .E2M3 / .E3M2 and the UNPACK_B back to fp16):
+//       v = half(x * RN(1/s)) == half(x/s)   (proof: fpq_common.cuh)
+//       w = v + 2^-17          widened by the mixed-precision add FHADD (add.f32.f16), which adds the
+//                              tie shift for free: +2^-17 moves exact midpoints to the side the kernel
+//                              rule sends them to (+inf) and is smaller than the distance from any
+//                              other fp16 value to a midpoint, so nothing else changes side; v has 11
+//                              significant bits, so v + 2^-17 is exact in fp32 and never a tie.
+//       q = fp16( cvt.rn.satfinite.<fmt>x2( w ) )          two elements per instruction, both ways
+//       out = fma.rn.f16x2(q, s, +0)   q has <= 4 significant bits and s 11, so the fp16 FMA rounds the
+//                              EXACT product once, like half(float(q) * float(s)); the +0 addend turns
+//                              the -0 the sign-magnitude formats return for tiny negative w into the
+//                              reference's +0 (its grid holds +0.0 only);
+//   * for the other formats (e1m2, e3m0) the same w goes through a magic-number FFMA:
+//       p = 2^max(exponent(w), EMIN);  y = RN(p * 1.5*2^(23-M) + w);  q = y - p * 1.5*2^(23-M)
 //   * per-group scalars without the guarded library sequences: s = half(a * RN(1/VMAX)) (equal to
 //     half(a / VMAX) for every fp16 a) and r = RN(1/s) by MUFU.RCP + one Newton step (s is a normal
 //     fp16 number here).
@@ -69,6 +71,17 @@ __device__ __forceinline__ uint64_t widen_h2(uint32_t h2) {              // two 
     const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h2));
     return pk(f.x, f.y);
 }
+__device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c) {     // fp16x2 fused multiply-add, one rounding
+    uint32_t d;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t hadd2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t dup_h(__half h) { return uint32_t(__half_as_ushort(h)) * 0x00010001u; }
 
 // The tie shift delta = 2^-17 of the kernel rule (header comment), kept in ONE vector register:
 // FHADD takes no immediate and no uniform register, and ptxas would otherwise copy the constant
@@ -85,31 +98,94 @@ template <class HG> struct Magic {
     static constexpr float INV_VMAX = 1.0f / HG::VMAX;         // RN(1/VMAX), evaluated by the compiler in fp32
 };
 
-// q = R_K(v) for the two halves of v2 (finite, |v| within the format's range), as packed fp32.
-// `em`/`sc` may differ per element (sign-split formats).
-__device__ __forceinline__ uint64_t round_pair_magic(uint32_t v2, float delta, float em0, float em1, float sc0, float sc1) {
-    const float w0 = fhadd(uint16_t(v2 & 0xffffu), delta);
-    const float w1 = fhadd(uint16_t(v2 >> 16), delta);
-    const float p0 = __uint_as_float(__float_as_uint(fmaxf(fabsf(w0), em0)) & 0x7F800000u);
-    const float p1 = __uint_as_float(__float_as_uint(fmaxf(fabsf(w1), em1)) & 0x7F800000u);
+// ---- grid rounding of a packed pair ------------------------------------------------------------
+// Formats the sm_100a conversion hardware knows: fp32 pair -> two 4/6-bit codes -> fp16 pair, two
+// instructions (F2FP.SATFINITE.<fmt>.F32.PACK_AB_MERGE_C + F2FP.F16.<fmt>.UNPACK_B).  The hardware
+// rounds to nearest EVEN; the caller's tie shift has removed every tie, so "nearest" is all that is
+// used.  satfinite clamps to +-VMAX, which is also what the reference's scan answers above the grid.
+// PRE: e1m2 (uniform, step 1/4 up to 1.75) is not a hardware format, but HALF of it is the uniform low end of e2m3
+// (step 1/8 up to 0.875): the group's reciprocal scale is halved and its scale doubled, both exact.  The doubled
+// scale must stay a finite fp16 number: S_MAX_BITS bounds the "regular" scales of the format.
+template <class HG> struct HwCvt { static constexpr bool OK = false; static constexpr float PRE = 1.0f; static constexpr uint32_t S_MAX_BITS = 0x7BFFu; };
+template <> struct HwCvt<HG_E2M1> {
+    static constexpr bool OK = true;
+    static constexpr float PRE = 1.0f;
+    static constexpr uint32_t S_MAX_BITS = 0x7BFFu;
+    static __device__ __forceinline__ uint32_t round_trip(float w0, float w1) {
+        uint32_t q2;
+        asm("{ .reg .b8 t; cvt.rn.satfinite.e2m1x2.f32 t, %1, %2; cvt.rn.f16x2.e2m1x2 %0, t; }" : "=r"(q2) : "f"(w1), "f"(w0));
+        return q2;
+    }
+};
+template <> struct HwCvt<HG_E2M3> {
+    static constexpr bool OK = true;
+    static constexpr float PRE = 1.0f;
+    static constexpr uint32_t S_MAX_BITS = 0x7BFFu;
+    static __device__ __forceinline__ uint32_t round_trip(float w0, float w1) {
+        uint32_t q2;
+        asm("{ .reg .b16 t; cvt.rn.satfinite.e2m3x2.f32 t, %1, %2; cvt.rn.f16x2.e2m3x2 %0, t; }" : "=r"(q2) : "f"(w1), "f"(w0));
+        return q2;
+    }
+};
+template <> struct HwCvt<HG_E3M2> {
+    static constexpr bool OK = true;
+    static constexpr float PRE = 1.0f;
+    static constexpr uint32_t S_MAX_BITS = 0x7BFFu;
+    static __device__ __forceinline__ uint32_t round_trip(float w0, float w1) {
+        uint32_t q2;
+        asm("{ .reg .b16 t; cvt.rn.satfinite.e3m2x2.f32 t, %1, %2; cvt.rn.f16x2.e3m2x2 %0, t; }" : "=r"(q2) : "f"(w1), "f"(w0));
+        return q2;
+    }
+};
+template <> struct HwCvt<HG_E1M2> {
+    static constexpr bool OK = true;
+    static constexpr float PRE = 0.5f;
+    static constexpr uint32_t S_MAX_BITS = 0x77FFu;          // 2 * s stays finite
+    static __device__ __forceinline__ uint32_t round_trip(float w0, float w1) { return HwCvt<HG_E2M3>::round_trip(w0, w1); }
+};
+
+// Any other half grid: q = R_K(w) by a magic-number FFMA, as packed fp32.
+__device__ __forceinline__ uint64_t round_pair_magic(float w0, float w1, float em, float sc) {
+    const float p0 = __uint_as_float(__float_as_uint(fmaxf(fabsf(w0), em)) & 0x7F800000u);
+    const float p1 = __uint_as_float(__float_as_uint(fmaxf(fabsf(w1), em)) & 0x7F800000u);
     const uint64_t p = pk(p0, p1), w = pk(w0, w1);
-    const uint64_t y = ffma2(p, pk(sc0, sc1), w);
-    return ffma2(p, pk(-sc0, -sc1), y);
+    const uint64_t y = ffma2(p, pk(sc, sc), w);
+    return ffma2(p, pk(-sc, -sc), y);
+}
+
+// Per-group constants of the symmetric flow: r = RN(1/s) as a packed fp32 pair, s as a packed fp32 pair
+// (magic path) or as an fp16 pair (hardware path); the hardware path folds the format's PRE factor into both.
+struct SymK {
+    uint64_t r2, s2;
+    uint32_t sh2;
+};
+template <class HG>
+__device__ __forceinline__ SymK make_symk(float s, float r) {
+    SymK k;
+    const float rr = r * HwCvt<HG>::PRE;                                  // power of two: exact
+    k.r2 = pk(rr, rr);
+    k.s2 = pk(s, s);
+    k.sh2 = dup_h(__float2half_rn(s * (1.0f / HwCvt<HG>::PRE)));          // s is an fp16 value <= S_MAX_BITS: exact
+    return k;
 }
 
 // One packed pair of the symmetric flow: two fp16 inputs (already widened to packed fp32) -> two fp16
 // outputs q*s.
 template <class HG>
-__device__ __forceinline__ uint32_t sym_pair_h16_w(uint64_t xf2, uint64_t r2, uint64_t s2, float delta) {
-    const uint32_t v2 = pack_h2_u64(fmul2(xf2, r2));                              // half(x/s)
-    const uint64_t q = round_pair_magic(v2, delta, Magic<HG>::EM, Magic<HG>::EM, Magic<HG>::SC, Magic<HG>::SC);
-    return pack_h2_u64(fmul2(q, s2));                                             // half(q*s)
+__device__ __forceinline__ uint32_t sym_pair_h16_w(uint64_t xf2, const SymK& k, float delta) {
+    const uint32_t v2 = pack_h2_u64(fmul2(xf2, k.r2));                            // half(x/s)
+    const float w0 = fhadd(uint16_t(v2 & 0xffffu), delta);
+    const float w1 = fhadd(uint16_t(v2 >> 16), delta);
+    if constexpr (HwCvt<HG>::OK) {
+        return hfma2(HwCvt<HG>::round_trip(w0, w1), k.sh2, 0u);                   // half(q*s), -0 -> +0
+    } else {
+        const uint64_t q = round_pair_magic(w0, w1, Magic<HG>::EM, Magic<HG>::SC);
+        return pack_h2_u64(fmul2(q, k.s2));                                       // half(q*s)
+    }
 }
 template <class HG>
-__device__ __forceinline__ uint32_t sym_pair_h16(uint32_t x2, uint64_t r2, uint64_t s2, float delta) {
-    const uint32_t v2 = pack_h2_u64(fmul2(widen_h2(x2), r2));                     // half(x/s)
-    const uint64_t q = round_pair_magic(v2, delta, Magic<HG>::EM, Magic<HG>::EM, Magic<HG>::SC, Magic<HG>::SC);
-    return pack_h2_u64(fmul2(q, s2));                                             // half(q*s)
+__device__ __forceinline__ uint32_t sym_pair_h16(uint32_t x2, const SymK& k, float delta) {
+    return sym_pair_h16_w<HG>(widen_h2(x2), k, delta);
 }
 
 // s = half(a / VMAX) for an fp16 absmax a (quant_utils.py:320).  a * RN(1/VMAX) is within 2^-23
@@ -129,14 +205,19 @@ __device__ __forceinline__ float rcp_rn_normal(float s) {
 }
 // "regular" on fp16 bits: 0x0400 <= bits <= 0x7BFF (normal, finite, positive)
 __device__ __forceinline__ bool scale_bits_regular(uint32_t sb) { return sb - 0x0400u < 0x7800u; }
+template <class HG> __device__ __forceinline__ bool scale_bits_regular_for(uint32_t sb) { return sb - 0x0400u <= HwCvt<HG>::S_MAX_BITS - 0x0400u; }
 
-// absmax of NW packed words as an fp16 bit pattern.  Integer max on |bits|: NaN patterns (> 0x7C00)
-// are the largest, so a NaN anywhere propagates exactly like torch's abs().max().
+// absmax of NW packed words as an fp16 bit pattern, one HMNMX2.NAN on |a|, |b| per word.  A NaN anywhere
+// comes out as a NaN pattern (> 0x7C00), exactly like torch's abs().max().
+__device__ __forceinline__ uint32_t hmax2_abs_nan(uint32_t a, uint32_t b) {
+    const __half2 r = __hmax2_nan(__habs2(*reinterpret_cast<const __half2*>(&a)), __habs2(*reinterpret_cast<const __half2*>(&b)));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
 template <int NW>
 __device__ __forceinline__ uint32_t absmax_bits(const uint32_t (&p)[NW]) {
     uint32_t m = 0;
 #pragma unroll
-    for (int i = 0; i < NW; ++i) m = __vmaxu2(m, p[i] & 0x7FFF7FFFu);
+    for (int i = 0; i < NW; ++i) m = hmax2_abs_nan(m, p[i]);
     return max(m & 0xffffu, m >> 16);
 }
 
@@ -153,14 +234,13 @@ __device__ __forceinline__ bool sym_quant_tile_h16(uint32_t (&p)[NW], float& s, 
     const float a = h2f(uint16_t(m));
     const __half sh = scale_from_absmax_h16<HG>(a);
     s = __half2float(sh);
-    if (!scale_bits_regular(__half_as_ushort(sh))) {
+    if (!scale_bits_regular_for<HG>(__half_as_ushort(sh))) {
         s = rnd_in<__half>(__fdiv_rn(a, HG::VMAX));      // the literal path gets the literal scale (exact ties among subnormals)
         return false;
     }
-    const float r = rcp_rn_normal(s);
-    const uint64_t r2 = pk(r, r), s2 = pk(s, s);
+    const SymK k = make_symk<HG>(s, rcp_rn_normal(s));
 #pragma unroll
-    for (int i = 0; i < NW; ++i) p[i] = sym_pair_h16<HG>(p[i], r2, s2, delta);
+    for (int i = 0; i < NW; ++i) p[i] = sym_pair_h16<HG>(p[i], k, delta);
     return true;
 }
 
@@ -214,81 +294,63 @@ static __device__ __noinline__ void literal_split_nan_group_h16(const __half* sr
 }
 
 // ---- sign-split ----------------------------------------------------------------------------
-// One pair: elements > 0 use (rp, sp, POS grid), elements < 0 use (rn, sn, NEG grid); +0 / -0 give +0
-// on either side, so the sign bit alone picks the side.  No NaN can reach this function (groups that
-// hold a NaN take the literal path).
-// How many of the per-element side selects (r, s, magic scale[, sign mask]) run as integer
-// multiply-adds on the FMA pipe instead of LOP3 on the ALU pipe.  Measured on B200 (tools/kbench.py,
-// fc2 shape 25600 x 7680): 0 -> 5.40, 1 -> 5.70, 2 -> 5.92, 3 -> 6.15 TB/s.
-#ifndef FPQ_SPLIT_IMAD
-#define FPQ_SPLIT_IMAD 3
-#endif
-// bit-pattern select between a "positive side" and a "negative side" constant with m = -1 (negative
-// element) or 0.  Two flavours so that the work can be spread over both math pipes of the SM
-// sub-partition (ncu: the ALU pipe, where FSEL/LOP3/FMNMX/F2FP live, is the busy one): an integer
-// multiply-add on the FMA pipe, or a LOP3 on the ALU pipe.
-__device__ __forceinline__ float sel_imad(int m, float pos, float neg) {
-    int d;
-    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(m), "r"(__float_as_int(pos) - __float_as_int(neg)), "r"(__float_as_int(pos)));
-    return __int_as_float(d);
-}
-__device__ __forceinline__ float sel_lop(int m, float pos, float neg) {
-    return __int_as_float(__float_as_int(pos) ^ ((__float_as_int(pos) ^ __float_as_int(neg)) & m));
-}
-
-// Sides with a UNIFORM negative grid (e1m2: step 1/4 up to 1.75; int: step 1 up to 32) share the
-// positive side's rounding constants: the negative side is rescaled by the power of two K that maps
-// its step onto the positive format's subnormal step 2^(EMIN-M) (rn' = rn*K, sn' = sn/K, both exact),
-// and p = 2^exponent(max(w, 2^EMIN)) is taken WITHOUT the absolute value, so every negative w gets the
-// constant p = 2^EMIN -- exactly the uniform grid.  Only r and s are then selected per element.
-template <class NEG, class POS> struct SplitScale {
+// Elements > 0 use (rp, sp, POS grid), elements < 0 use (rn, sn, NEG grid); +0 / -0 give +0 on either side,
+// so the sign bit alone picks the side.  No NaN can reach these functions (groups that hold a NaN take the
+// literal path).  BOTH sides are evaluated for the whole pair with packed instructions and uniform constants,
+// and the sign bits pick the result per half with two LOP3 (ncu r1b had the per-element selects of the first
+// version as the busiest part: 72 % ALU pipe):
+//   positive side   w = half(x * rp) + 2^-17 -> conversion hardware (e2m1 / e2m3), as in the symmetric flow
+//   negative side   a UNIFORM grid (e1m2: step 1/4 up to 1.75; int: step 1 up to 32) is rounded entirely in packed
+//                   fp16 with a magic constant C = 1.5 * 2^10 * step, whose ulp is the step:
+//                       y = fma.rn.f16x2(v, 1 - 2^-11, C);   q = y - C
+//                   The factor 1 - 2^-11 moves v towards zero by less than one fp16 ulp: exact midpoints fall to the
+//                   side the kernel rule sends them to (the larger value, i.e. towards zero for v <= 0) and no other
+//                   fp16 value reaches or crosses a midpoint (midpoints are fp16 numbers).  The FMA rounds once.
+//                   A non-uniform negative grid (afpq: e2m1 on both sides) goes through the conversion hardware too.
+// A lane of the wrong side computes garbage (possibly inf / NaN) that the select discards.
+template <class NEG> struct UniformNeg {
     // NEG uniform <=> all of its values lie in its own subnormal region or first binade with the same step
-    static constexpr bool UNIFORM_NEG = (NEG::M - NEG::EMIN == 2 && NEG::VNUM * 4 == 7 * NEG::VDEN) || (NEG::M == NEG::EMIN);
-    // K = step(POS subnormal) / step(NEG)
-    static constexpr float K = UNIFORM_NEG ? (Magic<POS>::EM / float(1u << POS::M)) / (Magic<NEG>::EM / float(1u << NEG::M)) : 1.0f;
+    static constexpr bool OK = (NEG::M - NEG::EMIN == 2 && NEG::VNUM * 4 == 7 * NEG::VDEN) || (NEG::M == NEG::EMIN);
+    static constexpr float STEP = Magic<NEG>::EM / float(1u << NEG::M);
+    static constexpr float C = 1536.0f * STEP;                 // 1.5 * 2^10 * step
 };
 
-template <class NEG, class POS>
-__device__ __forceinline__ uint32_t split_pair_h16_w(float2 x, float rn, float sn, float rp, float sp, float delta);
-
-template <class NEG, class POS>
-__device__ __forceinline__ uint32_t split_pair_h16(uint32_t x2, float rn, float sn, float rp, float sp, float delta) {
-    return split_pair_h16_w<NEG, POS>(__half22float2(*reinterpret_cast<const __half2*>(&x2)), rn, sn, rp, sp, delta);
+struct SplitK {
+    uint64_t rn2, rp2;          // RN(1/s) of each side as packed fp32 pairs (0 for a side without elements)
+    uint32_t snh2, sph2;        // the two scales as fp16 pairs
+};
+__device__ __forceinline__ SplitK make_splitk(float sn, float rn, float sp, float rp) {
+    SplitK k;
+    k.rn2 = pk(rn, rn);
+    k.rp2 = pk(rp, rp);
+    k.snh2 = dup_h(__float2half_rn(sn));
+    k.sph2 = dup_h(__float2half_rn(sp));
+    return k;
 }
 
 template <class NEG, class POS>
-__device__ __forceinline__ uint32_t split_pair_h16_w(float2 x, float rn, float sn, float rp, float sp, float delta) {
-    // rn, sn arrive pre-scaled by the caller when SplitScale::UNIFORM_NEG (rn*K, sn/K)
-#if FPQ_SPLIT_IMAD >= 4
-    const int m0 = -int(__umulhi(__float_as_uint(x.x), 2u)), m1 = -int(__umulhi(__float_as_uint(x.y), 2u));
-#else
-    const int m0 = __float_as_int(x.x) >> 31, m1 = __float_as_int(x.y) >> 31;      // -1: negative side
-#endif
-#if FPQ_SPLIT_IMAD >= 1
-    const float r0 = sel_imad(m0, rp, rn), r1 = sel_imad(m1, rp, rn);
-#else
-    const float r0 = sel_lop(m0, rp, rn), r1 = sel_lop(m1, rp, rn);
-#endif
-#if FPQ_SPLIT_IMAD >= 2
-    const float s0 = sel_imad(m0, sp, sn), s1 = sel_imad(m1, sp, sn);
-#else
-    const float s0 = sel_lop(m0, sp, sn), s1 = sel_lop(m1, sp, sn);
-#endif
-    const uint32_t v2 = pack_h2_u64(fmul2(pk(x.x, x.y), pk(r0, r1)));
-    uint64_t q;
-    if constexpr (SplitScale<NEG, POS>::UNIFORM_NEG) {
-        const float w0 = fhadd(uint16_t(v2 & 0xffffu), delta);
-        const float w1 = fhadd(uint16_t(v2 >> 16), delta);
-        const float p0 = __uint_as_float(__float_as_uint(fmaxf(w0, Magic<POS>::EM)) & 0x7F800000u);     // signed max
-        const float p1 = __uint_as_float(__float_as_uint(fmaxf(w1, Magic<POS>::EM)) & 0x7F800000u);
-        const uint64_t p = pk(p0, p1), w = pk(w0, w1);
-        const uint64_t y = ffma2(p, pk(Magic<POS>::SC, Magic<POS>::SC), w);
-        q = ffma2(p, pk(-Magic<POS>::SC, -Magic<POS>::SC), y);
+__device__ __forceinline__ uint32_t split_pair_h16_w(uint64_t xf2, uint32_t x2, const SplitK& k, float delta) {
+    static_assert(HwCvt<POS>::OK, "the positive side of every sign-split format is e2m1 or e2m3");
+    const uint32_t vp2 = pack_h2_u64(fmul2(xf2, k.rp2));                           // half(x/sp)
+    const uint32_t vn2 = pack_h2_u64(fmul2(xf2, k.rn2));                           // half(x/sn)
+    const uint32_t qp2 = HwCvt<POS>::round_trip(fhadd(uint16_t(vp2 & 0xffffu), delta), fhadd(uint16_t(vp2 >> 16), delta));
+    uint32_t qn2;
+    if constexpr (UniformNeg<NEG>::OK) {
+        const uint32_t c2 = dup_h(__float2half_rn(UniformNeg<NEG>::C));
+        qn2 = hadd2(hfma2(vn2, 0x3BFF3BFFu, c2), c2 ^ 0x80008000u);                // (v * (1 - 2^-11) + C) - C
     } else {
-        static_assert(Magic<NEG>::EM == Magic<POS>::EM && Magic<NEG>::SC == Magic<POS>::SC, "non-uniform negative grids must share the positive format");
-        q = round_pair_magic(v2, delta, Magic<POS>::EM, Magic<POS>::EM, Magic<POS>::SC, Magic<POS>::SC);
+        static_assert(HwCvt<NEG>::OK, "non-uniform negative grids must be hardware formats");
+        qn2 = HwCvt<NEG>::round_trip(fhadd(uint16_t(vn2 & 0xffffu), delta), fhadd(uint16_t(vn2 >> 16), delta));
     }
-    return pack_h2_u64(fmul2(q, pk(s0, s1)));
+    uint32_t neg;                                                                  // 0xFFFF in every half whose sign bit is set
+    asm("prmt.b32 %0, %1, 0, 0xBB99;" : "=r"(neg) : "r"(x2));
+    const uint32_t q2 = (qp2 & ~neg) | (qn2 & neg);
+    const uint32_t s2 = (k.sph2 & ~neg) | (k.snh2 & neg);
+    return hfma2(q2, s2, 0u);                                                      // half(q*s), -0 -> +0
+}
+template <class NEG, class POS>
+__device__ __forceinline__ uint32_t split_pair_h16(uint32_t x2, const SplitK& k, float delta) {
+    return split_pair_h16_w<NEG, POS>(widen_h2(x2), x2, k, delta);
 }
 
 }  // namespace fpq

@@ -6,17 +6,14 @@
 // so (x @ Q) on an aligned 128-chunk is FWHT_128(x * sigma) / c: 7 butterfly stages instead of a
 // dense C x C GEMM.
 //
-// Register tile: the same 8-lanes-per-128-group / 16-values-per-lane layout as the quant kernels
-// (fpq_common.cuh).  With fp32 input, value v[4j+k] of lane l is element e = 32j + 4l + k of the
-// chunk, so the seven index bits split as k (2 bits, in registers), l (3 bits, across lanes:
-// shfl.xor 1,2,4) and j (2 bits, in registers).  A Sylvester Hadamard transform is the tensor
-// product of a 2-point butterfly over every index bit, in any order (here: 0, 1, 4, 5, 6, 2, 3, in both layouts).
-#include <cstdlib>
-#include "fpq_h16.cuh"
-
-#ifndef FPQ_ROT_V2
-#define FPQ_ROT_V2 1
-#endif
+// Numerics shared by the two activation kernels below (so that a row rotates to the same bits whichever
+// kernel the launcher picks for the tensor's size; test_rotation_bits_do_not_depend_on_the_launch_size):
+//   * the per-column multiplier is m[c] = RN(smooth[c] * fl32(1/sqrt(128))) * sigma[c % 128] (the sign flip is
+//     exact), so every element costs ONE multiply in front of the butterflies and none behind them;
+//   * a Sylvester Hadamard transform is the tensor product of a 2-point butterfly (a + b, a - b) over every
+//     index bit of the chunk position, in any order; the order fixes the fp32 summation tree and is
+//     0, 1, 5, 6, 2, 3, 4 in both kernels.
+#include "fpq_stream.cuh"
 
 namespace fpq {
 
@@ -28,31 +25,76 @@ struct Modulate { const float* scale; const float* shift; size_t rows_per_batch;
 // 1 / fl32(sqrt(128)), rounded to fp32 (0x3DB504F3)
 __device__ __forceinline__ float inv_sqrt128() { return __uint_as_float(0x3DB504F3u); }
 
-// Activation kernel.  Work mapping: every 8-lane set owns ONE column chunk cc (so its 16
-// smooth*sign multipliers are loaded once and live in registers) and walks down the rows
-// k, k+K, k+2K, ... of that chunk column.  Arithmetic is two elements per instruction where the
-// ISA allows (FMUL2/FFMA2/FADD2 packed fp32, sm_100): P[2j] = (v[4j], v[4j+1]), P[2j+1] = (v[4j+2], v[4j+3]).
-// MOD (adaLN modulate fused in): a lane set walks CONTIGUOUS rows (k0*R .. k0*R + R - 1) instead of strided ones, so the
-// (scale+1) and shift values of its column change only when the batch index does and live in registers in between --
-// read from L2 once per (batch, column, row range) instead of once per chunk.
-// Occupancy hint of the adaLN-fused variant (MOD).  Compiled freely it takes 100 registers = 2 CTAs per SM and is latency-bound
-// (ncu r1e: 24 % warps active, long_scoreboard 2.5 per issue).  Measured (tools/kbench.py, 102400 x 1920, same run A/B,
-// profiles/r1_kbench.txt): plain bounds 4314 / 4317 GB/s; declared (256, 1) -- still 2 CTAs, but the compiler spends 114
-// registers and spills nothing -- 4526 / 4530; forced to 3 CTAs (80 registers, 48 B of spills) 3917; 4 CTAs (64 registers,
-// 120 B) 4338.  So MOD is declared (256, 1).  The plain variants keep the plain bounds: the (256, 1) form costs them
-// registers (67 -> 76) for nothing measured.
-#ifndef FPQ_ROT_MOD_CTAS
-#define FPQ_ROT_MOD_CTAS 1
-#endif
-#if FPQ_ROT_MOD_CTAS >= 1
-#define FPQ_ROT_BOUNDS __launch_bounds__(256, MOD ? FPQ_ROT_MOD_CTAS : 0)      // 0 = no occupancy hint
-#else
-#define FPQ_ROT_BOUNDS __launch_bounds__(256)
-#endif
+// multipliers of the four columns col0 .. col0 + 3 (col0 % 4 == 0), chunk positions e0 .. e0 + 3
+__device__ __forceinline__ void load_mult4(const float* __restrict__ smooth, const SignMask& sm, size_t col0, int e0, uint64_t& m01, uint64_t& m23) {
+    float4 s4 = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+    if (smooth != nullptr) s4 = __ldg(reinterpret_cast<const float4*>(smooth + col0));
+    float f[4] = {s4.x, s4.y, s4.z, s4.w};
+    const uint32_t bits = sm.w[e0 >> 5] >> (e0 & 31);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        f[k] = __fmul_rn(f[k], inv_sqrt128());
+        if (!((bits >> k) & 1u)) f[k] = -f[k];
+    }
+    m01 = pk(f[0], f[1]);
+    m23 = pk(f[2], f[3]);
+}
+
+// (scale + 1) and shift of four columns of batch row b
+__device__ __forceinline__ void load_mod4(const Modulate& mod, size_t off, uint64_t& a01, uint64_t& a23, uint64_t& s01, uint64_t& s23) {
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(mod.scale + off));
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(mod.shift + off));
+    const uint64_t one2 = pk(mod.one, mod.one);
+    a01 = fadd2(pk(sc.x, sc.y), one2);               // scale.add(1)
+    a23 = fadd2(pk(sc.z, sc.w), one2);
+    s01 = pk(sh.x, sh.y);
+    s23 = pk(sh.z, sh.w);
+}
+// .mul(scale.add(1)).add_(shift): the product with the SCALAR mul.rn.f32 (never contracted; ptxas fuses
+// mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 -- even through a *1 -- which would skip the rounding of the product
+// that the reference's separate ATen kernels perform)
+__device__ __forceinline__ uint64_t modulate2(uint64_t x, uint64_t a, uint64_t sh) {
+    const F2 xv = unpk(x), av = unpk(a);
+    return fadd2(pk(__fmul_rn(xv.lo, av.lo), __fmul_rn(xv.hi, av.hi)), sh);
+}
+
+// butterfly between packed registers at distance h of P[0..N)
+template <int N>
+__device__ __forceinline__ void reg_stage(uint64_t (&P)[N], int h) {
+    const uint64_t neg1 = pk(-1.0f, -1.0f);
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        if ((i & h) == 0) {
+            const uint64_t a = P[i], b = P[i + h];
+            P[i] = fadd2(a, b);
+            P[i + h] = ffma2(b, neg1, a);
+        }
+    }
+}
+// butterfly inside every packed pair (index bit 0)
+template <int N>
+__device__ __forceinline__ void pair_stage(uint64_t (&P)[N]) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const F2 f = unpk(P[i]);
+        P[i] = pk(f.lo + f.hi, f.lo - f.hi);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Small launches (the first stages of a VAR pass: a few thousand chunks, latency-bound): 8 lanes x 16 values per
+// chunk straight from global memory, every 8-lane set bound to ONE column chunk cc so that its 16 multipliers live in
+// registers, walking down the rows k, k+K, k+2K, ... of that column.  With fp32 input, value v[4j+k] of lane l is
+// element e = 32j + 4l + k of the chunk: index bits 0,1 (k) and 5,6 (j) are in registers, bits 2,3,4 (l) across
+// lanes (shfl.xor 1,2,4).  Arithmetic is two elements per instruction where the ISA allows (FMUL2/FFMA2/FADD2 packed
+// fp32, sm_100): P[2j] = (v[4j], v[4j+1]), P[2j+1] = (v[4j+2], v[4j+3]).
+// MOD (adaLN modulate fused in): a lane set walks CONTIGUOUS rows (k0*R .. k0*R + R - 1) instead of strided ones, so
+// the (scale+1) and shift values of its column change only when the batch index does and live in registers in between.
+// ------------------------------------------------------------------------------------------------------------
 template <int FMT, bool QUANT, bool MOD>
-__global__ void FPQ_ROT_BOUNDS transform_rotate_quant_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
-                                                                     SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
-                                                                     size_t n_rows, int cpr, size_t sets_per_col, Modulate mod) {
+__global__ void __launch_bounds__(256, MOD ? 1 : 0) transform_rotate_quant_small_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
+                                                                                       SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
+                                                                                       size_t n_rows, int cpr, size_t sets_per_col, Modulate mod) {
     constexpr int LPG = 8;
     pdl_launch_dependents();
     const int lane = threadIdx.x & 31;
@@ -62,31 +104,16 @@ __global__ void FPQ_ROT_BOUNDS transform_rotate_quant_kernel(const float* __rest
     const size_t k0 = ls / size_t(cpr);
     const bool active = k0 < sets_per_col;
     const size_t row_stride = size_t(cpr) * 128;
-
-    // multipliers m = smooth * sign for the 16 chunk positions of this lane (sign flips are exact,
-    // so (x*s)*sigma == x*(s*sigma) bit for bit)
-    uint64_t ms[8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        float4 s4 = make_float4(1.0f, 1.0f, 1.0f, 1.0f);
-        if (smooth != nullptr) s4 = __ldg(reinterpret_cast<const float4*>(smooth + size_t(cc) * 128 + (j * LPG + lig) * 4));
-        float f[4] = {s4.x, s4.y, s4.z, s4.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (!((sm.w[j] >> (4 * lig + k)) & 1u)) f[k] = -f[k];
-        ms[2 * j] = pk(f[0], f[1]);
-        ms[2 * j + 1] = pk(f[2], f[3]);
-    }
-    const uint64_t neg1 = pk(-1.0f, -1.0f);
     const float delta = tie_delta_kernel(uint32_t(ls >> 36));
-    const float cinv = inv_sqrt128();
-    const uint64_t cinv2 = pk(cinv, cinv);
-
     // uniform trip count across the warp (the shuffles need every lane)
     const size_t trips = (n_rows + sets_per_col - 1) / sets_per_col;
+    // Nothing is read before pdl_wait(): `smooth` may have been produced (cast, sliced) by the kernel in front of this one.
+    pdl_wait();
+    uint64_t ms[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) load_mult4(smooth, sm, size_t(cc) * 128 + 32 * j + 4 * lig, 32 * j + 4 * lig, ms[2 * j], ms[2 * j + 1]);
     uint64_t A[MOD ? 8 : 1], SH[MOD ? 8 : 1];         // (scale + 1) and shift of this lane's 16 columns for batch cur_b
     size_t cur_b = ~size_t(0);
-    pdl_wait();                                       // smooth / sign mask are parameters; x may come from the previous kernel
     for (size_t t = 0; t < trips; ++t) {
         const size_t row = MOD ? k0 * trips + t : k0 + t * sets_per_col;
         const bool valid = active && row < n_rows;
@@ -108,48 +135,21 @@ __global__ void FPQ_ROT_BOUNDS transform_rotate_quant_kernel(const float* __rest
             if (b != cur_b) {
                 cur_b = b;
                 const size_t mo = b * row_stride + size_t(cc) * 128;
-                const uint64_t one2 = pk(mod.one, mod.one);
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const float4 sc = __ldg(reinterpret_cast<const float4*>(mod.scale + mo + (j * LPG + lig) * 4));
-                    const float4 sh = __ldg(reinterpret_cast<const float4*>(mod.shift + mo + (j * LPG + lig) * 4));
-                    A[2 * j] = fadd2(pk(sc.x, sc.y), one2);               // scale.add(1)
-                    A[2 * j + 1] = fadd2(pk(sc.z, sc.w), one2);
-                    SH[2 * j] = pk(sh.x, sh.y);
-                    SH[2 * j + 1] = pk(sh.z, sh.w);
-                }
+                for (int j = 0; j < 4; ++j) load_mod4(mod, mo + (j * LPG + lig) * 4, A[2 * j], A[2 * j + 1], SH[2 * j], SH[2 * j + 1]);
             }
-            // .mul(scale.add(1)).add_(shift): the product with the SCALAR mul.rn.f32 (never contracted; ptxas fuses
-            // mul.rn.f32x2 + add.rn.f32x2 into one FFMA2, which would skip the rounding of the product)
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const F2 xv = unpk(P[i]), av = unpk(A[i]);
-                P[i] = fadd2(pk(__fmul_rn(xv.lo, av.lo), __fmul_rn(xv.hi, av.hi)), SH[i]);
-            }
+            for (int i = 0; i < 8; ++i) P[i] = modulate2(P[i], A[i], SH[i]);
         }
-        // x * (s * sigma): basic_var.py:263 `.mul(s)` in fp32, then the sign row of Q
+        // x * m: basic_var.py:263 `.mul(s)` in fp32, the sign row of Q and the 1/sqrt(128) of the Hadamard matrix
 #pragma unroll
         for (int i = 0; i < 8; ++i) P[i] = fmul2(P[i], ms[i]);
-        // index bit 0: inside a packed pair
+        pair_stage(P);          // index bit 0
+        reg_stage(P, 1);        // index bit 1
+        reg_stage(P, 2);        // index bit 5
+        reg_stage(P, 4);        // index bit 6
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const F2 f = unpk(P[i]);
-            P[i] = pk(f.lo + f.hi, f.lo - f.hi);
-        }
-        // The butterfly ORDER is part of the numerics (it fixes the fp32 summation tree).  Both layouts use the
-        // same one -- index bits 0, 1, 4, 5, 6, 2, 3 -- so a row rotates to the same bits whichever kernel the
-        // launcher picks for the tensor's size.
-        auto reg_stage = [&](int h) {                 // between packed registers at distance h in P[]
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                if ((i & h) == 0) {
-                    const uint64_t a = P[i], b = P[i + h];
-                    P[i] = fadd2(a, b);
-                    P[i + h] = ffma2(b, neg1, a);
-                }
-            }
-        };
-        auto lane_stage = [&](int o) {                // across the lanes of the set
+        for (int o = 1; o < 8; o <<= 1) {             // index bits 2, 3, 4: across the lanes of the set
             const float sg = (lig & o) ? -1.0f : 1.0f;
             const uint64_t sg2 = pk(sg, sg);
 #pragma unroll
@@ -158,17 +158,11 @@ __global__ void FPQ_ROT_BOUNDS transform_rotate_quant_kernel(const float* __rest
                 const uint64_t q = pk(__shfl_xor_sync(0xffffffffu, f.lo, o), __shfl_xor_sync(0xffffffffu, f.hi, o));
                 P[i] = ffma2(P[i], sg2, q);            // upper lane: partner - mine ; lower lane: mine + partner (exact: * +-1)
             }
-        };
-        reg_stage(1);      // index bit 1
-        lane_stage(4);     // index bit 4
-        reg_stage(2);      // index bit 5
-        reg_stage(4);      // index bit 6
-        lane_stage(1);     // index bit 2
-        lane_stage(2);     // index bit 3
-        // / fl32(sqrt(128)), rounded to fp16: the fp16 GEMM output of the reference
+        }
+        // rounded to fp16: the fp16 GEMM output of the reference
         uint32_t w[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) w[i] = pack_h2_u64(fmul2(P[i], cinv2));
+        for (int i = 0; i < 8; ++i) w[i] = pack_h2_u64(P[i]);
         if (valid && rotated != nullptr) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) stg_stream(rotated + off + (j * LPG + lig) * 4, make_uint2(w[2 * j], w[2 * j + 1]));
@@ -186,132 +180,250 @@ __global__ void FPQ_ROT_BOUNDS transform_rotate_quant_kernel(const float* __rest
     }
 }
 
-// Activation kernel, second layout (default): 4 lanes per chunk, 32 values (16 packed registers) per
-// lane: vector j (0..7) of lane l holds elements 16j + 4l + k, so only index bits 2 and 3 cross lanes
-// (2 SHFL per element instead of 3, and half the per-group scalar work per element).  The
-// smooth*sign multipliers of the whole row live in shared memory (n_cols floats), which frees the
-// registers the first layout spent on them and lets the chunks be walked with a plain grid stride.
-// MOD: the adaLN modulate in front of it is fused as well (basic_var.py:263,266):
-//     t = (x * (scale[b, c] + 1) + shift[b, c]) * smooth[c]        b = row / rows_per_batch
-// as four separately rounded fp32 operations, exactly the reference's `.mul(scale.add(1)).add_(shift).mul(s)`.
+// ------------------------------------------------------------------------------------------------------------
+// Streaming kernel (everything from a few thousand rows on).  One persistent CTA per contiguous range of rows
+// (ranges differ by at most one row: no partial wave at the end), two CTAs per SM.
+//   producer warp     one lane streams tiles of RS whole rows (contiguous bytes) into a ring of ROT_STAGES shared-memory
+//                     stages with 1-D bulk async copies (cp.async.bulk -> UBLKCP, the TMA engine) that complete on
+//                     an mbarrier: the bytes in flight cost shared memory, not registers, and never stall a compute warp
+//                     on global memory.
+//   consumer warps    a warp owns CW chunk columns x 8/CW rows of every tile (CW = 1, 2 or 4, chosen per row length by
+//                     rot_plan), the same columns in every tile, so the multipliers (and, with MOD, the adaLN
+//                     operands of the current batch) live in registers.  The transform runs in two passes over the
+//                     tile in shared memory, so that no butterfly crosses lanes (no SHFL at all):
+//       pass 1   8 lanes x 16 values per chunk: lane l holds the 16-byte units u = 8a + l (a = 0..3) of its chunk,
+//                i.e. index bits 0,1 (inside a unit) and 5,6 (a) -- multiply, butterflies 0,1,5,6, write back IN PLACE;
+//                a warp does this twice per tile (two sub-iterations of 4 chunks, same columns, next rows);
+//       pass 2   4 lanes x 32 values per chunk: lane l' holds the units 8l' + i (i = 0..7), index bits 0..4 --
+//                butterflies 2,3,4, round to fp16, per-group quantizer on the register tile, 128-bit stores of 32
+//                CONTIGUOUS elements per lane.
+//   bank conflicts    a chunk is 512 B = 4 x 128 B bank windows, and an LDS.128 / STS.128 is served 8 lanes at a time.
+//                Pass 1 reads 8 consecutive units per chunk: conflict-free as it is.  Pass 2 reads units 128 B apart
+//                in 4 lanes x 2 chunks per phase; the units are therefore stored XOR-swizzled inside their 128-byte
+//                window by pass 1: unit (a, c) sits at slot c ^ (2a + s), s = parity of the chunk among the warp's 8.
+//                Both the swizzled pass-1 stores and the pass-2 loads then touch 8 distinct 16-byte slots per phase.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int ROT_STAGES = 3;
+constexpr int ROT_MAX_WARPS = 9;                      // consumer warps per CTA
+constexpr int ROT_MAX_THREADS = 32 * (ROT_MAX_WARPS + 1);
 
+struct RotPlan {
+    int cpr;                 // chunks per row
+    int cw;                  // chunk columns per warp: 1, 2 or 4
+    int wcols;               // warps across the columns: ceil(cpr / cw)
+    int n_warps;             // consumer warps = wcols * (row groups)
+    int rs;                  // rows per tile = (n_warps / wcols) * 2 * (4 / cw)
+    unsigned stage_bytes;    // rs * cpr * 512
+};
+
+// Registers: 2 CTAs x 320 threads leave 96 per thread, enough without the adaLN operands.  With them (MOD, 32 more live
+// registers) the kernel is capped at 112 instead: two CTAs of 288 threads (rows of 15 chunks, VAR-d30) still fit, a CTA
+// of 320 threads (rows of 18 chunks, VAR-d36) runs alone on its SM.
 template <int FMT, bool QUANT, bool MOD>
-__global__ void __launch_bounds__(256) transform_rotate_quant_v2_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
-                                                                        SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
-                                                                        size_t n_chunks, int cpr, Modulate mod) {
-    // [cpr][ROW]: smooth[c] * sigma[c % 128]; rows padded by 16 floats so that the two lane sets of a
-    // quarter-warp (adjacent chunk columns) read from different banks
-    extern __shared__ float s_mul[];
-    constexpr int LPG = 4, NV = 8, ROW = 144;
-    // `smooth` and the sign mask are parameters of the model, not products of the previous kernel: the
-    // table is built before pdl_wait(), i.e. while the previous kernel is still draining
-    pdl_launch_dependents();
-    for (int c = threadIdx.x; c < cpr * 128; c += blockDim.x) {
-        const int e = c & 127;
-        const float sv = smooth != nullptr ? __ldg(smooth + c) : 1.0f;
-        s_mul[(c >> 7) * ROW + e] = ((sm.w[e >> 5] >> (e & 31)) & 1u) ? sv : -sv;      // sign flips are exact: (x*s)*sigma == x*(s*sigma)
+__device__ __forceinline__ void rotate_tma_body(const float* __restrict__ x, const float* __restrict__ smooth,
+                                                                                       SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
+                                                                                       size_t n_rows, RotPlan plan, Modulate mod) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + size_t(ROT_STAGES) * plan.stage_bytes);
+    uint64_t* empty = full + ROT_STAGES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int NW = plan.n_warps;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < ROT_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], uint32_t(NW));
+        }
+        mbar_fence_init();
     }
+    pdl_launch_dependents();
     __syncthreads();
-    pdl_wait();
-    // (Measured and rejected, profiles/r1_kbench.txt: requesting the first chunk before the barrier, or the
-    // next chunk before computing this one, costs 32 live registers -- 100 instead of 61, or spills at 64 --
-    // and loses 10-25 % at every size.)
-    const int lane = threadIdx.x & 31;
-    const int lig = lane % LPG;
-    const size_t warp_global = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-    const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
-    const uint64_t neg1 = pk(-1.0f, -1.0f);
-    const float delta = tie_delta_kernel(uint32_t(warp_global >> 33));
-    const float cinv = inv_sqrt128();
-    const uint64_t cinv2 = pk(cinv, cinv);
-    const float sg1 = (lig & 1) ? -1.0f : 1.0f, sg2 = (lig & 2) ? -1.0f : 1.0f;
 
-    for (size_t cbase = warp_global * 8; cbase < n_chunks; cbase += n_warps * 8) {
-        const size_t c = cbase + lane / LPG;
-        const bool valid = c < n_chunks;
-        const size_t off = c * 128;
-        const int ccol = valid ? int(c % size_t(cpr)) : 0;
-        const float* mrow = s_mul + ccol * ROW;
-        size_t moff = 0;
-        if constexpr (MOD) moff = (valid ? (c / size_t(cpr)) / mod.rows_per_batch : 0) * (size_t(cpr) * 128) + size_t(ccol) * 128;
-        uint64_t P[16];
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-            uint4 u = make_uint4(0u, 0u, 0u, 0u);
-            if (valid) u = ldg_stream(x + off + (j * LPG + lig) * 4);
-            const float4 m4 = *reinterpret_cast<const float4*>(mrow + (j * LPG + lig) * 4);
-            uint64_t xa = (uint64_t(u.y) << 32) | u.x, xb = (uint64_t(u.w) << 32) | u.z;
-            if constexpr (MOD) {
-                const size_t mo = moff + (j * LPG + lig) * 4;
-                const float4 sc = __ldg(reinterpret_cast<const float4*>(mod.scale + mo));
-                const float4 sh = __ldg(reinterpret_cast<const float4*>(mod.shift + mo));
-                const uint64_t one2 = pk(mod.one, mod.one);
-                // .mul(scale.add(1)).add_(shift).  The product uses the SCALAR mul.rn.f32 (never contracted):
-                // ptxas fuses mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 -- even through a *1 -- which would skip
-                // the rounding of the product that the reference's separate ATen kernels perform.
-                const F2 a0 = unpk(fadd2(pk(sc.x, sc.y), one2)), a1 = unpk(fadd2(pk(sc.z, sc.w), one2));
-                const F2 x0 = unpk(xa), x1 = unpk(xb);
-                xa = fadd2(pk(__fmul_rn(x0.lo, a0.lo), __fmul_rn(x0.hi, a0.hi)), pk(sh.x, sh.y));
-                xb = fadd2(pk(__fmul_rn(x1.lo, a1.lo), __fmul_rn(x1.hi, a1.hi)), pk(sh.z, sh.w));
+    // this CTA's rows: [r_begin, r_end), sizes differ by at most one row over the grid
+    const size_t per = n_rows / gridDim.x, rem = n_rows % gridDim.x;
+    const size_t r_begin = size_t(blockIdx.x) * per + (blockIdx.x < rem ? blockIdx.x : rem);
+    const size_t r_end = r_begin + per + (blockIdx.x < rem ? 1 : 0);
+    const size_t row_elems = size_t(plan.cpr) * 128;
+    const int RS = plan.rs;
+    // MOD: a tile never straddles two batches (its adaLN operands are per batch); `left` = rows to the end of the batch
+    size_t batch = 0, left = ~size_t(0);
+    if constexpr (MOD) {
+        batch = r_begin / mod.rows_per_batch;
+        left = mod.rows_per_batch - (r_begin - batch * mod.rows_per_batch);
+    }
+    // Nothing is read from global memory before pdl_wait(): x comes from the previous kernel, and `smooth` may too.
+    pdl_wait();
+
+    if (warp == NW) {
+        // ---------------- producer: one lane ----------------
+        if (lane == 0) {
+            uint32_t s = 0, lap = 0;
+            for (size_t r = r_begin; r < r_end;) {
+                size_t nr = r_end - r;
+                if (nr > size_t(RS)) nr = size_t(RS);
+                if (MOD && nr > left) nr = left;
+                if (lap > 0) mbar_wait(&empty[s], (lap - 1) & 1u);             // stage free again
+                const uint32_t bytes = uint32_t(nr * row_elems * sizeof(float));
+                mbar_arrive_expect_tx(&full[s], bytes);
+                bulk_load(smem + size_t(s) * plan.stage_bytes, x + r * row_elems, bytes, &full[s]);
+                r += nr;
+                if constexpr (MOD) { left -= nr; if (left == 0) left = mod.rows_per_batch; }
+                if (++s == ROT_STAGES) { s = 0; ++lap; }
             }
-            // x * (s * sigma): basic_var.py:263 `.mul(s)` in fp32, then the sign row of Q
-            P[2 * j] = fmul2(xa, pk(m4.x, m4.y));
-            P[2 * j + 1] = fmul2(xb, pk(m4.z, m4.w));
         }
-        // index bit 0: inside a packed pair
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const int wc = warp % plan.wcols, wr = warp / plan.wcols;      // column group, row group of this warp
+    const int rps = 4 / plan.cw;                                   // rows per pass-1 sub-iteration
+    // pass 1: 8 lanes per chunk; the warp's 4 chunks of a sub-iteration are cw columns x rps rows
+    const int g4 = lane >> 3, l8 = lane & 7;
+    const int col1 = wc * plan.cw + g4 % plan.cw;
+    const int trow1 = wr * 2 * rps + g4 / plan.cw;                 // + rps in the second sub-iteration
+    const bool colok1 = col1 < plan.cpr;
+    const int s1 = g4 & 1;                                         // parity of the chunk among the warp's 8 (pass-2 lane set index)
+    const uint32_t chunk1 = uint32_t(trow1 * plan.cpr + col1) * 512u;
+    const uint32_t sub_bytes = uint32_t(rps * plan.cpr) * 512u;    // second sub-iteration: rps rows further down
+    // pass 2: 4 lanes per chunk, lane set e = 4*sub + g4
+    const int g8 = lane >> 2, lq = lane & 3;
+    const int col2 = wc * plan.cw + (g8 & 3) % plan.cw;
+    const int trow2 = wr * 2 * rps + (g8 >> 2) * rps + (g8 & 3) / plan.cw;
+    const bool colok2 = col2 < plan.cpr;
+    const uint32_t chunk2 = uint32_t(trow2 * plan.cpr + col2) * 512u;
+    const uint32_t key2 = uint32_t(2 * lq + (g8 & 1));
+    const uint32_t smem_base = smem_u32(smem);
+    const float delta = tie_delta_kernel(uint32_t((r_begin + size_t(lane)) >> 44));       // 0, but not provably uniform (fpq_h16.cuh)
+
+    // multipliers of this lane's 16 columns (pass 1): units u = 8a + l8, elements 32a + 4*l8 + k
+    uint64_t ms[8];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const F2 f = unpk(P[i]);
-            P[i] = pk(f.lo + f.hi, f.lo - f.hi);
-        }
-        // index bits 1, 4, 5, 6: between packed registers (distance 1, 2, 4, 8 in P[])
+    for (int a = 0; a < 4; ++a) {
+        const int e0 = 32 * a + 4 * l8;
+        if (colok1) load_mult4(smooth, sm, size_t(col1) * 128 + e0, e0, ms[2 * a], ms[2 * a + 1]);
+        else ms[2 * a] = ms[2 * a + 1] = 0ull;
+    }
+    uint64_t A[MOD ? 8 : 1], SH[MOD ? 8 : 1];
+    size_t cur_b = ~size_t(0);
+
+    uint32_t s = 0, lap = 0;
+    for (size_t r = r_begin; r < r_end;) {
+        size_t nr_ = r_end - r;
+        if (nr_ > size_t(RS)) nr_ = size_t(RS);
+        if (MOD && nr_ > left) nr_ = left;
+        const int nr = int(nr_);
+        if constexpr (MOD) {
+            if (batch != cur_b) {             // first tile of a batch: this lane's (scale + 1) and shift
+                cur_b = batch;
+                if (colok1) {
 #pragma unroll
-        for (int h = 1; h < 16; h <<= 1) {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                if ((i & h) == 0) {
-                    const uint64_t a = P[i], b = P[i + h];
-                    P[i] = fadd2(a, b);
-                    P[i + h] = ffma2(b, neg1, a);
+                    for (int a = 0; a < 4; ++a)
+                        load_mod4(mod, batch * row_elems + size_t(col1) * 128 + 32 * a + 4 * l8, A[2 * a], A[2 * a + 1], SH[2 * a], SH[2 * a + 1]);
                 }
             }
         }
-        // index bits 2, 3: across the 4 lanes of the set
+        const uint32_t sb = smem_base + s * plan.stage_bytes;
+        mbar_wait(&full[s], lap & 1u);
+        // ---- pass 1 ----
 #pragma unroll
-        for (int o = 1; o < 4; o <<= 1) {
-            const float sg = o == 1 ? sg1 : sg2;
-            const uint64_t sgp = pk(sg, sg);
+        for (int sub = 0; sub < 2; ++sub) {
+            if (colok1 && trow1 + sub * rps < nr) {
+                const uint32_t cb = sb + chunk1 + uint32_t(sub) * sub_bytes;
+                uint64_t P[8];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const F2 f = unpk(P[i]);
-                const uint64_t q = pk(__shfl_xor_sync(0xffffffffu, f.lo, o), __shfl_xor_sync(0xffffffffu, f.hi, o));
-                P[i] = ffma2(P[i], sgp, q);            // upper lane: partner - mine ; lower lane: mine + partner (exact: * +-1)
+                for (int a = 0; a < 4; ++a) {
+                    uint4 u;
+                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(cb + uint32_t(a * 128 + l8 * 16)));
+                    P[2 * a] = (uint64_t(u.y) << 32) | u.x;
+                    P[2 * a + 1] = (uint64_t(u.w) << 32) | u.z;
+                }
+                if constexpr (MOD) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) P[i] = modulate2(P[i], A[i], SH[i]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) P[i] = fmul2(P[i], ms[i]);
+                pair_stage(P);          // index bit 0
+                reg_stage(P, 1);        // index bit 1
+                reg_stage(P, 2);        // index bit 5
+                reg_stage(P, 4);        // index bit 6
+                // in place: the 8 lanes of the chunk have all read their units before any of them overwrites one
+                __syncwarp(0xFFu << (8 * g4));
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    const F2 p0 = unpk(P[2 * a]), p1 = unpk(P[2 * a + 1]);
+                    const uint32_t slot = uint32_t(l8 ^ s1) ^ uint32_t(2 * a);          // unit (a, c = l8) at c ^ (2a + s)
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(cb + uint32_t(a * 128) + slot * 16u), "f"(p0.lo), "f"(p0.hi), "f"(p1.lo), "f"(p1.hi) : "memory");
+                }
             }
         }
-        // / fl32(sqrt(128)), rounded to fp16: the fp16 GEMM output of the reference
+        __syncwarp();
+        // ---- pass 2 ----
+        const bool valid = colok2 && trow2 < nr;
+        uint64_t Q[16];
+        if (valid) {
+            const uint32_t cb = sb + chunk2 + uint32_t(lq) * 128u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                uint4 u;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(cb + ((uint32_t(i) ^ key2) << 4)));
+                Q[2 * i] = (uint64_t(u.y) << 32) | u.x;
+                Q[2 * i + 1] = (uint64_t(u.w) << 32) | u.z;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) Q[i] = 0ull;
+        }
+        // the stage may be refilled (async proxy) once every warp has read its chunks: order this warp's generic-proxy
+        // accesses before the arrive
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
+        reg_stage(Q, 2);                // index bit 2
+        reg_stage(Q, 4);                // index bit 3
+        reg_stage(Q, 8);                // index bit 4
+        // rounded to fp16: the fp16 GEMM output of the reference.  Lane l' holds elements 32*l' .. 32*l' + 31 in order.
         uint32_t w[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) w[i] = pack_h2_u64(fmul2(P[i], cinv2));
+        for (int i = 0; i < 16; ++i) w[i] = pack_h2_u64(Q[i]);
+        const size_t off = (r + size_t(trow2)) * row_elems + size_t(col2) * 128;
         if (valid && rotated != nullptr) {
 #pragma unroll
-            for (int j = 0; j < NV; ++j) stg_stream(rotated + off + (j * LPG + lig) * 4, make_uint2(w[2 * j], w[2 * j + 1]));
+            for (int q = 0; q < 4; ++q) stg_stream(rotated + off + lq * 32 + q * 8, make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));
         }
         bool ok = true;
-        float s = 0.0f;
-        if constexpr (QUANT) ok = sym_quant_tile_h16<FMT, LPG, 16>(w, s, delta);
+        float sc = 0.0f;
+        if constexpr (QUANT) ok = sym_quant_tile_h16<FMT, 4, 16>(w, sc, delta);
         if (valid) {
 #pragma unroll
-            for (int j = 0; j < NV; ++j) stg_stream(out + off + (j * LPG + lig) * 4, make_uint2(w[2 * j], w[2 * j + 1]));
+            for (int q = 0; q < 4; ++q) stg_stream(out + off + lq * 32 + q * 8, make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));
             // irregular scale (zero / subnormal / inf / NaN): `out` now holds this lane's rotated values;
             // quantize them in place with the literal reference sequence
-            if (!ok) literal_sym_h16(out + off, out + off, lig, LPG, 4, NV, s, SymFmt<FMT>::GT);
+            if (!ok) literal_sym_h16(out + off, out + off, lq, 4, 32, 1, sc, SymFmt<FMT>::GT);
         }
+        r += nr_;
+        if constexpr (MOD) { left -= nr_; if (left == 0) { left = mod.rows_per_batch; ++batch; } }
+        if (++s == ROT_STAGES) { s = 0; ++lap; }
     }
 }
 
-// Weight side: one warp per (row, chunk); lane l holds elements 4l..4l+3 in fp64.
-__global__ void __launch_bounds__(256) transform_rotate_weight_kernel(const float* __restrict__ w, const float* __restrict__ smooth,
-                                                                      SignMask sm, float* __restrict__ w_out, size_t n_chunks,
+template <int FMT, bool QUANT>
+__global__ void __launch_bounds__(ROT_MAX_THREADS, 2) transform_rotate_quant_tma_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
+                                                                                       SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
+                                                                                       size_t n_rows, RotPlan plan, Modulate mod) {
+    rotate_tma_body<FMT, QUANT, false>(x, smooth, sm, out, rotated, n_rows, plan, mod);
+}
+template <int FMT, bool QUANT>
+__global__ void __maxnreg__(112) modulate_transform_rotate_quant_tma_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
+                                                                            SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
+                                                                            size_t n_rows, RotPlan plan, Modulate mod) {
+    rotate_tma_body<FMT, QUANT, true>(x, smooth, sm, out, rotated, n_rows, plan, mod);
+}
+
+// Weight side: one warp per (row, chunk); lane l holds elements 4l..4l+3 in fp64.  w_out may alias w (in place): every
+// element is read and written by the same thread, and neither pointer is declared __restrict__.
+__global__ void __launch_bounds__(256) transform_rotate_weight_kernel(const float* w, const float* __restrict__ smooth,
+                                                                      SignMask sm, float* w_out, size_t n_chunks,
                                                                       int chunks_per_row) {
     const int lane = threadIdx.x & 31;
     const size_t warp_global = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
@@ -355,9 +467,87 @@ __global__ void __launch_bounds__(256) transform_rotate_weight_kernel(const floa
 
 using namespace fpq;
 
+// Launch geometry of the streaming kernel for rows of `cpr` chunks; false if the row does not fit its tiles.
+static bool rot_plan(int cpr, RotPlan& best) {
+    bool found = false;
+    double best_util = 0.0;
+    for (int cw = 4; cw >= 1; cw >>= 1) {
+        const int wcols = (cpr + cw - 1) / cw;
+        if (wcols > ROT_MAX_WARPS) continue;
+        int wr = ROT_MAX_WARPS / wcols;                               // row groups: as many warps as fit, at most 8
+        if (wcols * wr > 8 && wr > 1) wr = 8 / wcols > 0 ? 8 / wcols : 1;
+        for (; wr >= 1; --wr) {
+            const int rs = wr * 2 * (4 / cw);
+            const size_t stage = size_t(rs) * cpr * 512;
+            if (stage * ROT_STAGES + 2 * ROT_STAGES * sizeof(uint64_t) > 110 * 1024) continue;      // two CTAs per SM
+            const double util = double(cpr) / double(wcols * cw);
+            if (!found || util > best_util + 1e-9) {
+                best = RotPlan{cpr, cw, wcols, wcols * wr, rs, unsigned(stage)};
+                best_util = util;
+                found = true;
+            }
+            break;
+        }
+    }
+    return found;
+}
+
+template <int FMT, bool QUANT, bool MOD>
+static int launch_tma(const float* x, const float* smooth, const SignMask& sm, __half* o, __half* rot, size_t n_rows, const RotPlan& plan,
+                      const Modulate& m, cudaStream_t st) {
+    void (*kernel)(const float*, const float*, SignMask, __half*, __half*, size_t, RotPlan, Modulate);
+    if constexpr (MOD) kernel = modulate_transform_rotate_quant_tma_kernel<FMT, QUANT>;
+    else kernel = transform_rotate_quant_tma_kernel<FMT, QUANT>;
+    const size_t smem = size_t(ROT_STAGES) * plan.stage_bytes + 2 * ROT_STAGES * sizeof(uint64_t);
+    static bool attr_done[64] = {};                    // per instantiation and device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_done[dev & 63]) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024) != cudaSuccess ||
+            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
+            return FPQ_ERR_CUDA;
+        attr_done[dev & 63] = true;
+    }
+    const size_t tiles = (n_rows + plan.rs - 1) / plan.rs;
+    const size_t cap = size_t(sm_count()) * 2;
+    const unsigned grid = unsigned(tiles < cap ? tiles : cap);
+    launch_pdl(kernel, grid, unsigned(32 * (plan.n_warps + 1)), smem, st, x, smooth, sm, o, rot, n_rows, plan, m);
+    return finish_launch();
+}
+
+template <int FMT, bool QUANT, bool MOD>
+static int launch_small(const float* x, const float* smooth, const SignMask& sm, __half* o, __half* rot, size_t n_rows, int cpr,
+                        const Modulate& m, cudaStream_t st) {
+    // lane sets, one per (chunk column, row phase); enough to fill every SM's thread slots (the modulate variant holds
+    // three operand tables in registers: 2 resident CTAs instead of 4)
+    const size_t max_sets = size_t(sm_count()) * (MOD ? 1024 : 2048) / 8;
+    size_t sets_per_col = max_sets / size_t(cpr);
+    if (sets_per_col < 1) sets_per_col = 1;
+    if (sets_per_col > n_rows) sets_per_col = n_rows;
+    // equal work per set: with `trips` passes over the rows, use just enough sets that every pass is full
+    const size_t trips = (n_rows + sets_per_col - 1) / sets_per_col;
+    sets_per_col = (n_rows + trips - 1) / trips;
+    const size_t n_sets = sets_per_col * size_t(cpr);
+    const unsigned grid = unsigned((n_sets + 31) / 32);            // 32 lane sets per 256-thread block
+    launch_pdl(transform_rotate_quant_small_kernel<FMT, QUANT, MOD>, grid, 256, 0, st, x, smooth, sm, o, rot, n_rows, cpr, sets_per_col, m);
+    return finish_launch();
+}
+
+template <int FMT, bool QUANT>
+static int launch_fmt(const float* x, const Modulate* mod, const float* smooth, const SignMask& sm, __half* o, __half* rot, size_t n_rows, int cpr,
+                      cudaStream_t st) {
+    const Modulate m = mod ? *mod : Modulate{nullptr, nullptr, 1, 1.0f};
+    RotPlan plan;
+    const bool big = n_rows * size_t(cpr) > size_t(g_tun.rot_small_max_chunks) && rot_plan(cpr, plan) &&
+                     (mod == nullptr || mod->rows_per_batch >= size_t(plan.rs)) &&
+                     ((reinterpret_cast<uintptr_t>(o) | reinterpret_cast<uintptr_t>(rot)) & 15) == 0;      // 128-bit stores
+    if (big) return mod ? launch_tma<FMT, QUANT, true>(x, smooth, sm, o, rot, n_rows, plan, m, st) : launch_tma<FMT, QUANT, false>(x, smooth, sm, o, rot, n_rows, plan, m, st);
+    return mod ? launch_small<FMT, QUANT, true>(x, smooth, sm, o, rot, n_rows, cpr, m, st) : launch_small<FMT, QUANT, false>(x, smooth, sm, o, rot, n_rows, cpr, m, st);
+}
+
 static int launch_rotate_quant(const float* x, const Modulate* mod, const float* smooth, const uint32_t* sign_bits_host, void* out, void* rotated,
                                size_t n_rows, size_t n_cols, int format, void* stream) {
-    if (n_cols == 0 || n_cols % 128 != 0 || !sign_bits_host || (n_rows && (!x || !out))) return FPQ_ERR_ARG;
+    if (n_cols == 0 || n_cols % 128 != 0 || n_cols / 128 > 0x7fffffff / 512 || !sign_bits_host || (n_rows && (!x || !out))) return FPQ_ERR_ARG;
     if (format < -1 || format >= FPQ_NUM_SYM_FORMATS) return FPQ_ERR_ARG;
     if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(smooth)) & 15) || (reinterpret_cast<uintptr_t>(out) & 7) ||
         (reinterpret_cast<uintptr_t>(rotated) & 7))
@@ -373,60 +563,25 @@ static int launch_rotate_quant(const float* x, const Modulate* mod, const float*
     const int cpr = int(n_cols / 128);
     __half* o = static_cast<__half*>(out);
     __half* rot = static_cast<__half*>(rotated);
-#if FPQ_ROT_V2
-    // Small launches (the first four stages of a VAR pass) are latency-bound: the first layout has no
-    // shared-memory table to build and twice as many lane sets per chunk, and is 5-35 % faster there
-    // (profiles/r1_stagebench.txt); from ~25 k chunks on the second layout wins (fewer instructions).
-    const bool small = n_rows * size_t(cpr) <= 24576;
-    // FPQ_ROT_MOD_V2=1 keeps the second layout for the modulate variant too (it re-reads scale/shift per chunk through L1:
-    // 3.6 TB/s-equivalent against the register-table variant of the first layout, see profiles/r1_kbench.txt)
-    static const bool mod_v2 = getenv("FPQ_ROT_MOD_V2") != nullptr;
-    if (!small && (mod == nullptr || mod_v2) && size_t(cpr) * 144 * sizeof(float) <= 48 * 1024) {
-        const size_t n_chunks = n_rows * size_t(cpr);
-        const unsigned grid = grid_for(n_chunks, 64, 4);              // 8 warps x 8 chunks per block and trip
-        const size_t smem = size_t(cpr) * 144 * sizeof(float);
-        const Modulate m = mod ? *mod : Modulate{nullptr, nullptr, 1, 1.0f};
-#define FPQ_TRQ2(F, Q)                                                                                                                     \
-    if (mod) launch_pdl(transform_rotate_quant_v2_kernel<F, Q, true>, grid, 256, smem, st, x, smooth, sm, o, rot, n_chunks, cpr, m);       \
-    else launch_pdl(transform_rotate_quant_v2_kernel<F, Q, false>, grid, 256, smem, st, x, smooth, sm, o, rot, n_chunks, cpr, m)
-        switch (format) {
-            case -1: FPQ_TRQ2(0, false); break;
-            case FPQ_FMT_E2M1: FPQ_TRQ2(FPQ_FMT_E2M1, true); break;
-            case FPQ_FMT_E1M2: FPQ_TRQ2(FPQ_FMT_E1M2, true); break;
-            case FPQ_FMT_E3M0: FPQ_TRQ2(FPQ_FMT_E3M0, true); break;
-            case FPQ_FMT_E2M3: FPQ_TRQ2(FPQ_FMT_E2M3, true); break;
-            default: FPQ_TRQ2(FPQ_FMT_E3M2, true); break;
-        }
-#undef FPQ_TRQ2
-        return finish_launch();
-    }
-#endif
-    // first layout: lane sets, one per (chunk column, row phase); enough to fill every SM's thread slots (the
-    // modulate variant holds three operand tables in registers: 2 resident CTAs instead of 4)
-    const size_t max_sets = size_t(sm_count()) * (mod ? 1024 : 2048) / 8;
-    size_t sets_per_col = max_sets / size_t(cpr);
-    if (sets_per_col < 1) sets_per_col = 1;
-    if (sets_per_col > n_rows) sets_per_col = n_rows;
-    // equal work per set: with `trips` passes over the rows, use just enough sets that every pass is full
-    // (25600 rows on 2525 sets would run 10 full passes and one at 10 %)
-    const size_t trips = (n_rows + sets_per_col - 1) / sets_per_col;
-    sets_per_col = (n_rows + trips - 1) / trips;
-    const size_t n_sets = sets_per_col * size_t(cpr);
-    const unsigned grid = unsigned((n_sets + 31) / 32);            // 32 lane sets per 256-thread block
-    const Modulate m1 = mod ? *mod : Modulate{nullptr, nullptr, 1, 1.0f};
-#define FPQ_TRQ(F, Q)                                                                                                                     \
-    if (mod) launch_pdl(transform_rotate_quant_kernel<F, Q, true>, grid, 256, 0, st, x, smooth, sm, o, rot, n_rows, cpr, sets_per_col, m1); \
-    else launch_pdl(transform_rotate_quant_kernel<F, Q, false>, grid, 256, 0, st, x, smooth, sm, o, rot, n_rows, cpr, sets_per_col, m1)
     switch (format) {
-        case -1: FPQ_TRQ(0, false); break;
-        case FPQ_FMT_E2M1: FPQ_TRQ(FPQ_FMT_E2M1, true); break;
-        case FPQ_FMT_E1M2: FPQ_TRQ(FPQ_FMT_E1M2, true); break;
-        case FPQ_FMT_E3M0: FPQ_TRQ(FPQ_FMT_E3M0, true); break;
-        case FPQ_FMT_E2M3: FPQ_TRQ(FPQ_FMT_E2M3, true); break;
-        default: FPQ_TRQ(FPQ_FMT_E3M2, true); break;
+        case -1: return launch_fmt<0, false>(x, mod, smooth, sm, o, rot, n_rows, cpr, st);
+        case FPQ_FMT_E2M1: return launch_fmt<FPQ_FMT_E2M1, true>(x, mod, smooth, sm, o, rot, n_rows, cpr, st);
+        case FPQ_FMT_E1M2: return launch_fmt<FPQ_FMT_E1M2, true>(x, mod, smooth, sm, o, rot, n_rows, cpr, st);
+        case FPQ_FMT_E3M0: return launch_fmt<FPQ_FMT_E3M0, true>(x, mod, smooth, sm, o, rot, n_rows, cpr, st);
+        case FPQ_FMT_E2M3: return launch_fmt<FPQ_FMT_E2M3, true>(x, mod, smooth, sm, o, rot, n_rows, cpr, st);
+        default: return launch_fmt<FPQ_FMT_E3M2, true>(x, mod, smooth, sm, o, rot, n_rows, cpr, st);
     }
-#undef FPQ_TRQ
-    return finish_launch();
+}
+
+// Introspection for tests/rotate_layout_model.py (the host-side model of the streaming kernel's shared-memory
+// choreography must plan exactly like the launcher): plan[6] = {cw, wcols, n_warps, rs, stage_bytes, stages}.
+extern "C" int fpq_rotate_plan(int chunks_per_row, int* plan_host) {
+    RotPlan p;
+    if (plan_host == nullptr || chunks_per_row < 1) return FPQ_ERR_ARG;
+    if (!rot_plan(chunks_per_row, p)) return FPQ_ERR_UNSUPPORTED;
+    plan_host[0] = p.cw; plan_host[1] = p.wcols; plan_host[2] = p.n_warps; plan_host[3] = p.rs; plan_host[4] = int(p.stage_bytes);
+    plan_host[5] = ROT_STAGES;
+    return FPQ_OK;
 }
 
 extern "C" int fpq_transform_rotate_quant(const float* x, const float* smooth, const uint32_t* sign_bits_host, void* out, void* rotated,

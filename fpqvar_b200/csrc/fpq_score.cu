@@ -151,71 +151,84 @@ __global__ void __launch_bounds__(256) score_formats_kernel(const InT* __restric
 
 // ------------------------------------------------------------------------------------------
 // Packed variant for fp16 tensors under the kernel tie rule (the proj / fc2 calibration activations):
-// the element functions of fpq_h16.cuh, ~9 instructions per element and candidate instead of ~20.
+// the element functions of fpq_h16.cuh (conversion hardware for e2m1 / e1m2 / e2m3 / e3m2), ~5 instructions per
+// element and candidate, and an error term that never leaves fp16 / mixed precision:
+//     d   = x - o          fp16x2 subtraction, EXACT: o is the grid value next to x, so o/2 <= x <= 2o (or o = 0)
+//     acc = d*d + acc      FHFMA (fp16 * fp16 + fp32 -> fp32), one per element
 // 4 lanes x 32 halves per group, like the quantizer kernels.
 // ------------------------------------------------------------------------------------------
-// acc2 += (x - o)^2 for a packed pair; x is kept widened (packed fp32) for the whole group
-__device__ __forceinline__ uint64_t sq_err_pair(uint64_t xf2, uint32_t o2, uint64_t acc2) {
-    const uint64_t d2 = ffma2(widen_h2(o2), pk(-1.0f, -1.0f), xf2);      // exact: neighbouring fp16 values
-    return ffma2(d2, d2, acc2);
+__device__ __forceinline__ uint32_t hsub2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
 }
-__device__ __forceinline__ float fold2(uint64_t acc2) { const F2 f = unpk(acc2); return f.lo + f.hi; }
+__device__ __forceinline__ float fhfma(uint16_t a, uint16_t b, float c) {        // fp32 = fp16 * fp16 + fp32
+    float d;
+    asm("fma.rn.f32.f16 %0, %1, %2, %3;" : "=f"(d) : "h"(a), "h"(b), "f"(c));
+    return d;
+}
+// (acc0, acc1) += (x - o)^2 of the two halves
+__device__ __forceinline__ void sq_err_pair(uint32_t x2, uint32_t o2, float& acc0, float& acc1) {
+    const uint32_t d2 = hsub2(x2, o2);
+    acc0 = fhfma(uint16_t(d2 & 0xffffu), uint16_t(d2 & 0xffffu), acc0);
+    acc1 = fhfma(uint16_t(d2 >> 16), uint16_t(d2 >> 16), acc1);
+}
 
 template <int FMT>
-__device__ __forceinline__ float sse_sym_h16(const uint64_t (&xf)[16], uint32_t absmax_b, float delta) {
+__device__ __forceinline__ float sse_sym_h16(const uint32_t (&p)[16], const uint64_t (&xf)[16], uint32_t absmax_b, float delta) {
     using HG = typename SymFmt<FMT>::HG;
     const float a = h2f(uint16_t(absmax_b));
     const __half sh = scale_from_absmax_h16<HG>(a);
-    uint64_t acc = 0ull;
-    if (scale_bits_regular(__half_as_ushort(sh))) {
-        const float s = __half2float(sh), r = rcp_rn_normal(s);
-        const uint64_t r2 = pk(r, r), s2 = pk(s, s);
+    float acc0 = 0.0f, acc1 = 0.0f;
+    if (scale_bits_regular_for<HG>(__half_as_ushort(sh))) {
+        const float s = __half2float(sh);
+        const SymK k = make_symk<HG>(s, rcp_rn_normal(s));
 #pragma unroll
-        for (int i = 0; i < 16; ++i) acc = sq_err_pair(xf[i], sym_pair_h16_w<HG>(xf[i], r2, s2, delta), acc);
+        for (int i = 0; i < 16; ++i) sq_err_pair(p[i], sym_pair_h16_w<HG>(xf[i], k, delta), acc0, acc1);
     } else {
         const float s = rnd_in<__half>(__fdiv_rn(a, HG::VMAX));
         const GridTable& gt = c_grids[SymFmt<FMT>::GT];
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 16; ++i) {
             const F2 f = unpk(xf[i]);
-            acc = sq_err_pair(xf[i], pack_h2(quant_elem_literal<__half, TIE_KERNEL>(f.lo, s, gt) * s, quant_elem_literal<__half, TIE_KERNEL>(f.hi, s, gt) * s), acc);
+            const float d0 = f.lo - rnd_in<__half>(quant_elem_literal<__half, TIE_KERNEL>(f.lo, s, gt) * s);
+            const float d1 = f.hi - rnd_in<__half>(quant_elem_literal<__half, TIE_KERNEL>(f.hi, s, gt) * s);
+            acc0 = fmaf(d0, d0, acc0);
+            acc1 = fmaf(d1, d1, acc1);
         }
     }
-    return fold2(acc);
+    return acc0 + acc1;
 }
 
 template <int SPLIT>
-__device__ __forceinline__ float sse_split_h16(const uint64_t (&xf)[16], uint32_t pbits, uint32_t nbits, float delta) {
+__device__ __forceinline__ float sse_split_h16(const uint32_t (&p)[16], const uint64_t (&xf)[16], uint32_t pbits, uint32_t nbits, float delta) {
     using SF = SplitFmtS<SPLIT>;
     const float an = h2f(uint16_t(nbits)), ap = h2f(uint16_t(pbits));
     const __half snh = scale_from_absmax_h16<typename SF::NEG>(an), sph = scale_from_absmax_h16<typename SF::POS>(ap);
     const bool fast = (scale_bits_regular(__half_as_ushort(snh)) || nbits == 0u) && (scale_bits_regular(__half_as_ushort(sph)) || pbits == 0u);
-    uint64_t acc = 0ull;
+    float acc0 = 0.0f, acc1 = 0.0f;
     if (fast) {
-        constexpr float K = SplitScale<typename SF::NEG, typename SF::POS>::K;
         const float sn = __half2float(snh), sp = __half2float(sph);
-        const float rn = nbits == 0u ? 0.0f : rcp_rn_normal(sn) * K, rp = pbits == 0u ? 0.0f : rcp_rn_normal(sp);
-        const float snk = sn * (1.0f / K);
+        const SplitK k = make_splitk(sn, nbits == 0u ? 0.0f : rcp_rn_normal(sn), sp, pbits == 0u ? 0.0f : rcp_rn_normal(sp));
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            const F2 f = unpk(xf[i]);
-            acc = sq_err_pair(xf[i], split_pair_h16_w<typename SF::NEG, typename SF::POS>(make_float2(f.lo, f.hi), rn, snk, rp, sp, delta), acc);
-        }
+        for (int i = 0; i < 16; ++i) sq_err_pair(p[i], split_pair_h16_w<typename SF::NEG, typename SF::POS>(xf[i], p[i], k, delta), acc0, acc1);
     } else {
         const float sn = rnd_in<__half>(__fdiv_rn(an, SF::NEG::VMAX)), sp = rnd_in<__half>(__fdiv_rn(ap, SF::POS::VMAX));
         auto lit = [&](float xv) {
             const float xn = (xv <= 0.0f) ? xv : 0.0f, xp = (xv > 0.0f) ? xv : 0.0f;
             const float qn = scan_kernel_rule(rnd_in<__half>(__fdiv_rn(xn, sn)), c_grids[SF::GT_N].v, c_grids[SF::GT_N].k);
             const float qp = scan_kernel_rule(rnd_in<__half>(__fdiv_rn(xp, sp)), c_grids[SF::GT_P].v, c_grids[SF::GT_P].k);
-            return __fadd_rn(__fmul_rn(qn, sn), __fmul_rn(qp, sp));
+            return rnd_in<__half>(__fadd_rn(__fmul_rn(qn, sn), __fmul_rn(qp, sp)));
         };
-#pragma unroll
+#pragma unroll 1
         for (int i = 0; i < 16; ++i) {
             const F2 f = unpk(xf[i]);
-            acc = sq_err_pair(xf[i], pack_h2(lit(f.lo), lit(f.hi)), acc);
+            const float d0 = f.lo - lit(f.lo), d1 = f.hi - lit(f.hi);
+            acc0 = fmaf(d0, d0, acc0);
+            acc1 = fmaf(d1, d1, acc1);
         }
     }
-    return fold2(acc);
+    return acc0 + acc1;
 }
 
 __global__ void __launch_bounds__(256) score_formats_h16_kernel(const __half* __restrict__ x, size_t n_groups, Candidates cand, double* __restrict__ sse) {
@@ -269,14 +282,14 @@ __global__ void __launch_bounds__(256) score_formats_h16_kernel(const __half* __
         for (int c = 0; c < cand.n; ++c) {
             float e;
             switch (cand.fmt[c]) {
-                case FPQ_FMT_E2M1: e = sse_sym_h16<FPQ_FMT_E2M1>(xf, amax, delta); break;
-                case FPQ_FMT_E1M2: e = sse_sym_h16<FPQ_FMT_E1M2>(xf, amax, delta); break;
-                case FPQ_FMT_E3M0: e = sse_sym_h16<FPQ_FMT_E3M0>(xf, amax, delta); break;
-                case FPQ_FMT_E2M3: e = sse_sym_h16<FPQ_FMT_E2M3>(xf, amax, delta); break;
-                case FPQ_FMT_E3M2: e = sse_sym_h16<FPQ_FMT_E3M2>(xf, amax, delta); break;
-                case 16 + FPQ_SPLIT_E1M2NEG_E2M1POS: e = sse_split_h16<FPQ_SPLIT_E1M2NEG_E2M1POS>(xf, pbits, nbits, delta); break;
-                case 16 + FPQ_SPLIT_INTNEG_E2M3POS: e = sse_split_h16<FPQ_SPLIT_INTNEG_E2M3POS>(xf, pbits, nbits, delta); break;
-                default: e = sse_split_h16<FPQ_SPLIT_AFPQ_E2M1>(xf, pbits, nbits, delta); break;
+                case FPQ_FMT_E2M1: e = sse_sym_h16<FPQ_FMT_E2M1>(p, xf, amax, delta); break;
+                case FPQ_FMT_E1M2: e = sse_sym_h16<FPQ_FMT_E1M2>(p, xf, amax, delta); break;
+                case FPQ_FMT_E3M0: e = sse_sym_h16<FPQ_FMT_E3M0>(p, xf, amax, delta); break;
+                case FPQ_FMT_E2M3: e = sse_sym_h16<FPQ_FMT_E2M3>(p, xf, amax, delta); break;
+                case FPQ_FMT_E3M2: e = sse_sym_h16<FPQ_FMT_E3M2>(p, xf, amax, delta); break;
+                case 16 + FPQ_SPLIT_E1M2NEG_E2M1POS: e = sse_split_h16<FPQ_SPLIT_E1M2NEG_E2M1POS>(p, xf, pbits, nbits, delta); break;
+                case 16 + FPQ_SPLIT_INTNEG_E2M3POS: e = sse_split_h16<FPQ_SPLIT_INTNEG_E2M3POS>(p, xf, pbits, nbits, delta); break;
+                default: e = sse_split_h16<FPQ_SPLIT_AFPQ_E2M1>(p, xf, pbits, nbits, delta); break;
             }
             // 32 lanes x 32 elements in fp32, then one fp64 add per warp, trip and candidate
 #pragma unroll

@@ -149,25 +149,8 @@ __global__ void __launch_bounds__(256) signsplit_row_kernel(const InT* __restric
 // fp6_quant_int_neg_e2m3_pos_per_token_cuda qu.py:614-646): one CTA per row, V 16-byte vectors per
 // thread, one HBM pass, the next row's loads in flight during the block reduction.
 // ------------------------------------------------------------------------------------------
-// FPQ_ROW_BCAST=1: row scalars derived once per row by warp 0 (measured: rows of 7680 / 9216 fp16 4.59 / 4.34 -> 5.25 / 5.01 TB/s,
-// rows of 1920 unchanged); 0 keeps the every-thread form.
-#ifndef FPQ_ROW_BCAST
-#define FPQ_ROW_BCAST 1
-#endif
-__device__ __forceinline__ void block_max2(float& a, float& b, float (&red)[104]) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, o));
-        b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, o));
-    }
-    const int w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-    __syncthreads();
-    if ((threadIdx.x & 31) == 0) { red[w] = a; red[32 + w] = b; }
-    __syncthreads();
-    a = red[0]; b = red[32];
-    for (int i = 1; i < nw; ++i) { a = fmaxf(a, red[i]); b = fmaxf(b, red[32 + i]); }
-}
-
+// Row scalars are derived once per row by warp 0 and broadcast (measured against the every-thread form: rows of 7680 / 9216
+// fp16 4.59 / 4.34 -> 5.25 / 5.01 TB/s, rows of 1920 unchanged).
 template <typename InT, typename OutT, int SPLIT, int TIE, int V>
 __global__ void __launch_bounds__(1024) signsplit_row_reg_kernel(const InT* __restrict__ x, OutT* __restrict__ out, size_t n_rows,
                                                                  int row_vecs, unsigned* __restrict__ nan_flag) {
@@ -236,7 +219,6 @@ __global__ void __launch_bounds__(1024) signsplit_row_reg_kernel(const InT* __re
             float_maxima();
         }
         if (nan_flag != nullptr && has_nan) atomicOr(nan_flag, 1u);
-#if FPQ_ROW_BCAST
         // Row scalars once per row: warp partials -> shared, warp 0 finishes the reduction and derives the scales, everybody
         // reads five floats back (instead of every thread redoing the reduction, two IEEE divisions and two reciprocals).
 #pragma unroll
@@ -270,17 +252,7 @@ __global__ void __launch_bounds__(1024) signsplit_row_reg_kernel(const InT* __re
         __syncthreads();
         const float sn = red[96], sp = red[97], rn = red[98], rp = red[99];
         const bool fast = red[100] != 0.0f;
-#else
-        block_max2(an, ap, red);
-        const bool row_nan = __syncthreads_or(has_nan ? 1 : 0) != 0;
-        const float sn = rnd_in<InT>(__fdiv_rn(an, SF::NEG::VMAX));
-        const float sp = rnd_in<InT>(__fdiv_rn(ap, SF::POS::VMAX));
-        const bool fast = split_fast_ok<InT, TIE>(sn, sp) && !row_nan;      // rows holding a NaN take the literal sequence
-        const float rn = (fast && sn != 0.0f) ? __frcp_rn(sn) : 0.0f;
-        const float rp = (fast && sp != 0.0f) ? __frcp_rn(sp) : 0.0f;
-#endif
-        constexpr float K = SplitScale<typename SF::NEG, typename SF::POS>::K;
-        const float rnk = rn * K, snk = sn * (1.0f / K);
+        const SplitK sk = make_splitk(sn, rn, sp, rp);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
             const int vi = tid + k * nt;
@@ -291,10 +263,10 @@ __global__ void __launch_bounds__(1024) signsplit_row_reg_kernel(const InT* __re
                 // registers are not addressable), so the loop the hardware fetches stays small
                 uint4 o;
                 if (fast) {
-                    o.x = split_pair_h16<typename SF::NEG, typename SF::POS>(w[0], rnk, snk, rp, sp, delta);
-                    o.y = split_pair_h16<typename SF::NEG, typename SF::POS>(w[1], rnk, snk, rp, sp, delta);
-                    o.z = split_pair_h16<typename SF::NEG, typename SF::POS>(w[2], rnk, snk, rp, sp, delta);
-                    o.w = split_pair_h16<typename SF::NEG, typename SF::POS>(w[3], rnk, snk, rp, sp, delta);
+                    o.x = split_pair_h16<typename SF::NEG, typename SF::POS>(w[0], sk, delta);
+                    o.y = split_pair_h16<typename SF::NEG, typename SF::POS>(w[1], sk, delta);
+                    o.z = split_pair_h16<typename SF::NEG, typename SF::POS>(w[2], sk, delta);
+                    o.w = split_pair_h16<typename SF::NEG, typename SF::POS>(w[3], sk, delta);
                 } else {
                     o = signsplit_vec_literal_h16<SPLIT>(u[k], sn, sp);
                 }

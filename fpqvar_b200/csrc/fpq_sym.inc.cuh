@@ -97,11 +97,8 @@ __global__ void __launch_bounds__(256) fake_quant_row_kernel(const InT* __restri
 // per_channel shapes of the FP6 README configs (rows of 1920 .. 9216) when the row is 16-byte
 // aligned and fits V <= 4 vectors x 1024 threads.
 // ------------------------------------------------------------------------------------------
-// FPQ_ROW_BCAST_SYM=1: row scalars derived once per row by warp 0 (measured, rows of 2304 / 7680 / 9216 fp16:
-// 4.77 / 5.00 / 4.80 -> 5.66 / 5.59 / 5.32 TB/s); 0 keeps the every-thread form.
-#ifndef FPQ_ROW_BCAST_SYM
-#define FPQ_ROW_BCAST_SYM 1
-#endif
+// Row scalars are derived once per row by warp 0 and broadcast (measured against the every-thread form, rows of 2304 /
+// 7680 / 9216 fp16: 4.77 / 5.00 / 4.80 -> 5.66 / 5.59 / 5.32 TB/s).
 template <typename InT, typename OutT, int FMT, int TIE, int V>
 __global__ void __launch_bounds__(1024) fake_quant_row_reg_kernel(const InT* __restrict__ x, OutT* __restrict__ out, size_t n_rows,
                                                                   int row_vecs, int clamp3) {
@@ -143,7 +140,6 @@ __global__ void __launch_bounds__(1024) fake_quant_row_reg_kernel(const InT* __r
                 }
             }
         }
-#if FPQ_ROW_BCAST_SYM
         // row scalars once per row (see signsplit_row_reg_kernel)
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a = fmax_nan(a, __shfl_xor_sync(0xffffffffu, a, o));
@@ -164,12 +160,6 @@ __global__ void __launch_bounds__(1024) fake_quant_row_reg_kernel(const InT* __r
         __syncthreads();
         const float s = red[32], r = red[33];
         const bool regular = red[34] != 0.0f;
-#else
-        a = block_max_nan(a, red);
-        const float s = rnd_in<InT>(__fdiv_rn(a, HG::VMAX));                     // quant_utils.py:505 / :239
-        const bool regular = scale_regular<InT>(s);
-        const float r = regular ? __frcp_rn(s) : 0.0f;
-#endif
         const GridTable& gt = c_grids[SymFmt<FMT>::GT];
 #pragma unroll
         for (int k = 0; k < V; ++k) {
@@ -178,10 +168,10 @@ __global__ void __launch_bounds__(1024) fake_quant_row_reg_kernel(const InT* __r
             const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
             if constexpr (sizeof(InT) == 2 && sizeof(OutT) == 2 && TIE == TIE_KERNEL) {
                 uint32_t o[4];
-                if (regular && !clamp3) {
-                    const uint64_t r2 = pk(r, r), s2 = pk(s, s);
+                if (regular && !clamp3 && scale_bits_regular_for<HG>(f2h(s))) {      // s is an fp16 value here
+                    const SymK sk = make_symk<HG>(s, r);
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) o[q] = sym_pair_h16<HG>(w[q], r2, s2, delta);
+                    for (int q = 0; q < 4; ++q) o[q] = sym_pair_h16<HG>(w[q], sk, delta);
                 } else {
 #pragma unroll
                     for (int q = 0; q < 4; ++q) {
@@ -260,7 +250,7 @@ static int launch_sym(const void* x, void* out, size_t n_rows, size_t row_len, i
                             ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
     if constexpr (sizeof(InT) == 2 && sizeof(OutT) == 2 && TIE == TIE_KERNEL) {
         if (pow2_group && row_len == 128 && !clamp3) return launch_sym_h16(FMT, x, out, n_rows, st);
-        if (pow2_group && row_len == 64 && !clamp3 && getenv("FPQ_NO_G64") == nullptr) return launch_sym_h16_g64(FMT, x, out, n_rows, st);
+        if (pow2_group && row_len == 64 && !clamp3) return launch_sym_h16_g64(FMT, x, out, n_rows, st);
     }
     if (pow2_group) {
         const int lpg = int(row_len / 16);

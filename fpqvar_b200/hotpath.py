@@ -36,20 +36,38 @@ def seed42_sign_bits():
 
 class DeviceReplay:
     """Launches :class:`Call` s on device pointers.  ``smooth``: dict site -> fp32 CUDA tensor [C]
-    (the GALT factor of that site) or None."""
+    (the GALT factor of that site) or None.  ``modulate``: dict site -> (gain, shift), two fp32 CUDA tensors
+    [max batches, C] holding ``scale + 1`` and ``shift`` of the adaLN modulate (basic_var.py:258: what ada_lin produced
+    for this block), read by "mod_rotate_quant" calls.  One instance serves one device; launches may go to any of its
+    streams (the sign-split workspace is kept per stream)."""
 
-    def __init__(self, device: torch.device, smooth: Optional[dict] = None, sign_bits=None, global_clip: bool = True):
+    def __init__(self, device: torch.device, smooth: Optional[dict] = None, sign_bits=None, global_clip: bool = True,
+                 modulate: Optional[dict] = None):
         if device.type != "cuda":
             raise L.FpqError("DeviceReplay needs a CUDA device (fpqvar_b200 has no CPU fallback)")
         self.device = device
         self.lib = L.lib()
         self.smooth = smooth or {}
+        self.modulate = modulate or {}
         self.sign_bits = sign_bits if sign_bits is not None else seed42_sign_bits()
         self.global_clip = global_clip
-        # NaN flag of the sign-split whole-tensor clip (fpq_fake_quant_signsplit, FPQ_FLAG_GLOBAL_CLIP)
-        self.flag = torch.zeros(2, dtype=torch.int32, device=device) if global_clip else None      # {flag, ticket}
+        # {flag, ticket} of the sign-split whole-tensor clip (fpq_fake_quant_signsplit, FPQ_FLAG_GLOBAL_CLIP), one per stream:
+        # two launches on different streams must not share a ticket
+        self._flags: dict = {}
+
+    def _flag(self, stream: int) -> int:
+        ws = self._flags.get(stream)
+        if ws is None:
+            ws = self._flags[stream] = torch.zeros(2, dtype=torch.int32, device=self.device)
+        return ws.data_ptr()
 
     def launch(self, call: Call, in_ptr: int, out_ptr: int, stream: int) -> None:
+        if torch.cuda.current_device() != self.device.index:
+            with torch.cuda.device(self.device):          # the CUDA runtime launches on the calling thread's current device
+                return self._launch(call, in_ptr, out_ptr, stream)
+        return self._launch(call, in_ptr, out_ptr, stream)
+
+    def _launch(self, call: Call, in_ptr: int, out_ptr: int, stream: int) -> None:
         lib = self.lib
         if call.op == "group":
             n_groups = call.elems // 128
@@ -60,13 +78,22 @@ class DeviceReplay:
             n_groups = call.elems // 128
             rc = lib.fpq_fake_quant_signsplit(in_ptr, out_ptr, n_groups, 128, _DT[call.in_dtype], _DT[call.out_dtype],
                                               L.SPLIT[call.fmt], L.TIE["kernel"], L.FLAG_GLOBAL_CLIP if self.global_clip else 0,
-                                              self.flag.data_ptr() if self.flag is not None else None, stream)
+                                              self._flag(stream) if self.global_clip else None, stream)
             L.check(rc, "fpq_fake_quant_signsplit")
         elif call.op == "rotate_quant":
             s = self.smooth.get(call.site)
             rc = lib.fpq_transform_rotate_quant(in_ptr, s.data_ptr() if s is not None else None, self.sign_bits, out_ptr, None,
                                                 call.rows, call.cols, L.FMT[call.fmt], stream)
             L.check(rc, "fpq_transform_rotate_quant")
+        elif call.op == "mod_rotate_quant":
+            s = self.smooth.get(call.site)
+            gain, shift = self.modulate[call.site]
+            if gain.shape[0] * call.rows_per_batch < call.rows or gain.shape[1] != call.cols:
+                raise L.FpqError(f"modulate tensors of {call.site} are too small for {call.rows} rows / {call.rows_per_batch} per batch")
+            rc = lib.fpq_modulate_transform_rotate_quant(in_ptr, gain.data_ptr(), shift.data_ptr(), call.rows_per_batch,
+                                                         s.data_ptr() if s is not None else None, self.sign_bits, out_ptr, None,
+                                                         call.rows, call.cols, L.FMT[call.fmt], L.MOD_GAIN, stream)
+            L.check(rc, "fpq_modulate_transform_rotate_quant")
         else:
             raise L.FpqError(f"unknown op {call.op!r}")
 
@@ -77,9 +104,9 @@ class HostPipeline:
     ``slots`` device staging buffers."""
 
     def __init__(self, device: torch.device, max_in_bytes: int, max_out_bytes: int, smooth: Optional[dict] = None,
-                 slots: int = 2, global_clip: bool = True):
+                 slots: int = 2, global_clip: bool = True, modulate: Optional[dict] = None):
         self.device = device
-        self.replay = DeviceReplay(device, smooth, global_clip=global_clip)
+        self.replay = DeviceReplay(device, smooth, global_clip=global_clip, modulate=modulate)
         self.slots = slots
         self.d_in = [torch.empty(max_in_bytes, dtype=torch.uint8, device=device) for _ in range(slots)]
         self.d_out = [torch.empty(max_out_bytes, dtype=torch.uint8, device=device) for _ in range(slots)]
@@ -132,4 +159,6 @@ def run_call(call: Call, x: torch.Tensor, smooth: Optional[torch.Tensor] = None,
         return ops.fake_quant_signsplit(x, call.fmt, 128, "kernel", global_clip=global_clip)
     if call.op == "rotate_quant":
         return ops.transform_rotate_quant(x, smooth, seed42_sign_bits(), call.fmt)
+    if call.op == "mod_rotate_quant":
+        raise L.FpqError("run_call: a mod_rotate_quant call needs its adaLN tensors; use ops.modulate_transform_rotate_quant")
     raise L.FpqError(f"unknown op {call.op!r}")

@@ -72,6 +72,21 @@ def _rows(x: torch.Tensor, row_len: Optional[int]) -> tuple[int, int]:
     return n // row_len, row_len
 
 
+def _smooth_f32(smooth: Optional[torch.Tensor], n_cols: int, what: str) -> Optional[torch.Tensor]:
+    """The GALT factor as the kernels take it: a float32 contiguous CUDA vector of `n_cols` entries.  Anything else is
+    converted on the current stream (the kernels read it only after their programmatic-dependency wait, so a cast
+    kernel launched right in front of them is ordered like any other producer)."""
+    if smooth is None:
+        return None
+    _require_cuda(smooth, f"{what}(smooth)")
+    if smooth.numel() != n_cols:
+        raise L.FpqError(f"{what}: smooth has {smooth.numel()} entries, expected {n_cols}")
+    smooth = smooth.detach()
+    if smooth.dtype != torch.float32 or not smooth.is_contiguous():
+        smooth = smooth.to(torch.float32).contiguous()
+    return smooth.reshape(-1)
+
+
 def fake_quant(x: torch.Tensor, fmt: str, row_len: Optional[int] = 128, tie: str = "kernel", clamp3: bool = False,
                out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """Symmetric fake-quant (fpq_fake_quant). ``row_len=None``: the last dim shares one scale
@@ -159,11 +174,7 @@ def transform_rotate_quant(x: torch.Tensor, smooth: Optional[torch.Tensor], sign
         raise L.FpqError("transform_rotate_quant: x must be float32 (the adaLN-modulated LayerNorm output)")
     x = x.contiguous()
     c = x.shape[-1]
-    if smooth is not None:
-        _require_cuda(smooth, "transform_rotate_quant(smooth)")
-        smooth = smooth.detach().to(torch.float32).contiguous()
-        if smooth.numel() != c:
-            raise L.FpqError(f"smooth has {smooth.numel()} entries, expected {c}")
+    smooth = _smooth_f32(smooth, c, "transform_rotate_quant")
     out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
     rot = torch.empty_like(out) if return_rotated else None
     n_rows = x.numel() // c if c else 0
@@ -201,10 +212,7 @@ def modulate_transform_rotate_quant(x: torch.Tensor, scale: torch.Tensor, shift:
     if scale.dtype == torch.float16:
         scale, flags = scale.detach().add(1), L.MOD_GAIN
     mods = [t.detach().to(torch.float32).contiguous() for t in (scale, shift)]
-    if smooth is not None:
-        smooth = smooth.detach().to(torch.float32).contiguous()
-        if smooth.numel() != c:
-            raise L.FpqError(f"smooth has {smooth.numel()} entries, expected {c}")
+    smooth = _smooth_f32(smooth, c, "modulate_transform_rotate_quant")
     out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
     rot = torch.empty_like(out) if return_rotated else None
     with _on_device(x) as _di:
@@ -225,8 +233,7 @@ def transform_rotate_weight(w: torch.Tensor, smooth: Optional[torch.Tensor], sig
         if inplace:
             raise L.FpqError("transform_rotate_weight: in-place needs a contiguous tensor")
         w = w.contiguous()
-    if smooth is not None:
-        smooth = smooth.detach().to(torch.float32).contiguous()
+    smooth = _smooth_f32(smooth, w.shape[1], "transform_rotate_weight")
     out = w if inplace else torch.empty_like(w)
     with _on_device(w) as _di:
         rc = L.lib().fpq_transform_rotate_weight(w.data_ptr(), smooth.data_ptr() if smooth is not None else None, sign_bits,
@@ -246,6 +253,9 @@ def score_formats(x: torch.Tensor, formats: Sequence[str], tie: str = "kernel", 
     x = x.contiguous()
     if sse is None:
         sse = torch.zeros(len(formats), dtype=torch.float64, device=x.device)
+    elif not (isinstance(sse, torch.Tensor) and sse.is_cuda and sse.device == x.device and sse.dtype == torch.float64
+              and sse.is_contiguous() and sse.numel() >= len(formats)):
+        raise L.FpqError(f"score_formats: sse must be a contiguous float64 tensor of >= {len(formats)} entries on {x.device}")
     codes = (ctypes.c_int * len(formats))(*[_fmt_code(f) for f in formats])
     n_rows, rl = _rows(x, 128)
     with _on_device(x) as _di:

@@ -29,7 +29,9 @@ PATCH_NUMS_512 = (1, 2, 3, 4, 6, 9, 13, 18, 24, 32)      # evaluate_fp_quant_tra
 @dataclass(frozen=True)
 class Call:
     """One activation-quantizer call.  ``op``: "group" (symmetric per-group), "signsplit",
-    "rotate_quant" (GALT multiply + block Hadamard + per-group quant)."""
+    "rotate_quant" (GALT multiply + block Hadamard + per-group quant), "mod_rotate_quant" (the same with the adaLN
+    modulate ``x * (scale + 1) + shift`` in front of it, basic_var.py:263,266: what INTEGRATION.md level (c) runs at
+    mat_qkv / fc1; ``rows_per_batch`` token rows share one [C] row of scale / shift)."""
     stage: int
     block: int
     site: str
@@ -39,6 +41,7 @@ class Call:
     cols: int
     in_dtype: str        # "f32" | "f16"
     out_dtype: str
+    rows_per_batch: int = 0
 
     @property
     def elems(self) -> int:
@@ -53,9 +56,14 @@ class Call:
         return self.elems * (4 if self.out_dtype == "f32" else 2)
 
     @property
+    def aux_bytes(self) -> int:
+        """The fp32 adaLN scale and shift rows a "mod_rotate_quant" call reads: 2 x [rows / rows_per_batch, cols]."""
+        return 2 * (self.rows // self.rows_per_batch) * self.cols * 4 if self.op == "mod_rotate_quant" else 0
+
+    @property
     def bytes(self) -> int:
-        """Algorithmic bytes: every input element read once, every output element written once."""
-        return self.in_bytes + self.out_bytes
+        """Algorithmic bytes: every input element (and adaLN operand) read once, every output element written once."""
+        return self.in_bytes + self.out_bytes + self.aux_bytes
 
 
 @dataclass(frozen=True)
@@ -68,6 +76,7 @@ class VarHotPath:
     act_fmt: str = "e2m1"            # fp_e2
     fc2_op: str = "signsplit"
     fc2_fmt: str = "e1m2_neg_e2m1_pos"
+    modulate: bool = False           # mat_qkv / fc1: the adaLN modulate fused into the rotate kernel (needs rotate_transform)
 
     @property
     def width(self) -> int:
@@ -79,15 +88,17 @@ class VarHotPath:
     def calls(self, blocks: Sequence[int] | None = None) -> List[Call]:
         c = self.width
         out: List[Call] = []
+        rot_op = "mod_rotate_quant" if self.modulate else "rotate_quant"
         for si, rows in enumerate(self.stage_rows()):
+            rpb = self.patch_nums[si] ** 2 if self.modulate else 0        # token rows of one image at this stage
             for b in (range(self.depth) if blocks is None else blocks):
                 if self.rotate_transform:
-                    out.append(Call(si, b, "mat_qkv", "rotate_quant", self.act_fmt, rows, c, "f32", "f16"))
+                    out.append(Call(si, b, "mat_qkv", rot_op, self.act_fmt, rows, c, "f32", "f16", rpb))
                 else:
                     out.append(Call(si, b, "mat_qkv", "group", self.act_fmt, rows, c, "f32", "f32"))
                 out.append(Call(si, b, "proj", "group", self.act_fmt, rows, c, "f16", "f16"))
                 if self.rotate_transform:
-                    out.append(Call(si, b, "fc1", "rotate_quant", self.act_fmt, rows, c, "f32", "f16"))
+                    out.append(Call(si, b, "fc1", rot_op, self.act_fmt, rows, c, "f32", "f16", rpb))
                 else:
                     out.append(Call(si, b, "fc1", "group", self.act_fmt, rows, c, "f32", "f32"))
                 out.append(Call(si, b, "fc2", self.fc2_op, self.fc2_fmt, rows, 4 * c, "f16", "f16"))
@@ -104,10 +115,14 @@ class VarHotPath:
 WORKLOADS = {
     # configs[1]: VAR-d16 256x256 W4A4 fp_e2 per-group, batch 64 (models_fp_quant: no rotation)
     "var_d16_w4a4": VarHotPath("var_d16_w4a4", 16, 64, PATCH_NUMS_256, False, "e2m1", "group", "e2m1"),
-    # configs[2]: VAR-d30 256x256 W4A4 fp_e2 + fc2 fp_e1m2_neg_e2m1_pos, block rotate + GALT (README.md:33), B=50 per GPU
-    "var_d30_w4a4_rot": VarHotPath("var_d30_w4a4_rot", 30, 50, PATCH_NUMS_256, True, "e2m1", "signsplit", "e1m2_neg_e2m1_pos"),
+    # configs[2]: VAR-d30 256x256 W4A4 fp_e2 + fc2 fp_e1m2_neg_e2m1_pos, block rotate + GALT (README.md:33), B=50 per GPU;
+    # mat_qkv / fc1 through the adaLN-fused kernel, as INTEGRATION.md level (c) calls it
+    "var_d30_w4a4_rot": VarHotPath("var_d30_w4a4_rot", 30, 50, PATCH_NUMS_256, True, "e2m1", "signsplit", "e1m2_neg_e2m1_pos", True),
     # configs[3]: VAR-d36 512x512 W6A6 FP6 per-group, rotate + transform, B=10 per call
-    "var_d36_w6a6_rot": VarHotPath("var_d36_w6a6_rot", 36, 10, PATCH_NUMS_512, True, "e2m3", "signsplit", "int_neg_e2m3_pos"),
+    "var_d36_w6a6_rot": VarHotPath("var_d36_w6a6_rot", 36, 10, PATCH_NUMS_512, True, "e2m3", "signsplit", "int_neg_e2m3_pos", True),
+    # the same two with the modulate left to the caller (three ATen kernels in front of `.mul(s) @ Q`): round-1's step
+    "var_d30_w4a4_rot_nomod": VarHotPath("var_d30_w4a4_rot_nomod", 30, 50, PATCH_NUMS_256, True, "e2m1", "signsplit", "e1m2_neg_e2m1_pos"),
+    "var_d36_w6a6_rot_nomod": VarHotPath("var_d36_w6a6_rot_nomod", 36, 10, PATCH_NUMS_512, True, "e2m3", "signsplit", "int_neg_e2m3_pos"),
 }
 
 

@@ -86,6 +86,16 @@ FPQ_API const char *fpq_last_cuda_error(void);
 FPQ_API uint64_t fpq_launch_count(void);
 
 /*
+ * Measurement aid: launch-geometry choices that were made from measurements can be moved at run time (by tools/ and the
+ * GPU tests; never through the environment).  Process-wide; not meant to be changed while other threads launch.
+ *   "pdl"                  1 (default) | 0: programmatic dependent launch of the activation kernels on / off
+ *   "row_v"                0 (default: chosen per row length) | 1 | 2 | 4: 16-byte vectors per thread of the per-token kernels
+ *   "rot_small_max_chunks" rotate launches of up to this many 128-chunks take the small-launch kernel (default 24576)
+ * Results never depend on a tunable (tests/test_gpu_shapes.py).  Returns FPQ_ERR_ARG for an unknown name or value.
+ */
+FPQ_API int fpq_set_tunable(const char *name, long long value);
+
+/*
  * z[i] = nearest entry of grid[0..k) to x[i] (fp32, n elements), reference scan semantics;
  * k <= 256.  tie_mode FPQ_TIE_KERNEL reproduces quant_cuda.quant exactly, including grids it
  * has never seen (unsorted, duplicated entries); the reference's own grids take a closed-form
@@ -128,13 +138,14 @@ FPQ_API int fpq_fake_quant_signsplit(const void *x, void *out, size_t n_rows, si
 /*
  * Fused activation path of the rotated/transformed model (basic_var.py:263,266 followed by
  * QuantizedLinear.forward qu.py:764-769):
- *     y   = half( FWHT_128( x[., c] * smooth[c] * sign[c % 128] ) / fl32(sqrt(128)) )
+ *     y   = half( FWHT_128( x[., c] * m[c] ) ),   m[c] = fl32(smooth[c] * fl32(1/sqrt(128))) * sign[c % 128]
  *     out = fake_quant_group128(y, format)         (fp16 in, fp16 out, FPQ_TIE_KERNEL)
  *   x        : fp32 [n_rows, n_cols], n_cols % 128 == 0 (adaLN-modulated LayerNorm output)
  *   smooth   : fp32 [n_cols] GALT factor s, or NULL for 1
  *   sign_bits: 128-bit mask, bit i of word i/32 set = +1 (the seed-42 vector of
  *              rotate_utils/hadamard_utils.py:95-97); host memory, read at call time
- *   out      : fp16 [n_rows, n_cols] fake-quantized
+ *   out      : fp16 [n_rows, n_cols] fake-quantized; 8-byte aligned (16-byte aligned outputs let large launches take the
+ *              streaming kernel; the values do not depend on which kernel runs)
  *   rotated  : optional fp16 [n_rows, n_cols]: the pre-quantization rotated values (NULL to skip)
  *   format   : FPQ_FMT_* or -1 to skip quantization (then `out` receives the rotated values)
  */
@@ -158,6 +169,14 @@ FPQ_API int fpq_transform_rotate_quant(const float *x, const float *smooth, cons
 FPQ_API int fpq_modulate_transform_rotate_quant(const float *x, const float *scale, const float *shift, size_t rows_per_batch,
                                         const float *smooth, const uint32_t *sign_bits_host, void *out, void *rotated,
                                         size_t n_rows, size_t n_cols, int format, int flags, void *stream);
+
+/*
+ * Launch plan of the streaming rotate kernel for rows of `chunks_per_row` 128-element chunks (host-only query, no CUDA
+ * call; used by the CPU tests to keep tests/rotate_layout_model.py in step with the launcher):
+ * plan_host[6] = {chunk columns per warp, warps across the columns, consumer warps, rows per tile, bytes per stage,
+ * stages}.  FPQ_ERR_UNSUPPORTED when such rows only take the small-launch kernel.
+ */
+FPQ_API int fpq_rotate_plan(int chunks_per_row, int *plan_host);
 
 /*
  * Weight side of the same transform (transform_model_utils.py:8-28, rotation_utils.py:129-154):

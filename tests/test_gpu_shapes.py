@@ -79,17 +79,21 @@ def test_signsplit_row_kernels(ops, row_len, din, tie):
         assert bits_equal(got, want), f"split rows {row_len} {din} {fmt} {tie}\n" + mismatch_report(got, want)
 
 
-@pytest.mark.parametrize("v", ["1", "2", "4"])
-def test_row_kernels_values_per_thread_override(ops, v, monkeypatch):
-    """FPQ_ROW_V (measurement aid, read per launch) must not change results."""
-    monkeypatch.setenv("FPQ_ROW_V", v)
-    torch.manual_seed(int(v))
-    for row_len in (520, 1920, 7680):
-        x = (torch.randn(9, row_len, device="cuda") * 3).half()
-        x[2, 5] = float("nan")
-        assert bits_equal(host(ops.fake_quant(x, "e2m3", None, "kernel")), O.fake_quant(host(x), "e2m3", None, "kernel"))
-        assert bits_equal(host(ops.fake_quant_signsplit(x, "int_neg_e2m3_pos", None, "kernel")),
-                          O.fake_quant_signsplit(host(x), "int_neg_e2m3_pos", None, "kernel", clipping_strength=None))
+@pytest.mark.parametrize("v", [1, 2, 4])
+def test_row_kernels_values_per_thread_override(ops, v):
+    """The tunable row_v (values per thread of the per-token kernels, a measurement aid) must not change results."""
+    from fpqvar_b200 import _lib as L
+    L.set_tunable("row_v", v)
+    try:
+        torch.manual_seed(v)
+        for row_len in (520, 1920, 7680):
+            x = (torch.randn(9, row_len, device="cuda") * 3).half()
+            x[2, 5] = float("nan")
+            assert bits_equal(host(ops.fake_quant(x, "e2m3", None, "kernel")), O.fake_quant(host(x), "e2m3", None, "kernel"))
+            assert bits_equal(host(ops.fake_quant_signsplit(x, "int_neg_e2m3_pos", None, "kernel")),
+                              O.fake_quant_signsplit(host(x), "int_neg_e2m3_pos", None, "kernel", clipping_strength=None))
+    finally:
+        L.set_tunable("row_v", 0)
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.float16])
@@ -134,19 +138,61 @@ def test_side_stream_and_graph_replay(ops):
     assert bits_equal(host(y2), want), "workspace not reset after a poisoned call"
 
 
-def test_results_identical_without_pdl():
-    """FPQ_NO_PDL=1 (plain stream-ordered launches) must give the same bits."""
-    code = ("import torch, hashlib; from fpqvar_b200 import ops; from fpqvar_b200.hotpath import seed42_sign_bits;"
-            "torch.manual_seed(0); x=torch.randn(3000,1920,device='cuda'); h=torch.nn.functional.gelu(x).half();"
-            "a=ops.transform_rotate_quant(x, None, seed42_sign_bits(), 'e2m1'); b=ops.fake_quant_signsplit(h,'e1m2_neg_e2m1_pos',128,'kernel',global_clip=True);"
-            "c=ops.fake_quant(h,'e2m1',128,'kernel'); torch.cuda.synchronize();"
-            "print(hashlib.sha256(a.cpu().numpy().tobytes()+b.cpu().numpy().tobytes()+c.cpu().numpy().tobytes()).hexdigest())")
-    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    outs = []
-    for env_extra in ({}, {"FPQ_NO_PDL": "1"}):
-        env = dict(os.environ, **env_extra)
-        outs.append(subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300).stdout.strip())
-    assert outs[0] and outs[0] == outs[1], outs
+def test_results_identical_without_pdl(ops):
+    """Plain stream-ordered launches (tunable pdl = 0) must give the same bits as programmatic dependent launches."""
+    from fpqvar_b200 import _lib as L
+    from fpqvar_b200.hotpath import seed42_sign_bits
+    torch.manual_seed(0)
+    x = torch.randn(3000, 1920, device="cuda")
+    h = torch.nn.functional.gelu(x).half()
+    s_ = torch.exp(torch.rand(1920, device="cuda") * 2 - 1)
+
+    def run():
+        a = ops.transform_rotate_quant(x, s_, seed42_sign_bits(), "e2m1")
+        b = ops.fake_quant_signsplit(h, "e1m2_neg_e2m1_pos", 128, "kernel", global_clip=True)
+        c = ops.fake_quant(h, "e2m1", 128, "kernel")
+        torch.cuda.synchronize()
+        return [host(t) for t in (a, b, c)]
+
+    with_pdl = run()
+    L.set_tunable("pdl", 0)
+    try:
+        without = run()
+    finally:
+        L.set_tunable("pdl", 1)
+    for u, v in zip(with_pdl, without):
+        assert bits_equal(u, v)
+
+
+def test_rotate_kernel_choice_does_not_change_results(ops):
+    """The tunable rot_small_max_chunks moves the boundary between the small-launch rotate kernel and the streaming
+    (bulk-copy staged) one: the same tensor must rotate and quantize to the same bits through either, with and without the
+    adaLN modulate, for every row length the streaming kernel plans differently (chunk columns per warp 1 / 2 / 4, idle lane
+    sets, 8 or 9 consumer warps)."""
+    from fpqvar_b200 import _lib as L
+    from fpqvar_b200.hotpath import seed42_sign_bits
+    sb = seed42_sign_bits()
+    torch.manual_seed(11)
+    try:
+        for cols, rows, rpb in ((128, 777, 7), (256, 500, 50), (384, 301, 43), (640, 257, 257), (1024, 130, 65), (1920, 143, 11),
+                                (2304, 97, 97), (2944, 50, 25), (4608, 37, 37)):
+            x = torch.randn(rows, cols, device="cuda") * torch.exp(torch.randn(rows, 1, device="cuda"))
+            x[rows // 2, : 128] = 0.0                                   # an all-zero group (irregular scale)
+            s_ = torch.exp(torch.rand(cols, device="cuda") * 2 - 1)
+            b = rows // rpb
+            sc = torch.randn(b, 1, cols, device="cuda") * 0.3
+            sh = torch.randn(b, 1, cols, device="cuda") * 0.5
+            res = []
+            for small_max in (1 << 40, 0):                              # everything small / everything streaming
+                L.set_tunable("rot_small_max_chunks", small_max)
+                q, r = ops.transform_rotate_quant(x, s_, sb, "e2m1", return_rotated=True)
+                q6 = ops.transform_rotate_quant(x, None, sb, "e3m2")
+                qm, rm = ops.modulate_transform_rotate_quant(x.view(b, rpb, cols), sc, sh, s_, sb, "e2m3", return_rotated=True)
+                res.append([host(t) for t in (q, r, q6, qm, rm)])
+            for u, v in zip(*res):
+                assert bits_equal(u, v), (cols, rows, rpb)
+    finally:
+        L.set_tunable("rot_small_max_chunks", 24576)
 
 
 def test_randomized_differential_against_oracle(ops):

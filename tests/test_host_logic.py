@@ -69,13 +69,94 @@ def test_var_workload_shapes_and_bytes():
     assert {c.site for c in calls} == {"mat_qkv", "proj", "fc1", "fc2"}
     # 548 M activation elements per image: 68000 rows x 7C x 30 blocks / 50 images
     assert d30.elems_per_pass() == 68000 * 7 * 1920 * 30
-    assert d30.bytes_per_pass() == 68000 * 30 * 32 * 1920          # 6C + 4C + 6C + 16C bytes per token and block
+    # 6C + 4C + 6C + 16C bytes per token and block, plus the adaLN rows the fused mat_qkv / fc1 kernel reads:
+    # 2 sites x (scale, shift) x 100 batch rows x C x 4 bytes per block and stage
+    assert d30.modulate and all(c.op == "mod_rotate_quant" and c.rows_per_batch * 100 == c.rows for c in calls if c.site in ("mat_qkv", "fc1"))
+    assert d30.bytes_per_pass() == 68000 * 30 * 32 * 1920 + 10 * 30 * 2 * 2 * 100 * 1920 * 4
+    nomod = WORKLOADS["var_d30_w4a4_rot_nomod"]
+    assert nomod.bytes_per_pass() == 68000 * 30 * 32 * 1920 and all(c.op != "mod_rotate_quant" for c in nomod.calls())
     d16 = WORKLOADS["var_d16_w4a4"]
     assert d16.stage_rows()[-1] == 32768 and d16.width == 1024
     assert all(c.op == "group" for c in d16.calls())
     d36 = WORKLOADS["var_d36_w6a6_rot"]
     assert d36.stage_rows() == [20, 80, 180, 320, 720, 1620, 3380, 6480, 11520, 20480] and d36.width == 2304
     assert all(c.elems % 128 == 0 for w in WORKLOADS.values() for c in w.calls())
+
+
+# ---------------------------------------------------------------------------------------------
+# streaming rotate kernel: launch plan and shared-memory choreography (tests/rotate_layout_model.py)
+# ---------------------------------------------------------------------------------------------
+ROT_CPRS = [1, 2, 3, 4, 5, 7, 8, 12, 15, 16, 18, 20, 23, 32, 36]
+
+
+def test_rotate_plan_model_matches_the_launcher():
+    """The Python mirror of rot_plan() plans exactly like the C++ launcher (fpq_rotate_plan is a host-only query)."""
+    import ctypes
+    import rotate_layout_model as M
+    from fpqvar_b200 import _lib as L
+    lib = L.lib()
+    for cpr in list(range(1, 80)) + [128, 1000]:
+        out = (ctypes.c_int * 6)()
+        rc = lib.fpq_rotate_plan(cpr, out)
+        want = M.rot_plan(cpr)
+        if want is None:
+            assert rc == L.FPQ_ERR_UNSUPPORTED, cpr
+            continue
+        assert rc == 0, cpr
+        assert list(out) == [want["cw"], want["wcols"], want["n_warps"], want["rs"], want["stage_bytes"], M.ROT_STAGES], cpr
+        assert want["n_warps"] <= M.ROT_MAX_WARPS and M.ROT_STAGES * want["stage_bytes"] + 48 <= 110 * 1024
+    assert M.rot_plan(15)["rs"] == 4 and M.rot_plan(15)["n_warps"] == 8       # VAR-d30: 2 CTAs x 8 consumer warps per SM
+    assert M.rot_plan(18)["cw"] == 2 and M.rot_plan(18)["n_warps"] == 9       # VAR-d36: no idle lane sets
+
+
+@pytest.mark.parametrize("cpr", ROT_CPRS)
+def test_rotate_streaming_layout_covers_every_unit_without_bank_conflicts(cpr):
+    import rotate_layout_model as M
+    plan = M.rot_plan(cpr)
+    seen1, seen2 = {}, {}
+    for warp in range(plan["n_warps"]):
+        for sub in range(2):
+            for ph in range(4):
+                accs = [M.pass1_accesses(plan, warp, lane, sub) for lane in range(8 * ph, 8 * ph + 8)]
+                for a in range(4):
+                    assert M.conflict_free([x[a][0] if x else None for x in accs]), ("pass-1 load", warp, sub, ph, a)
+                    assert M.conflict_free([x[a][1] if x else None for x in accs]), ("pass-1 store", warp, sub, ph, a)
+                for x in accs:
+                    for ld, st in (x or []):
+                        seen1[ld] = seen1.get(ld, 0) + 1
+                # in place: a chunk's swizzled stores stay inside the units its own 8 lanes loaded
+                for g in range(0, 8, 8):
+                    lds = {ld for x in accs[g:g + 8] if x for ld, _ in x}
+                    sts = {st for x in accs[g:g + 8] if x for _, st in x}
+                    assert lds == sts
+        for ph in range(4):
+            accs = [M.pass2_accesses(plan, warp, lane) for lane in range(8 * ph, 8 * ph + 8)]
+            for i in range(8):
+                assert M.conflict_free([x[i] if x else None for x in accs]), ("pass-2 load", warp, ph, i)
+            for x in accs:
+                for a in (x or []):
+                    seen2[a] = seen2.get(a, 0) + 1
+    n_units = plan["rs"] * cpr * 32
+    assert len(seen1) == n_units and set(seen1.values()) == {1}
+    assert len(seen2) == n_units and set(seen2.values()) == {1}
+    assert max(seen1) + 16 <= plan["stage_bytes"]
+
+
+@pytest.mark.parametrize("cpr", [1, 3, 8, 15, 18, 36])
+def test_rotate_streaming_two_pass_butterflies_are_the_hadamard_transform(cpr):
+    """Pass 1 (bits 0,1,5,6, written back swizzled in place) + pass 2 (bits 2,3,4) == x * m @ H_128 on every chunk."""
+    import rotate_layout_model as M
+    plan = M.rot_plan(cpr)
+    rng = np.random.default_rng(cpr)
+    tile = rng.standard_normal((plan["rs"], cpr * 128))
+    mult = rng.standard_normal(cpr * 128)
+    h = np.array([[1.0]])
+    for _ in range(7):
+        h = np.block([[h, h], [h, -h]])
+    want = ((tile * mult).reshape(plan["rs"], cpr, 128) @ h).reshape(plan["rs"], -1)
+    got = M.simulate_tile(plan, tile, mult)
+    assert not np.isnan(got).any()
+    assert np.abs(got - want).max() <= 1e-11 * np.abs(want).max()
 
 
 def test_shard_units_partition():

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Per-token / per-channel (row) kernels at the README FP6 shapes (development aid): rows of C and 4C of VAR-d30 / d36,
-symmetric e2m3 and sign-split int_neg_e2m3_pos, fp16 -> fp16, for every values-per-thread choice (FPQ_ROW_V).
+symmetric e2m3 and sign-split int_neg_e2m3_pos, fp16 -> fp16, for every values-per-thread choice (tunable row_v).
 Rotating buffers (>> L2), CUDA events, algorithmic GB/s (4 B/element)."""
 import os
 import sys
@@ -44,16 +44,13 @@ def main():
                          ("split int_neg_e2m3_pos", lambda i: lib.fpq_fake_quant_signsplit(x[i].data_ptr(), o[i].data_ptr(), rows, row_len, 1, 1, 1, 0, 0, None, st))):
             cells = []
             for v in ("", "1", "2", "4"):
-                if v:
-                    os.environ["FPQ_ROW_V"] = v
-                else:
-                    os.environ.pop("FPQ_ROW_V", None)
+                lib.fpq_set_tunable(b"row_v", int(v) if v else 0)
                 if v and (row_len // 8 + int(v) - 1) // int(v) > 1024:
                     cells.append(f"{'-':>10}")
                     continue
                 t = timeit(fn)
                 cells.append(f"{rows * row_len * 4 / t / 1e9:10.0f}")
-            os.environ.pop("FPQ_ROW_V", None)
+            lib.fpq_set_tunable(b"row_v", 0)
             print(f"{row_len:>8} {rows:>7} {name:<28} " + " ".join(cells), flush=True)
         del x, o
         torch.cuda.empty_cache()

@@ -20,7 +20,12 @@ big = torch.randn(1 << 29, device=dev)                      # 2 GiB fp32
 bigh = torch.nn.functional.gelu(torch.randn(1 << 30, device=dev)).half()   # 2 GiB fp16
 outb = torch.empty(1 << 31, dtype=torch.uint8, device=dev)
 smooth = {s: torch.exp(torch.rand(C, device=dev) * 2 - 1) for s in ("mat_qkv", "fc1")}
-rep = DeviceReplay(dev, smooth)
+modulate = {s: (1.0 + 0.3 * torch.randn(2 * hot.batch, C, device=dev), 0.5 * torch.randn(2 * hot.batch, C, device=dev)) for s in ("mat_qkv", "fc1")}
+rep = DeviceReplay(dev, smooth, modulate=modulate)
+for kv in os.environ.get("FPQ_TUNABLES", "").split(","):        # e.g. FPQ_TUNABLES=rot_small_max_chunks=0,pdl=0
+    if kv:
+        k, v = kv.split("=")
+        _L.set_tunable(k, int(v))
 side = torch.cuda.Stream()
 cur = {"f32": 0, "f16": 0, "out": 0}
 
