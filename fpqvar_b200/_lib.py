@@ -27,7 +27,7 @@ SIGNATURES = {
     "fpq_last_cuda_error": (_c.c_char_p, []),
     "fpq_launch_count": (_c.c_uint64, []),
     "fpq_set_tunable": (_c.c_int, [_c.c_char_p, _c.c_longlong]),
-    "fpq_rotate_plan": (_c.c_int, [_c.c_int, _c.c_void_p]),
+    "fpq_rotate_plan": (_c.c_int, [_c.c_int, _c.c_int, _c.c_void_p]),
     "fpq_quant_grid": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_size_t, _c.c_void_p, _c.c_int, _c.c_void_p]),
     "fpq_fake_quant": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                   _c.c_uint, _c.c_void_p]),

@@ -125,8 +125,16 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 
+// Every activation kernel asks for the same L1 / shared-memory split (the largest shared-memory carveout): the streaming
+// rotate kernel needs it, the others stream with L1::no_allocate loads and lose nothing -- and an SM only changes its
+// split when it is idle, so kernels that alternate between two splits (rotate -> group -> rotate -> sign-split ... in a
+// VAR pass) cannot overlap their tails and pay a drain per launch (measured: 28.1 ms instead of 24.7 ms per step when
+// only the rotate kernel asked for it).  Set once per (kernel, device); defined in fpq_grid.cu.
+void prefer_max_smem(const void* kernel);
+
 template <typename... KArgs, typename... Args>
 static inline void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args... args) {
+    prefer_max_smem(reinterpret_cast<const void*>(kernel));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(block);

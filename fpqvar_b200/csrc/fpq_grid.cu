@@ -95,6 +95,25 @@ int finish_launch() {
 
 Tunables g_tun;
 
+void prefer_max_smem(const void* kernel) {
+    // open-addressed set of (kernel, device) pairs that already carry the attribute; a lost race only repeats the call
+    constexpr int N = 1024;
+    static const void* seen_fn[N];
+    static int seen_dev[N];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    unsigned h = unsigned((reinterpret_cast<uintptr_t>(kernel) >> 4) * 2654435761u + unsigned(dev) * 40503u) % N;
+    for (int probe = 0; probe < N; ++probe, h = (h + 1) % N) {
+        if (seen_fn[h] == kernel && seen_dev[h] == dev) return;
+        if (seen_fn[h] == nullptr) {
+            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            seen_dev[h] = dev;
+            seen_fn[h] = kernel;
+            return;
+        }
+    }
+}
+
 int sm_count() {
     static int n = 0;
     if (n == 0) {

@@ -181,71 +181,60 @@ __global__ void __launch_bounds__(256, MOD ? 1 : 0) transform_rotate_quant_small
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Streaming kernel (everything from a few thousand rows on).  One persistent CTA per contiguous range of rows
-// (ranges differ by at most one row: no partial wave at the end), two CTAs per SM.
-//   producer warp     one lane streams tiles of RS whole rows (contiguous bytes) into a ring of ROT_STAGES shared-memory
-//                     stages with 1-D bulk async copies (cp.async.bulk -> UBLKCP, the TMA engine) that complete on
-//                     an mbarrier: the bytes in flight cost shared memory, not registers, and never stall a compute warp
-//                     on global memory.
-//   consumer warps    a warp owns CW chunk columns x 8/CW rows of every tile (CW = 1, 2 or 4, chosen per row length by
-//                     rot_plan), the same columns in every tile, so the multipliers (and, with MOD, the adaLN
-//                     operands of the current batch) live in registers.  The transform runs in two passes over the
-//                     tile in shared memory, so that no butterfly crosses lanes (no SHFL at all):
+// Streaming kernel (everything from a few thousand chunks on; rows of 4 .. 36 chunks).
+//   work split      a CTA has one warp per group of 4 chunk columns (rows of 15 chunks, VAR-d30: 4 warps; 18 chunks,
+//                   VAR-d36: 5 warps) and owns a contiguous range of rows (ranges differ by at most one row over the
+//                   grid: no partial wave at the end); several CTAs per SM (about 20 warps, the register budget).  A warp
+//                   walks down its rows two at a time, always on the same 4 columns, so that the multipliers (and, with
+//                   MOD, the adaLN operands of the current batch) live in registers.
+//   staging         every warp has a PRIVATE double buffer of 2 x 4 KB in shared memory and is its own producer: lane 0
+//                   fetches the warp's next 2 rows x 4 chunks with 1-D bulk async copies (cp.async.bulk -> UBLKCP, the TMA
+//                   engine; 2 KB of contiguous bytes per row) that complete on the buffer's mbarrier.  The bytes in flight
+//                   cost shared memory, not registers, no warp ever waits for another one (no CTA barrier after the
+//                   prologue), and the copy for step k+2 is issued as soon as step k has left its buffer.
+//   transform       two passes over the 8 chunks in shared memory, so that no butterfly crosses lanes (no SHFL at all):
 //       pass 1   8 lanes x 16 values per chunk: lane l holds the 16-byte units u = 8a + l (a = 0..3) of its chunk,
 //                i.e. index bits 0,1 (inside a unit) and 5,6 (a) -- multiply, butterflies 0,1,5,6, write back IN PLACE;
-//                a warp does this twice per tile (two sub-iterations of 4 chunks, same columns, next rows);
+//                done twice per step (row r, then row r + 1, same columns);
 //       pass 2   4 lanes x 32 values per chunk: lane l' holds the units 8l' + i (i = 0..7), index bits 0..4 --
 //                butterflies 2,3,4, round to fp16, per-group quantizer on the register tile, 128-bit stores of 32
 //                CONTIGUOUS elements per lane.
-//   bank conflicts    a chunk is 512 B = 4 x 128 B bank windows, and an LDS.128 / STS.128 is served 8 lanes at a time.
+//   bank conflicts  a chunk is 512 B = 4 x 128 B bank windows, and an LDS.128 / STS.128 is served 8 lanes at a time.
 //                Pass 1 reads 8 consecutive units per chunk: conflict-free as it is.  Pass 2 reads units 128 B apart
 //                in 4 lanes x 2 chunks per phase; the units are therefore stored XOR-swizzled inside their 128-byte
 //                window by pass 1: unit (a, c) sits at slot c ^ (2a + s), s = parity of the chunk among the warp's 8.
-//                Both the swizzled pass-1 stores and the pass-2 loads then touch 8 distinct 16-byte slots per phase.
+//                Both the swizzled pass-1 stores and the pass-2 loads then touch 8 distinct 16-byte slots per phase
+//                (tests/rotate_layout_model.py replays the choreography on the host).
 // ------------------------------------------------------------------------------------------------------------
-constexpr int ROT_STAGES = 3;
-constexpr int ROT_MAX_WARPS = 9;                      // consumer warps per CTA
-constexpr int ROT_MAX_THREADS = 32 * (ROT_MAX_WARPS + 1);
+constexpr int ROT_MIN_CPR = 4, ROT_MAX_CPR = 36;       // rows the streaming kernel takes, in chunks
+constexpr int ROT_WARP_STAGE_BYTES = 4096;             // 2 rows x 4 chunks x 512 B
+constexpr int ROT_WARP_SMEM = 2 * ROT_WARP_STAGE_BYTES + 16;      // + the two mbarriers
 
-struct RotPlan {
-    int cpr;                 // chunks per row
-    int cw;                  // chunk columns per warp: 1, 2 or 4
-    int wcols;               // warps across the columns: ceil(cpr / cw)
-    int n_warps;             // consumer warps = wcols * (row groups)
-    int rs;                  // rows per tile = (n_warps / wcols) * 2 * (4 / cw)
-    unsigned stage_bytes;    // rs * cpr * 512
-};
-
-// Registers: 2 CTAs x 320 threads leave 96 per thread, enough without the adaLN operands.  With them (MOD, 32 more live
-// registers) the kernel is capped at 112 instead: two CTAs of 288 threads (rows of 15 chunks, VAR-d30) still fit, a CTA
-// of 320 threads (rows of 18 chunks, VAR-d36) runs alone on its SM.
 template <int FMT, bool QUANT, bool MOD>
-__device__ __forceinline__ void rotate_tma_body(const float* __restrict__ x, const float* __restrict__ smooth,
-                                                                                       SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
-                                                                                       size_t n_rows, RotPlan plan, Modulate mod) {
+__device__ __forceinline__ void rotate_stream_body(const float* __restrict__ x, const float* __restrict__ smooth,
+                                                   SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
+                                                   size_t n_rows, int cpr, Modulate mod) {
     extern __shared__ __align__(128) unsigned char smem[];
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + size_t(ROT_STAGES) * plan.stage_bytes);
-    uint64_t* empty = full + ROT_STAGES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int NW = plan.n_warps;
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int s = 0; s < ROT_STAGES; ++s) {
-            mbar_init(&full[s], 1);
-            mbar_init(&empty[s], uint32_t(NW));
-        }
+    const int n_warps = blockDim.x >> 5;
+    unsigned char* stage0 = smem + size_t(warp) * (2 * ROT_WARP_STAGE_BYTES);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + size_t(n_warps) * (2 * ROT_WARP_STAGE_BYTES)) + 2 * warp;
+    if (lane == 0) {
+        mbar_init(&full[0], 1);
+        mbar_init(&full[1], 1);
         mbar_fence_init();
     }
     pdl_launch_dependents();
-    __syncthreads();
+    __syncwarp();
 
     // this CTA's rows: [r_begin, r_end), sizes differ by at most one row over the grid
     const size_t per = n_rows / gridDim.x, rem = n_rows % gridDim.x;
     const size_t r_begin = size_t(blockIdx.x) * per + (blockIdx.x < rem ? blockIdx.x : rem);
     const size_t r_end = r_begin + per + (blockIdx.x < rem ? 1 : 0);
-    const size_t row_elems = size_t(plan.cpr) * 128;
-    const int RS = plan.rs;
-    // MOD: a tile never straddles two batches (its adaLN operands are per batch); `left` = rows to the end of the batch
+    const size_t row_elems = size_t(cpr) * 128;
+    const int col0 = 4 * warp;                                          // first chunk column of this warp
+    const int ncols = cpr - col0 < 4 ? cpr - col0 : 4;                  // its columns that exist (the last warp may own fewer)
+    // MOD: a step never straddles two batches (its adaLN operands are per batch); `left` = rows to the end of the batch
     size_t batch = 0, left = ~size_t(0);
     if constexpr (MOD) {
         batch = r_begin / mod.rows_per_batch;
@@ -254,45 +243,37 @@ __device__ __forceinline__ void rotate_tma_body(const float* __restrict__ x, con
     // Nothing is read from global memory before pdl_wait(): x comes from the previous kernel, and `smooth` may too.
     pdl_wait();
 
-    if (warp == NW) {
-        // ---------------- producer: one lane ----------------
+    // ---- producer side (lane 0): the copy of step k + 2 is issued when step k has left its buffer ----
+    size_t r_issue = r_begin, left_issue = left;
+    auto issue = [&](uint32_t s) {
+        if (r_issue >= r_end) return;
+        size_t nr = r_end - r_issue;
+        if (nr > 2) nr = 2;
+        if (MOD && nr > left_issue) nr = left_issue;
         if (lane == 0) {
-            uint32_t s = 0, lap = 0;
-            for (size_t r = r_begin; r < r_end;) {
-                size_t nr = r_end - r;
-                if (nr > size_t(RS)) nr = size_t(RS);
-                if (MOD && nr > left) nr = left;
-                if (lap > 0) mbar_wait(&empty[s], (lap - 1) & 1u);             // stage free again
-                const uint32_t bytes = uint32_t(nr * row_elems * sizeof(float));
-                mbar_arrive_expect_tx(&full[s], bytes);
-                bulk_load(smem + size_t(s) * plan.stage_bytes, x + r * row_elems, bytes, &full[s]);
-                r += nr;
-                if constexpr (MOD) { left -= nr; if (left == 0) left = mod.rows_per_batch; }
-                if (++s == ROT_STAGES) { s = 0; ++lap; }
-            }
+            const uint32_t row_bytes = uint32_t(ncols) * 512u;
+            mbar_arrive_expect_tx(&full[s], uint32_t(nr) * row_bytes);
+            for (size_t j = 0; j < nr; ++j)
+                bulk_load(stage0 + s * ROT_WARP_STAGE_BYTES + j * 2048, x + (r_issue + j) * row_elems + size_t(col0) * 128, row_bytes, &full[s]);
         }
-        return;
-    }
+        r_issue += nr;
+        if constexpr (MOD) { left_issue -= nr; if (left_issue == 0) left_issue = mod.rows_per_batch; }
+    };
+    issue(0);
+    issue(1);
 
-    // ---------------- consumers ----------------
-    const int wc = warp % plan.wcols, wr = warp / plan.wcols;      // column group, row group of this warp
-    const int rps = 4 / plan.cw;                                   // rows per pass-1 sub-iteration
-    // pass 1: 8 lanes per chunk; the warp's 4 chunks of a sub-iteration are cw columns x rps rows
+    // pass 1: 8 lanes per chunk; sub-iteration `sub` = row, g4 = column within the warp
     const int g4 = lane >> 3, l8 = lane & 7;
-    const int col1 = wc * plan.cw + g4 % plan.cw;
-    const int trow1 = wr * 2 * rps + g4 / plan.cw;                 // + rps in the second sub-iteration
-    const bool colok1 = col1 < plan.cpr;
-    const int s1 = g4 & 1;                                         // parity of the chunk among the warp's 8 (pass-2 lane set index)
-    const uint32_t chunk1 = uint32_t(trow1 * plan.cpr + col1) * 512u;
-    const uint32_t sub_bytes = uint32_t(rps * plan.cpr) * 512u;    // second sub-iteration: rps rows further down
-    // pass 2: 4 lanes per chunk, lane set e = 4*sub + g4
+    const bool colok1 = g4 < ncols;
+    const uint32_t chunk1 = uint32_t(g4) * 512u;                        // + 2048 for the second row
+    const uint32_t slot1 = uint32_t(l8 ^ (g4 & 1));                     // pass-1 store slot before the per-unit ^ 2a
+    // pass 2: 4 lanes per chunk, lane set g8 = 4 * row + column
     const int g8 = lane >> 2, lq = lane & 3;
-    const int col2 = wc * plan.cw + (g8 & 3) % plan.cw;
-    const int trow2 = wr * 2 * rps + (g8 >> 2) * rps + (g8 & 3) / plan.cw;
-    const bool colok2 = col2 < plan.cpr;
-    const uint32_t chunk2 = uint32_t(trow2 * plan.cpr + col2) * 512u;
+    const int row2 = g8 >> 2, c2 = g8 & 3;
+    const bool colok2 = c2 < ncols;
+    const uint32_t chunk2 = uint32_t(row2) * 2048u + uint32_t(c2) * 512u + uint32_t(lq) * 128u;
     const uint32_t key2 = uint32_t(2 * lq + (g8 & 1));
-    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t smem_base = smem_u32(stage0);
     const float delta = tie_delta_kernel(uint32_t((r_begin + size_t(lane)) >> 44));       // 0, but not provably uniform (fpq_h16.cuh)
 
     // multipliers of this lane's 16 columns (pass 1): units u = 8a + l8, elements 32a + 4*l8 + k
@@ -300,35 +281,35 @@ __device__ __forceinline__ void rotate_tma_body(const float* __restrict__ x, con
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const int e0 = 32 * a + 4 * l8;
-        if (colok1) load_mult4(smooth, sm, size_t(col1) * 128 + e0, e0, ms[2 * a], ms[2 * a + 1]);
+        if (colok1) load_mult4(smooth, sm, size_t(col0 + g4) * 128 + e0, e0, ms[2 * a], ms[2 * a + 1]);
         else ms[2 * a] = ms[2 * a + 1] = 0ull;
     }
     uint64_t A[MOD ? 8 : 1], SH[MOD ? 8 : 1];
     size_t cur_b = ~size_t(0);
 
-    uint32_t s = 0, lap = 0;
+    uint32_t s = 0, phase = 0;
     for (size_t r = r_begin; r < r_end;) {
         size_t nr_ = r_end - r;
-        if (nr_ > size_t(RS)) nr_ = size_t(RS);
+        if (nr_ > 2) nr_ = 2;
         if (MOD && nr_ > left) nr_ = left;
         const int nr = int(nr_);
         if constexpr (MOD) {
-            if (batch != cur_b) {             // first tile of a batch: this lane's (scale + 1) and shift
+            if (batch != cur_b) {             // first step of a batch: this lane's (scale + 1) and shift
                 cur_b = batch;
                 if (colok1) {
 #pragma unroll
                     for (int a = 0; a < 4; ++a)
-                        load_mod4(mod, batch * row_elems + size_t(col1) * 128 + 32 * a + 4 * l8, A[2 * a], A[2 * a + 1], SH[2 * a], SH[2 * a + 1]);
+                        load_mod4(mod, batch * row_elems + size_t(col0 + g4) * 128 + 32 * a + 4 * l8, A[2 * a], A[2 * a + 1], SH[2 * a], SH[2 * a + 1]);
                 }
             }
         }
-        const uint32_t sb = smem_base + s * plan.stage_bytes;
-        mbar_wait(&full[s], lap & 1u);
+        const uint32_t sb = smem_base + s * ROT_WARP_STAGE_BYTES;
+        mbar_wait(&full[s], phase);
         // ---- pass 1 ----
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
-            if (colok1 && trow1 + sub * rps < nr) {
-                const uint32_t cb = sb + chunk1 + uint32_t(sub) * sub_bytes;
+            if (colok1 && sub < nr) {
+                const uint32_t cb = sb + chunk1 + uint32_t(sub) * 2048u;
                 uint64_t P[8];
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
@@ -352,17 +333,17 @@ __device__ __forceinline__ void rotate_tma_body(const float* __restrict__ x, con
 #pragma unroll
                 for (int a = 0; a < 4; ++a) {
                     const F2 p0 = unpk(P[2 * a]), p1 = unpk(P[2 * a + 1]);
-                    const uint32_t slot = uint32_t(l8 ^ s1) ^ uint32_t(2 * a);          // unit (a, c = l8) at c ^ (2a + s)
+                    const uint32_t slot = slot1 ^ uint32_t(2 * a);                      // unit (a, c = l8) at c ^ (2a + s)
                     asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(cb + uint32_t(a * 128) + slot * 16u), "f"(p0.lo), "f"(p0.hi), "f"(p1.lo), "f"(p1.hi) : "memory");
                 }
             }
         }
         __syncwarp();
         // ---- pass 2 ----
-        const bool valid = colok2 && trow2 < nr;
+        const bool valid = colok2 && row2 < nr;
         uint64_t Q[16];
         if (valid) {
-            const uint32_t cb = sb + chunk2 + uint32_t(lq) * 128u;
+            const uint32_t cb = sb + chunk2;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 uint4 u;
@@ -374,11 +355,11 @@ __device__ __forceinline__ void rotate_tma_body(const float* __restrict__ x, con
 #pragma unroll
             for (int i = 0; i < 16; ++i) Q[i] = 0ull;
         }
-        // the stage may be refilled (async proxy) once every warp has read its chunks: order this warp's generic-proxy
-        // accesses before the arrive
+        // the buffer is refilled by the async proxy: order this warp's generic-proxy accesses (reads and the in-place
+        // writes of pass 1) before the copy that lane 0 issues next
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
+        issue(s);                       // step k + 2 into the buffer step k just left
         reg_stage(Q, 2);                // index bit 2
         reg_stage(Q, 4);                // index bit 3
         reg_stage(Q, 8);                // index bit 4
@@ -386,7 +367,7 @@ __device__ __forceinline__ void rotate_tma_body(const float* __restrict__ x, con
         uint32_t w[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) w[i] = pack_h2_u64(Q[i]);
-        const size_t off = (r + size_t(trow2)) * row_elems + size_t(col2) * 128;
+        const size_t off = (r + size_t(row2)) * row_elems + size_t(col0 + c2) * 128;
         if (valid && rotated != nullptr) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) stg_stream(rotated + off + lq * 32 + q * 8, make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));
@@ -403,21 +384,24 @@ __device__ __forceinline__ void rotate_tma_body(const float* __restrict__ x, con
         }
         r += nr_;
         if constexpr (MOD) { left -= nr_; if (left == 0) { left = mod.rows_per_batch; ++batch; } }
-        if (++s == ROT_STAGES) { s = 0; ++lap; }
+        s ^= 1u;
+        if (s == 0) phase ^= 1u;
     }
 }
 
+// Registers: about 20 resident warps per SM at 96 registers; the adaLN variant keeps 32 more operands live and is
+// capped at 112 (18 warps).
 template <int FMT, bool QUANT>
-__global__ void __launch_bounds__(ROT_MAX_THREADS, 2) transform_rotate_quant_tma_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
-                                                                                       SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
-                                                                                       size_t n_rows, RotPlan plan, Modulate mod) {
-    rotate_tma_body<FMT, QUANT, false>(x, smooth, sm, out, rotated, n_rows, plan, mod);
+__global__ void __maxnreg__(96) transform_rotate_quant_stream_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
+                                                                    SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
+                                                                    size_t n_rows, int cpr, Modulate mod) {
+    rotate_stream_body<FMT, QUANT, false>(x, smooth, sm, out, rotated, n_rows, cpr, mod);
 }
 template <int FMT, bool QUANT>
-__global__ void __maxnreg__(112) modulate_transform_rotate_quant_tma_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
-                                                                            SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
-                                                                            size_t n_rows, RotPlan plan, Modulate mod) {
-    rotate_tma_body<FMT, QUANT, true>(x, smooth, sm, out, rotated, n_rows, plan, mod);
+__global__ void __maxnreg__(112) modulate_transform_rotate_quant_stream_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
+                                                                              SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
+                                                                              size_t n_rows, int cpr, Modulate mod) {
+    rotate_stream_body<FMT, QUANT, true>(x, smooth, sm, out, rotated, n_rows, cpr, mod);
 }
 
 // Weight side: one warp per (row, chunk); lane l holds elements 4l..4l+3 in fp64.  w_out may alias w (in place): every
@@ -467,51 +451,35 @@ __global__ void __launch_bounds__(256) transform_rotate_weight_kernel(const floa
 
 using namespace fpq;
 
-// Launch geometry of the streaming kernel for rows of `cpr` chunks; false if the row does not fit its tiles.
-static bool rot_plan(int cpr, RotPlan& best) {
-    bool found = false;
-    double best_util = 0.0;
-    for (int cw = 4; cw >= 1; cw >>= 1) {
-        const int wcols = (cpr + cw - 1) / cw;
-        if (wcols > ROT_MAX_WARPS) continue;
-        int wr = ROT_MAX_WARPS / wcols;                               // row groups: as many warps as fit, at most 8
-        if (wcols * wr > 8 && wr > 1) wr = 8 / wcols > 0 ? 8 / wcols : 1;
-        for (; wr >= 1; --wr) {
-            const int rs = wr * 2 * (4 / cw);
-            const size_t stage = size_t(rs) * cpr * 512;
-            if (stage * ROT_STAGES + 2 * ROT_STAGES * sizeof(uint64_t) > 110 * 1024) continue;      // two CTAs per SM
-            const double util = double(cpr) / double(wcols * cw);
-            if (!found || util > best_util + 1e-9) {
-                best = RotPlan{cpr, cw, wcols, wcols * wr, rs, unsigned(stage)};
-                best_util = util;
-                found = true;
-            }
-            break;
-        }
-    }
-    return found;
+// Launch geometry of the streaming kernel: warps per CTA (one per 4 chunk columns) and CTAs per SM (register budget:
+// about 20 warps, 18 with the adaLN operands).
+struct RotPlan { int warps; int ctas_per_sm; };
+static bool rot_plan(int cpr, bool mod, RotPlan& p) {
+    if (cpr < ROT_MIN_CPR || cpr > ROT_MAX_CPR) return false;
+    p.warps = (cpr + 3) / 4;
+    p.ctas_per_sm = (mod ? 18 : 20) / p.warps;
+    if (p.ctas_per_sm < 1) p.ctas_per_sm = 1;
+    return true;
 }
 
 template <int FMT, bool QUANT, bool MOD>
-static int launch_tma(const float* x, const float* smooth, const SignMask& sm, __half* o, __half* rot, size_t n_rows, const RotPlan& plan,
-                      const Modulate& m, cudaStream_t st) {
-    void (*kernel)(const float*, const float*, SignMask, __half*, __half*, size_t, RotPlan, Modulate);
-    if constexpr (MOD) kernel = modulate_transform_rotate_quant_tma_kernel<FMT, QUANT>;
-    else kernel = transform_rotate_quant_tma_kernel<FMT, QUANT>;
-    const size_t smem = size_t(ROT_STAGES) * plan.stage_bytes + 2 * ROT_STAGES * sizeof(uint64_t);
+static int launch_stream(const float* x, const float* smooth, const SignMask& sm, __half* o, __half* rot, size_t n_rows, int cpr,
+                         const RotPlan& plan, const Modulate& m, cudaStream_t st) {
+    void (*kernel)(const float*, const float*, SignMask, __half*, __half*, size_t, int, Modulate);
+    if constexpr (MOD) kernel = modulate_transform_rotate_quant_stream_kernel<FMT, QUANT>;
+    else kernel = transform_rotate_quant_stream_kernel<FMT, QUANT>;
+    const size_t smem = size_t(plan.warps) * ROT_WARP_SMEM;
     static bool attr_done[64] = {};                    // per instantiation and device
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_done[dev & 63]) {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024) != cudaSuccess ||
-            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared) != cudaSuccess)
-            return FPQ_ERR_CUDA;
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (ROT_MAX_CPR + 3) / 4 * ROT_WARP_SMEM) != cudaSuccess) return FPQ_ERR_CUDA;
         attr_done[dev & 63] = true;
     }
-    const size_t tiles = (n_rows + plan.rs - 1) / plan.rs;
-    const size_t cap = size_t(sm_count()) * 2;
-    const unsigned grid = unsigned(tiles < cap ? tiles : cap);
-    launch_pdl(kernel, grid, unsigned(32 * (plan.n_warps + 1)), smem, st, x, smooth, sm, o, rot, n_rows, plan, m);
+    const size_t steps = (n_rows + 1) / 2;
+    const size_t cap = size_t(sm_count()) * plan.ctas_per_sm;
+    const unsigned grid = unsigned(steps < cap ? steps : cap);
+    launch_pdl(kernel, grid, unsigned(32 * plan.warps), smem, st, x, smooth, sm, o, rot, n_rows, cpr, m);
     return finish_launch();
 }
 
@@ -538,10 +506,10 @@ static int launch_fmt(const float* x, const Modulate* mod, const float* smooth, 
                       cudaStream_t st) {
     const Modulate m = mod ? *mod : Modulate{nullptr, nullptr, 1, 1.0f};
     RotPlan plan;
-    const bool big = n_rows * size_t(cpr) > size_t(g_tun.rot_small_max_chunks) && rot_plan(cpr, plan) &&
-                     (mod == nullptr || mod->rows_per_batch >= size_t(plan.rs)) &&
+    const bool big = n_rows * size_t(cpr) > size_t(g_tun.rot_small_max_chunks) && rot_plan(cpr, mod != nullptr, plan) &&
+                     (mod == nullptr || mod->rows_per_batch >= 2) &&
                      ((reinterpret_cast<uintptr_t>(o) | reinterpret_cast<uintptr_t>(rot)) & 15) == 0;      // 128-bit stores
-    if (big) return mod ? launch_tma<FMT, QUANT, true>(x, smooth, sm, o, rot, n_rows, plan, m, st) : launch_tma<FMT, QUANT, false>(x, smooth, sm, o, rot, n_rows, plan, m, st);
+    if (big) return mod ? launch_stream<FMT, QUANT, true>(x, smooth, sm, o, rot, n_rows, cpr, plan, m, st) : launch_stream<FMT, QUANT, false>(x, smooth, sm, o, rot, n_rows, cpr, plan, m, st);
     return mod ? launch_small<FMT, QUANT, true>(x, smooth, sm, o, rot, n_rows, cpr, m, st) : launch_small<FMT, QUANT, false>(x, smooth, sm, o, rot, n_rows, cpr, m, st);
 }
 
@@ -573,14 +541,13 @@ static int launch_rotate_quant(const float* x, const Modulate* mod, const float*
     }
 }
 
-// Introspection for tests/rotate_layout_model.py (the host-side model of the streaming kernel's shared-memory
-// choreography must plan exactly like the launcher): plan[6] = {cw, wcols, n_warps, rs, stage_bytes, stages}.
-extern "C" int fpq_rotate_plan(int chunks_per_row, int* plan_host) {
+// Introspection for the CPU tests (tests/rotate_layout_model.py mirrors the launcher): plan[2] = {warps per CTA, CTAs per SM}.
+extern "C" int fpq_rotate_plan(int chunks_per_row, int with_modulate, int* plan_host) {
     RotPlan p;
     if (plan_host == nullptr || chunks_per_row < 1) return FPQ_ERR_ARG;
-    if (!rot_plan(chunks_per_row, p)) return FPQ_ERR_UNSUPPORTED;
-    plan_host[0] = p.cw; plan_host[1] = p.wcols; plan_host[2] = p.n_warps; plan_host[3] = p.rs; plan_host[4] = int(p.stage_bytes);
-    plan_host[5] = ROT_STAGES;
+    if (!rot_plan(chunks_per_row, with_modulate != 0, p)) return FPQ_ERR_UNSUPPORTED;
+    plan_host[0] = p.warps;
+    plan_host[1] = p.ctas_per_sm;
     return FPQ_OK;
 }
 

@@ -171,12 +171,12 @@ FPQ_API int fpq_modulate_transform_rotate_quant(const float *x, const float *sca
                                         size_t n_rows, size_t n_cols, int format, int flags, void *stream);
 
 /*
- * Launch plan of the streaming rotate kernel for rows of `chunks_per_row` 128-element chunks (host-only query, no CUDA
- * call; used by the CPU tests to keep tests/rotate_layout_model.py in step with the launcher):
- * plan_host[6] = {chunk columns per warp, warps across the columns, consumer warps, rows per tile, bytes per stage,
- * stages}.  FPQ_ERR_UNSUPPORTED when such rows only take the small-launch kernel.
+ * Launch plan of the streaming rotate kernel for rows of `chunks_per_row` 128-element chunks, without / with the adaLN
+ * modulate (host-only query, no CUDA call; the CPU tests use it to keep tests/rotate_layout_model.py in step with the
+ * launcher): plan_host[2] = {warps per CTA (one per 4 chunk columns), CTAs per SM}.  FPQ_ERR_UNSUPPORTED when such
+ * rows only take the small-launch kernel.
  */
-FPQ_API int fpq_rotate_plan(int chunks_per_row, int *plan_host);
+FPQ_API int fpq_rotate_plan(int chunks_per_row, int with_modulate, int *plan_host);
 
 /*
  * Weight side of the same transform (transform_model_utils.py:8-28, rotation_utils.py:129-154):

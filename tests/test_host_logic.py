@@ -86,9 +86,6 @@ def test_var_workload_shapes_and_bytes():
 # ---------------------------------------------------------------------------------------------
 # streaming rotate kernel: launch plan and shared-memory choreography (tests/rotate_layout_model.py)
 # ---------------------------------------------------------------------------------------------
-ROT_CPRS = [1, 2, 3, 4, 5, 7, 8, 12, 15, 16, 18, 20, 23, 32, 36]
-
-
 def test_rotate_plan_model_matches_the_launcher():
     """The Python mirror of rot_plan() plans exactly like the C++ launcher (fpq_rotate_plan is a host-only query)."""
     import ctypes
@@ -96,65 +93,57 @@ def test_rotate_plan_model_matches_the_launcher():
     from fpqvar_b200 import _lib as L
     lib = L.lib()
     for cpr in list(range(1, 80)) + [128, 1000]:
-        out = (ctypes.c_int * 6)()
-        rc = lib.fpq_rotate_plan(cpr, out)
-        want = M.rot_plan(cpr)
-        if want is None:
-            assert rc == L.FPQ_ERR_UNSUPPORTED, cpr
-            continue
-        assert rc == 0, cpr
-        assert list(out) == [want["cw"], want["wcols"], want["n_warps"], want["rs"], want["stage_bytes"], M.ROT_STAGES], cpr
-        assert want["n_warps"] <= M.ROT_MAX_WARPS and M.ROT_STAGES * want["stage_bytes"] + 48 <= 110 * 1024
-    assert M.rot_plan(15)["rs"] == 4 and M.rot_plan(15)["n_warps"] == 8       # VAR-d30: 2 CTAs x 8 consumer warps per SM
-    assert M.rot_plan(18)["cw"] == 2 and M.rot_plan(18)["n_warps"] == 9       # VAR-d36: no idle lane sets
+        for mod in (False, True):
+            out = (ctypes.c_int * 2)()
+            rc = lib.fpq_rotate_plan(cpr, int(mod), out)
+            want = M.rot_plan(cpr, mod)
+            if want is None:
+                assert rc == L.FPQ_ERR_UNSUPPORTED, cpr
+                continue
+            assert rc == 0 and tuple(out) == want, (cpr, mod)
+            assert want[0] * want[1] <= 20 or want[1] == 1
+    assert M.rot_plan(15) == (4, 5) and M.rot_plan(18) == (5, 4) and M.rot_plan(8) == (2, 10)     # VAR-d30 / d36 / d16
 
 
-@pytest.mark.parametrize("cpr", ROT_CPRS)
-def test_rotate_streaming_layout_covers_every_unit_without_bank_conflicts(cpr):
+@pytest.mark.parametrize("ncols,nr", [(4, 2), (3, 2), (1, 2), (4, 1), (2, 1)])
+def test_rotate_streaming_layout_covers_every_unit_without_bank_conflicts(ncols, nr):
     import rotate_layout_model as M
-    plan = M.rot_plan(cpr)
     seen1, seen2 = {}, {}
-    for warp in range(plan["n_warps"]):
-        for sub in range(2):
-            for ph in range(4):
-                accs = [M.pass1_accesses(plan, warp, lane, sub) for lane in range(8 * ph, 8 * ph + 8)]
-                for a in range(4):
-                    assert M.conflict_free([x[a][0] if x else None for x in accs]), ("pass-1 load", warp, sub, ph, a)
-                    assert M.conflict_free([x[a][1] if x else None for x in accs]), ("pass-1 store", warp, sub, ph, a)
-                for x in accs:
-                    for ld, st in (x or []):
-                        seen1[ld] = seen1.get(ld, 0) + 1
-                # in place: a chunk's swizzled stores stay inside the units its own 8 lanes loaded
-                for g in range(0, 8, 8):
-                    lds = {ld for x in accs[g:g + 8] if x for ld, _ in x}
-                    sts = {st for x in accs[g:g + 8] if x for _, st in x}
-                    assert lds == sts
-        for ph in range(4):
-            accs = [M.pass2_accesses(plan, warp, lane) for lane in range(8 * ph, 8 * ph + 8)]
-            for i in range(8):
-                assert M.conflict_free([x[i] if x else None for x in accs]), ("pass-2 load", warp, ph, i)
-            for x in accs:
-                for a in (x or []):
-                    seen2[a] = seen2.get(a, 0) + 1
-    n_units = plan["rs"] * cpr * 32
-    assert len(seen1) == n_units and set(seen1.values()) == {1}
-    assert len(seen2) == n_units and set(seen2.values()) == {1}
-    assert max(seen1) + 16 <= plan["stage_bytes"]
+    for sub in range(2):
+        for ph in range(4):                                   # a phase of pass 1 = the 8 lanes of one chunk
+            accs = [M.pass1_accesses(lane, sub, ncols, nr) for lane in range(8 * ph, 8 * ph + 8)]
+            for a in range(4):
+                assert M.conflict_free([x[a][0] if x else None for x in accs]), ("pass-1 load", sub, ph, a)
+                assert M.conflict_free([x[a][1] if x else None for x in accs]), ("pass-1 store", sub, ph, a)
+            lds = {ld for x in accs if x for ld, _ in x}
+            sts = {st for x in accs if x for _, st in x}
+            assert lds == sts                                 # in place: stores stay inside the chunk's own units
+            for ld in lds:
+                seen1[ld] = seen1.get(ld, 0) + 1
+    for ph in range(4):
+        accs = [M.pass2_accesses(lane, ncols, nr) for lane in range(8 * ph, 8 * ph + 8)]
+        for i in range(8):
+            assert M.conflict_free([x[i] if x else None for x in accs]), ("pass-2 load", ph, i)
+        for x in accs:
+            for a in (x or []):
+                seen2[a] = seen2.get(a, 0) + 1
+    want = {row * 2048 + col * 512 + u * 16 for row in range(nr) for col in range(ncols) for u in range(32)}
+    assert set(seen1) == want and set(seen1.values()) == {1}
+    assert set(seen2) == want and set(seen2.values()) == {1}
 
 
-@pytest.mark.parametrize("cpr", [1, 3, 8, 15, 18, 36])
-def test_rotate_streaming_two_pass_butterflies_are_the_hadamard_transform(cpr):
+@pytest.mark.parametrize("ncols,nr", [(4, 2), (3, 2), (4, 1), (1, 1)])
+def test_rotate_streaming_two_pass_butterflies_are_the_hadamard_transform(ncols, nr):
     """Pass 1 (bits 0,1,5,6, written back swizzled in place) + pass 2 (bits 2,3,4) == x * m @ H_128 on every chunk."""
     import rotate_layout_model as M
-    plan = M.rot_plan(cpr)
-    rng = np.random.default_rng(cpr)
-    tile = rng.standard_normal((plan["rs"], cpr * 128))
-    mult = rng.standard_normal(cpr * 128)
+    rng = np.random.default_rng(10 * ncols + nr)
+    tile = rng.standard_normal((nr, ncols * 128))
+    mult = rng.standard_normal(ncols * 128)
     h = np.array([[1.0]])
     for _ in range(7):
         h = np.block([[h, h], [h, -h]])
-    want = ((tile * mult).reshape(plan["rs"], cpr, 128) @ h).reshape(plan["rs"], -1)
-    got = M.simulate_tile(plan, tile, mult)
+    want = ((tile * mult).reshape(nr, ncols, 128) @ h).reshape(nr, -1)
+    got = M.simulate_step(tile, mult, ncols)
     assert not np.isnan(got).any()
     assert np.abs(got - want).max() <= 1e-11 * np.abs(want).max()
 
