@@ -51,12 +51,30 @@ def parse_args():
     ap.add_argument("--no-generation", action="store_true",
                     help="skip the images/sec leg (tools/var_generate.py: a full VAR generation pass around the hot path)")
     ap.add_argument("--gen-iters", type=int, default=3)
+    ap.add_argument("--no-reference-legs", action="store_true",
+                    help="skip reference_gpu_path / generation_reference_model (the unmodified reference from baseline/_ref on this GPU)")
+    ap.add_argument("--no-other-configs", action="store_true",
+                    help="skip the short device-resident runs of the other BASELINE configs (other_configs)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--sample-stages", type=int, default=0,
                     help="CPU legs only: restrict the bounded sample to the first N stages (0 = all; used by the CPU unit test)")
     ap.add_argument("--profile", action="store_true",
                     help="for ncu: one warm-up replay + the timed steps only (no roofline graphs, no e2e, no CPU baseline)")
     return ap.parse_args()
+
+
+def bench_config(hot, world):
+    """The `config` object of the JSON line; identical in both arms (--impl b200 / --impl reference)."""
+    calls = hot.calls()
+    step_bytes = sum(c.bytes for c in calls)
+    bits = 6 if hot.act_fmt in ("e2m3", "e3m2") else 4
+    return {
+        "workload": hot.name,
+        "desc": f"VAR-d{hot.depth} W{bits}A{bits} hot path: {len(calls)} activation fake-quant calls of one generation pass, B={hot.batch}/GPU "
+                f"({hot.elems_per_pass() / 1e9:.2f} G elements, {step_bytes / 1e9:.1f} GB algorithmic per GPU per step)",
+        "l2": "inputs/outputs rotate through 2 GiB/1 GiB/2 GiB/2 GiB arenas (>> 126 MB L2); no address is re-read within 1 GiB of traffic",
+        "launch": "one CUDA-graph replay per step", "parallelism": f"dp{world} (independent image batches, no data-path collective)",
+    }
 
 
 def load_peaks():
@@ -180,40 +198,31 @@ def cpu_baseline(hot, seconds, steps=None, warmup=1, stages=0):
     }, mean, len(times)
 
 
+def reference_cpu_leg(hot, steps, warmup, budget_s, stages=0):
+    """The reference's CPU implementation of the path on this box's host cores: its own torch functions from baseline/_ref
+    when the reference is installed (kind "reference"), else the C port of the oracle (kind "port")."""
+    from baseline import ref_env
+    if ref_env.available() and not stages:
+        from baseline import ref_legs
+        return ref_legs.cpu_reference_sample(hot, max_rows=2048, steps=steps, warmup=warmup, budget_s=budget_s)
+    return cpu_baseline(hot, 0.0, steps=steps, warmup=warmup, stages=stages)
+
+
 def run_reference(args, hot):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
     stages = args.sample_stages
-    if not stages and args.steps > 8:
-        # keep the whole run within a few minutes whatever K is: time the smallest half of the stages once and, if K
-        # steps of the full sample would not fit ~150 s, keep only as many (early) stages as do
-        import numpy as np
-        from oracle import port as P
-        n_st = len(hot.patch_nums)
-        calls, data = cpu_sample_inputs(hot, np, stages=n_st // 2)
-        smooth = np.ones(hot.width, np.float32)
-        global MOD_GAIN, MOD_SHIFT
-        MOD_GAIN = np.ones((2 * hot.batch, hot.width), np.float32)
-        MOD_SHIFT = np.zeros((2 * hot.batch, hot.width), np.float32)
-        t0 = time.perf_counter()
-        cpu_run_sample(calls, data, smooth, P)
-        t_half = time.perf_counter() - t0
-        per_byte = t_half / sum(c.bytes for c in calls)
-        full = [c for c in hot.calls(blocks=[0])]
-        budget = 150.0 / (args.steps + max(1, min(args.warmup, 2)))
-        acc = 0.0
-        for st in range(n_st):
-            acc += sum(c.bytes for c in full if c.stage == st) * per_byte
-            if acc > budget:
-                stages = max(3, st)
-                break
-    base, mean, n = cpu_baseline(hot, 0.0, steps=max(1, args.steps), warmup=max(1, min(args.warmup, 2)), stages=stages)
+    if stages:
+        base, mean, n = cpu_baseline(hot, 0.0, steps=steps, warmup=max(1, warmup), stages=stages)
+    else:
+        base, mean, n = reference_cpu_leg(hot, steps, max(1, warmup), budget_s=150.0)
     line = {
-        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": n,
-        "warmup": max(1, min(args.warmup, 2)), "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": mean * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32/f16", "data": "synthetic",
-        "config": {"workload": hot.name, "step": "bounded sample: " + base["sample"]},
+        "config": bench_config(hot, args.gpus),
         "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -310,6 +319,75 @@ def generation_leg(torch, dist, dev, hot, iters, rank, world):
         else:
             out[mode] = {"images_per_sec": world * hot.batch / (worst / 1e3), "ms_per_batch": worst,
                          "decode_ms_per_batch": r["decode_ms_per_batch"], "fpq_launches_per_batch": r["fpq_launches_per_batch"]}
+    return out
+
+
+def ncu_traffic(dom_key, bytes_per_avg_launch):
+    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed
+    `ncu --set full` capture (profiles/r2_traffic.json, written by tools/ncu_summary.py from the .ncu-rep), scaled from the
+    captured launch to the step's average launch by algorithmic bytes (traffic / algorithmic is what the capture measures)."""
+    path = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        table = json.load(f)
+    op, fmt, din, dout = dom_key
+    ent = table.get(f"{op}:{fmt}:{din}->{dout}")
+    if not ent:
+        return None
+    ratio = ent["dram_bytes"] / ent["algorithmic_bytes"]
+    return {"per_avg_launch": ratio * bytes_per_avg_launch, "captured_launch": ent, "ratio_dram_over_algorithmic": ratio}
+
+
+def reference_gpu_legs(torch, dev, hot, args):
+    """(reference_gpu_path, generation_reference_model): the UNMODIFIED reference from baseline/_ref on this GPU."""
+    from baseline import ref_env
+    if not ref_env.available():
+        why = {"unavailable": ref_env.why_unavailable()}
+        return why, why
+    gpu = gen = None
+    try:
+        from baseline import ref_legs
+        gpu = ref_legs.gpu_reference_step(hot, dev, iters=2)
+    except Exception as e:  # noqa: BLE001  (reported in the JSON line)
+        gpu = {"error": f"{type(e).__name__}: {e}"}
+    torch.cuda.empty_cache()
+    if not args.no_generation and hot.rotate_transform:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_model_generate", os.path.join(ROOT, "tools", "ref_model_generate.py"))
+        rg = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(rg)
+        ns = ref_env.load(str(dev))
+        res = 512 if hot.patch_nums[-1] == 32 else 256
+        bits = 6 if hot.act_fmt in ("e2m3", "e3m2") else 4
+        gen = {"unit": "images/s", "model": f"the reference's own VAR-d{hot.depth} {res}x{res} (build_vae_var, autoregressive_infer_cfg, fp16 autocast), "
+                                             f"B={hot.batch}, W{bits}A{bits}, random init", "harness": "tools/ref_model_generate.py"}
+        for mode in ("fp16", "reference", "dropin", "fused"):
+            try:
+                r = rg.measure(ns, dev, hot.depth, hot.batch, res, bits, mode, iters=2, warmup=1)
+                gen[mode] = {k: r[k] for k in ("images_per_sec", "ms_per_batch", "finite", "fpq_launches_per_batch")}
+                gen["galt_factors"] = r["galt_factors"]
+            except Exception as e:  # noqa: BLE001
+                gen[mode] = {"error": f"{type(e).__name__}: {e}"}
+            torch.cuda.empty_cache()
+    return gpu, gen
+
+
+def other_configs(args):
+    """BASELINE configs[1] and [3] (VAR-d16 plain, VAR-d36 W6A6 rotate): the device-resident step of each, measured by a
+    short child run of this script (its own process: fresh arenas, same timing code)."""
+    out = {}
+    for wl in ("var_d16_w4a4", "var_d36_w6a6_rot"):
+        if wl == args.workload:
+            continue
+        try:
+            r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", wl, "--steps", "10", "--warmup", "3", "--no-e2e", "--no-cpu",
+                                "--no-generation", "--no-reference-legs", "--no-other-configs"], capture_output=True, text=True, timeout=300)
+            d = json.loads(r.stdout.strip().splitlines()[-1])
+            out[wl] = {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "frac_of_measured_peak": d["value"] / d["roofline"]["peak"],
+                       "desc": d["config"]["desc"], "kernels": {k: v["GB/s"] for k, v in d["kernels"].items()}}
+        except Exception as e:  # noqa: BLE001
+            out[wl] = {"error": f"{type(e).__name__}: {e}"}
     return out
 
 
@@ -477,6 +555,15 @@ def main():
     if not args.no_generation:
         generation = generation_leg(torch, dist, dev, hot, args.gen_iters, rank, world)
 
+    # ---- the reference's own GPU path and its own model on this box (rank 0, N=1; outside every timed region above) ----
+    reference_gpu = generation_ref = other = None
+    if world == 1 and not args.no_reference_legs:
+        del replay, graph, big_graph, arenas, a_f32, a_f16, a_gelu, a_out, plan
+        torch.cuda.empty_cache()
+        reference_gpu, generation_ref = reference_gpu_legs(torch, dev, hot, args)
+    if world == 1 and not args.no_other_configs:
+        other = other_configs(args)
+
     # ---- gather (the only collective) --------------------------------------------------------
     if world > 1:
         keys = sorted(fam)
@@ -501,28 +588,22 @@ def main():
             base = {"group": "fake_quant_group", "signsplit": "signsplit_group"}[op]
             return f"{base}_h16_kernel<{fmt}> (f16->f16)" if packed else f"{base}_kernel<{din}->{dout},{fmt}>"
         kname = kernel_name(dom_key)
+        traffic = ncu_traffic(dom_key, dom_bytes / max(1, dom_launches))
         kernels = {kernel_name(k): {"GB/s": args.steps * b / t / 1e9, "launches_per_step": n_l, "share_of_step_bytes": b / step_bytes,
                                     "ms_per_step_alone": t / args.steps * 1e3} for k, (t, n_l, b) in fam.items()}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": t_dev / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32/f16", "data": "synthetic",
-            "config": {
-                "workload": hot.name,
-                "desc": f"VAR-d{hot.depth} W4A4 hot path: {len(calls)} activation fake-quant calls of one generation pass, B={hot.batch}/GPU "
-                        f"({hot.elems_per_pass() / 1e9:.2f} G elements, {step_bytes / 1e9:.1f} GB algorithmic per GPU per step)",
-                "l2": "inputs/outputs rotate through 2 GiB/1 GiB/2 GiB/2 GiB arenas (>> 126 MB L2); no address is re-read within 1 GiB of traffic",
-                "launch": "one CUDA-graph replay per step", "parallelism": f"dp{world} (independent image batches, no data-path collective)",
-            },
+            "config": bench_config(hot, world),
             "roofline": {
                 "bound": "hbm", "kernel": kname, "achieved": dom_gbs, "peak": peak,
-                "unit": "GB/s", "frac": dom_gbs / peak, "traffic": None, "peak_source": peak_src,
+                "unit": "GB/s", "frac": dom_gbs / peak, "traffic": traffic["per_avg_launch"] if traffic else None, "peak_source": peak_src,
                 "launches_per_step": dom_launches, "avg_launch_us": t_dom / args.steps / max(1, dom_launches) * 1e6,
                 "bytes_per_launch": dom_bytes / max(1, dom_launches),
                 "large_launches": {"min_bytes": 64 << 20, "achieved": big_gbs, "frac": big_gbs / peak, "n": len(big)},
                 "frac_of_nominal_8TBps": dom_gbs / 8000.0,
-                "traffic_largest_launch": {"dram_bytes": 745.3e6, "algorithmic_bytes": 786.4e6,
-                                           "source": "profiles/r1c_final_kernels_ncu.txt (ncu --set full, fc2 input 25600x7680; the tail of the writes is still in L2 when the kernel ends)"},
+                "traffic_detail": traffic,
             },
             "kernels": kernels,
             "images_per_sec_hot_path_only": world * hot.batch / (t_dev / args.steps),
@@ -533,9 +614,18 @@ def main():
             line["e2e"] = e2e
         if generation is not None:
             line["generation"] = generation
+        if reference_gpu is not None:
+            line["reference_gpu_path"] = reference_gpu
+        if generation_ref is not None:
+            line["generation_reference_model"] = generation_ref
+        if other is not None:
+            line["other_configs"] = other
         if world == 1 and not args.no_cpu:
-            base, _, _ = cpu_baseline(hot, args.cpu_seconds)
+            base, _, _ = reference_cpu_leg(hot, 1, 1, budget_s=2 * args.cpu_seconds)
             line["cpu_baseline"] = base
+            if base["kind"] != "port":
+                port, _, _ = cpu_baseline(hot, args.cpu_seconds)
+                line["cpu_port"] = port
             line["config1"] = config1_extra(torch, lib, dev, side)
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -61,6 +61,7 @@ struct Tunables {
     int pdl = 1;                               // programmatic dependent launch on (0: plain stream-ordered launches)
     int row_v = 0;                             // values-per-thread of the per-token kernels: 0 = chosen by row_reg_vectors, else 1 | 2 | 4
     long long rot_small_max_chunks = 24576;    // rotate launches up to this many 128-chunks take the small-launch kernel
+    int smem_kb = 0;                           // shared-memory carveout (KB per SM) every activation kernel asks for; 0 = leave it to the driver
 };
 extern Tunables g_tun;
 // symmetric fake quant, one translation unit per tie rule (fpq_sym_k.cu / fpq_sym_a.cu)
@@ -125,16 +126,18 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 
-// Every activation kernel asks for the same L1 / shared-memory split (the largest shared-memory carveout): the streaming
-// rotate kernel needs it, the others stream with L1::no_allocate loads and lose nothing -- and an SM only changes its
-// split when it is idle, so kernels that alternate between two splits (rotate -> group -> rotate -> sign-split ... in a
-// VAR pass) cannot overlap their tails and pay a drain per launch (measured: 28.1 ms instead of 24.7 ms per step when
-// only the rotate kernel asked for it).  Set once per (kernel, device); defined in fpq_grid.cu.
-void prefer_max_smem(const void* kernel);
+// Every activation kernel asks for the SAME L1 / shared-memory split (tunable smem_kb): an SM only changes its split when
+// it is idle, so kernels that alternate between two splits (rotate -> group -> rotate -> sign-split ... in a VAR pass)
+// cannot overlap their tails and pay a drain per launch (measured: 28.1 ms instead of 24.7 ms per step when only the
+// streaming rotate kernel asked for shared memory).  The split is a trade: the streaming rotate kernel keeps its bytes in
+// flight in shared memory, the register-tile kernels keep theirs in L1 lines (a pending ld.global holds a line of the L1
+// data array even with L1::no_allocate), so shrinking L1 to the minimum costs them a quarter of their bandwidth
+// (6.4 -> 4.8 TB/s with the 228 KB carveout).  Set once per (kernel, device, value); defined in fpq_grid.cu.
+void prefer_carveout(const void* kernel);
 
 template <typename... KArgs, typename... Args>
 static inline void launch_pdl(void (*kernel)(KArgs...), unsigned grid, unsigned block, size_t smem, cudaStream_t st, Args... args) {
-    prefer_max_smem(reinterpret_cast<const void*>(kernel));
+    prefer_carveout(reinterpret_cast<const void*>(kernel));
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(block);

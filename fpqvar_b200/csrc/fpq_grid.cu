@@ -95,19 +95,26 @@ int finish_launch() {
 
 Tunables g_tun;
 
-void prefer_max_smem(const void* kernel) {
-    // open-addressed set of (kernel, device) pairs that already carry the attribute; a lost race only repeats the call
+void prefer_carveout(const void* kernel) {
+    // open-addressed set of (kernel, device) pairs that already carry the attribute for the current value of the tunable;
+    // a lost race only repeats the call
     constexpr int N = 1024;
     static const void* seen_fn[N];
     static int seen_dev[N];
+    static int seen_kb[N];
+    const int kb = g_tun.smem_kb;
+    if (kb <= 0) return;
     int dev = 0;
     cudaGetDevice(&dev);
     unsigned h = unsigned((reinterpret_cast<uintptr_t>(kernel) >> 4) * 2654435761u + unsigned(dev) * 40503u) % N;
     for (int probe = 0; probe < N; ++probe, h = (h + 1) % N) {
-        if (seen_fn[h] == kernel && seen_dev[h] == dev) return;
-        if (seen_fn[h] == nullptr) {
-            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        const bool mine = seen_fn[h] == kernel && seen_dev[h] == dev;
+        if (mine && seen_kb[h] == kb) return;
+        if (mine || seen_fn[h] == nullptr) {
+            const int pct = kb >= 228 ? 100 : (kb * 100 + 227) / 228;
+            cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
             seen_dev[h] = dev;
+            seen_kb[h] = kb;
             seen_fn[h] = kernel;
             return;
         }
@@ -141,6 +148,11 @@ extern "C" int fpq_set_tunable(const char* name, long long value) {
         return FPQ_OK;
     }
     if (strcmp(name, "rot_small_max_chunks") == 0) { g_tun.rot_small_max_chunks = value; return FPQ_OK; }
+    if (strcmp(name, "smem_kb") == 0) {
+        if (value < 0 || value > 228) return FPQ_ERR_ARG;
+        g_tun.smem_kb = int(value);
+        return FPQ_OK;
+    }
     return FPQ_ERR_ARG;
 }
 

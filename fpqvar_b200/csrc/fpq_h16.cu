@@ -164,7 +164,7 @@ __device__ __forceinline__ int split_quant_tile_h16(uint32_t (&p)[NW], float& sn
         sp = rnd_in<__half>(__fdiv_rn(ap, SF::POS::VMAX));
         return 1;
     }
-    const SplitK k = make_splitk(sn, nbits == 0u ? 0.0f : rcp_rn_normal(sn), sp, pbits == 0u ? 0.0f : rcp_rn_normal(sp));
+    const SplitK k = make_splitk<typename SF::NEG, typename SF::POS>(sn, nbits == 0u ? 0.0f : rcp_rn_normal(sn), sp, pbits == 0u ? 0.0f : rcp_rn_normal(sp));
 #pragma unroll
     for (int i = 0; i < NW; ++i) p[i] = split_pair_h16<typename SF::NEG, typename SF::POS>(p[i], k, delta);
     return 0;
@@ -320,7 +320,7 @@ __global__ void selftest_f16_flow_kernel(unsigned long long* result) {
         } else {
             using SF = SplitH16<CODE - 16>;
             // the other side's scale does not influence an element: use the same s on both sides
-            got = split_pair_h16<typename SF::NEG, typename SF::POS>(x2, make_splitk(s, r, s, r), delta);
+            got = split_pair_h16<typename SF::NEG, typename SF::POS>(x2, make_splitk<typename SF::NEG, typename SF::POS>(s, r, s, r), delta);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const float xv = h ? -x : x;

@@ -106,7 +106,11 @@ template <class HG> struct Magic {
 // PRE: e1m2 (uniform, step 1/4 up to 1.75) is not a hardware format, but HALF of it is the uniform low end of e2m3
 // (step 1/8 up to 0.875): the group's reciprocal scale is halved and its scale doubled, both exact.  The doubled
 // scale must stay a finite fp16 number: S_MAX_BITS bounds the "regular" scales of the format.
+#ifndef FPQ_HWCVT
+#define FPQ_HWCVT 0          // 1: use the conversion hardware (measured: slower, see the header comment); 0: magic-number FFMA
+#endif
 template <class HG> struct HwCvt { static constexpr bool OK = false; static constexpr float PRE = 1.0f; static constexpr uint32_t S_MAX_BITS = 0x7BFFu; };
+#if FPQ_HWCVT
 template <> struct HwCvt<HG_E2M1> {
     static constexpr bool OK = true;
     static constexpr float PRE = 1.0f;
@@ -143,6 +147,8 @@ template <> struct HwCvt<HG_E1M2> {
     static constexpr uint32_t S_MAX_BITS = 0x77FFu;          // 2 * s stays finite
     static __device__ __forceinline__ uint32_t round_trip(float w0, float w1) { return HwCvt<HG_E2M3>::round_trip(w0, w1); }
 };
+
+#endif
 
 // Any other half grid: q = R_K(w) by a magic-number FFMA, as packed fp32.
 __device__ __forceinline__ uint64_t round_pair_magic(float w0, float w1, float em, float sc) {
@@ -308,6 +314,7 @@ static __device__ __noinline__ void literal_split_nan_group_h16(const __half* sr
 //                   fp16 value reaches or crosses a midpoint (midpoints are fp16 numbers).  The FMA rounds once.
 //                   A non-uniform negative grid (afpq: e2m1 on both sides) goes through the conversion hardware too.
 // A lane of the wrong side computes garbage (possibly inf / NaN) that the select discards.
+#if FPQ_HWCVT
 template <class NEG> struct UniformNeg {
     // NEG uniform <=> all of its values lie in its own subnormal region or first binade with the same step
     static constexpr bool OK = (NEG::M - NEG::EMIN == 2 && NEG::VNUM * 4 == 7 * NEG::VDEN) || (NEG::M == NEG::EMIN);
@@ -319,6 +326,7 @@ struct SplitK {
     uint64_t rn2, rp2;          // RN(1/s) of each side as packed fp32 pairs (0 for a side without elements)
     uint32_t snh2, sph2;        // the two scales as fp16 pairs
 };
+template <class NEG, class POS>
 __device__ __forceinline__ SplitK make_splitk(float sn, float rn, float sp, float rp) {
     SplitK k;
     k.rn2 = pk(rn, rn);
@@ -352,5 +360,63 @@ template <class NEG, class POS>
 __device__ __forceinline__ uint32_t split_pair_h16(uint32_t x2, const SplitK& k, float delta) {
     return split_pair_h16_w<NEG, POS>(widen_h2(x2), x2, k, delta);
 }
+
+#else
+// (default build) Per-element constants picked with integer multiply-adds on the FMA pipe (ncu r1b: the ALU pipe, where
+// FSEL / LOP3 / FMNMX / F2FP live, is the busy one; measured 5.40 -> 6.15 TB/s against LOP3 selects).  Sides with a
+// UNIFORM negative grid (e1m2: step 1/4 up to 1.75; int: step 1 up to 32) share the positive side's rounding constants:
+// the negative side is rescaled by the power of two K that maps its step onto the positive format's subnormal step
+// 2^(EMIN-M) (rn' = rn*K, sn' = sn/K, both exact), and p = 2^exponent(max(w, 2^EMIN)) is taken WITHOUT the absolute
+// value, so every negative w gets the constant p = 2^EMIN -- exactly the uniform grid.
+template <class NEG, class POS> struct SplitScale {
+    static constexpr bool UNIFORM_NEG = (NEG::M - NEG::EMIN == 2 && NEG::VNUM * 4 == 7 * NEG::VDEN) || (NEG::M == NEG::EMIN);
+    static constexpr float K = UNIFORM_NEG ? (Magic<POS>::EM / float(1u << POS::M)) / (Magic<NEG>::EM / float(1u << NEG::M)) : 1.0f;
+};
+struct SplitK {
+    int rp, rd, sp, sd;          // bit patterns: positive-side constant and (positive - negative) difference, for r and s
+};
+template <class NEG, class POS>
+__device__ __forceinline__ SplitK make_splitk(float sn, float rn, float sp, float rp) {
+    constexpr float K = SplitScale<NEG, POS>::K;
+    SplitK k;
+    k.rp = __float_as_int(rp);
+    k.rd = __float_as_int(rp) - __float_as_int(rn * K);
+    k.sp = __float_as_int(sp);
+    k.sd = __float_as_int(sp) - __float_as_int(sn * (1.0f / K));
+    return k;
+}
+// pos for m = 0, neg for m = -1
+__device__ __forceinline__ float sel_imad(int m, int pos, int pos_minus_neg) {
+    int d;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(m), "r"(pos_minus_neg), "r"(pos));
+    return __int_as_float(d);
+}
+template <class NEG, class POS>
+__device__ __forceinline__ uint32_t split_pair_h16_w(uint64_t xf2, uint32_t x2, const SplitK& k, float delta) {
+    const F2 x = unpk(xf2);
+    const int m0 = __float_as_int(x.lo) >> 31, m1 = __float_as_int(x.hi) >> 31;      // -1: negative side
+    const float r0 = sel_imad(m0, k.rp, k.rd), r1 = sel_imad(m1, k.rp, k.rd);
+    const float s0 = sel_imad(m0, k.sp, k.sd), s1 = sel_imad(m1, k.sp, k.sd);
+    const uint32_t v2 = pack_h2_u64(fmul2(xf2, pk(r0, r1)));
+    const float w0 = fhadd(uint16_t(v2 & 0xffffu), delta);
+    const float w1 = fhadd(uint16_t(v2 >> 16), delta);
+    uint64_t q;
+    if constexpr (SplitScale<NEG, POS>::UNIFORM_NEG) {
+        const float p0 = __uint_as_float(__float_as_uint(fmaxf(w0, Magic<POS>::EM)) & 0x7F800000u);     // signed max
+        const float p1 = __uint_as_float(__float_as_uint(fmaxf(w1, Magic<POS>::EM)) & 0x7F800000u);
+        const uint64_t p = pk(p0, p1), w = pk(w0, w1);
+        const uint64_t y = ffma2(p, pk(Magic<POS>::SC, Magic<POS>::SC), w);
+        q = ffma2(p, pk(-Magic<POS>::SC, -Magic<POS>::SC), y);
+    } else {
+        static_assert(Magic<NEG>::EM == Magic<POS>::EM && Magic<NEG>::SC == Magic<POS>::SC, "non-uniform negative grids must share the positive format");
+        q = round_pair_magic(w0, w1, Magic<POS>::EM, Magic<POS>::SC);
+    }
+    return pack_h2_u64(fmul2(q, pk(s0, s1)));
+}
+template <class NEG, class POS>
+__device__ __forceinline__ uint32_t split_pair_h16(uint32_t x2, const SplitK& k, float delta) {
+    return split_pair_h16_w<NEG, POS>(widen_h2(x2), x2, k, delta);
+}
+#endif
 
 }  // namespace fpq

@@ -210,6 +210,124 @@ constexpr int ROT_MIN_CPR = 4, ROT_MAX_CPR = 36;       // rows the streaming ker
 constexpr int ROT_WARP_STAGE_BYTES = 4096;             // 2 rows x 4 chunks x 512 B
 constexpr int ROT_WARP_SMEM = 2 * ROT_WARP_STAGE_BYTES + 16;      // + the two mbarriers
 
+// Loop bookkeeping is kept to a minimum (ncu r2: the first version of this body spent 10 of its 27 instructions per
+// element on 64-bit row arithmetic, re-derived shared-memory addresses and branches): rows are 32-bit counters relative to
+// the CTA's first row, global pointers are advanced instead of recomputed, every shared-memory address is a lane constant
+// plus an immediate, and the two buffers are two copies of the step body with compile-time offsets.
+template <int FMT, bool QUANT, bool MOD>
+struct RotStream {
+    // lane constants
+    uint32_t p1;            // pass 1: this lane's first unit of its chunk (row 0, buffer 0)
+    uint32_t q1[4];         // pass 1: swizzled store addresses of its four units
+    uint32_t a2[8];         // pass 2: swizzled load addresses of its eight units (buffer 0)
+    bool colok1, colok2;
+    int row2;
+    int lq;
+    uint64_t ms[8];
+    uint64_t A[MOD ? 8 : 1], SH[MOD ? 8 : 1];
+    float delta;
+    // MOD: adaLN operands of the batch the next row belongs to
+    const float* pa;
+    const float* psh;
+    uint32_t left, rpb, row_elems;
+    bool reload;
+    // output
+    __half* op;             // this lane's 32 output elements of row `row2` of the current step
+    __half* rp;             // same in `rotated` (or nullptr)
+
+    __device__ __forceinline__ void pass1(uint32_t buf_off, int nr) {
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+            if (sub < nr) {
+                if constexpr (MOD) {
+                    if (reload) {                                 // first row of a batch: this lane's (scale + 1) and shift
+                        reload = false;
+                        if (colok1) {
+                            Modulate m{pa, psh, 0, mod_one};
+#pragma unroll
+                            for (int a = 0; a < 4; ++a) load_mod4(m, size_t(32 * a), A[2 * a], A[2 * a + 1], SH[2 * a], SH[2 * a + 1]);
+                        }
+                    }
+                    if (--left == 0) { left = rpb; pa += row_elems; psh += row_elems; reload = true; }
+                }
+                if (colok1) {
+                    const uint32_t off = buf_off + uint32_t(sub) * 2048u;
+                    uint64_t P[8];
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        uint4 u;
+                        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(p1 + off + uint32_t(a * 128)));
+                        P[2 * a] = (uint64_t(u.y) << 32) | u.x;
+                        P[2 * a + 1] = (uint64_t(u.w) << 32) | u.z;
+                    }
+                    if constexpr (MOD) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) P[i] = modulate2(P[i], A[i], SH[i]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) P[i] = fmul2(P[i], ms[i]);
+                    pair_stage(P);          // index bit 0
+                    reg_stage(P, 1);        // index bit 1
+                    reg_stage(P, 2);        // index bit 5
+                    reg_stage(P, 4);        // index bit 6
+                    // in place: the 8 lanes of the chunk have all read their units before any of them overwrites one
+                    __syncwarp(lanes8);
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const F2 p0 = unpk(P[2 * a]), p1v = unpk(P[2 * a + 1]);
+                        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(q1[a] + off), "f"(p0.lo), "f"(p0.hi), "f"(p1v.lo), "f"(p1v.hi) : "memory");
+                    }
+                }
+            }
+        }
+    }
+    float mod_one;
+    uint32_t lanes8;
+
+    // returns after the loads of pass 2 (the caller then hands the buffer back to the producer) -- Q holds the values
+    __device__ __forceinline__ void pass2_load(uint32_t buf_off, bool valid, uint64_t (&Q)[16]) {
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                uint4 u;
+                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(a2[i] + buf_off));
+                Q[2 * i] = (uint64_t(u.y) << 32) | u.x;
+                Q[2 * i + 1] = (uint64_t(u.w) << 32) | u.z;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) Q[i] = 0ull;
+        }
+    }
+    __device__ __forceinline__ void pass2_finish(bool valid, uint64_t (&Q)[16]) {
+        reg_stage(Q, 2);                // index bit 2
+        reg_stage(Q, 4);                // index bit 3
+        reg_stage(Q, 8);                // index bit 4
+        // rounded to fp16: the fp16 GEMM output of the reference.  Lane l' holds elements 32*l' .. 32*l' + 31 in order.
+        uint32_t w[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) w[i] = pack_h2_u64(Q[i]);
+        if (rp != nullptr) {
+            if (valid) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) stg_stream(rp + q * 8, make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));
+            }
+            rp += 2 * size_t(row_elems);
+        }
+        bool ok = true;
+        float sc = 0.0f;
+        if constexpr (QUANT) ok = sym_quant_tile_h16<FMT, 4, 16>(w, sc, delta);
+        if (valid) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) stg_stream(op + q * 8, make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));
+            // irregular scale (zero / subnormal / inf / NaN): `out` now holds this lane's rotated values;
+            // quantize them in place with the literal reference sequence
+            if (!ok) literal_sym_h16(op - lq * 32, op - lq * 32, lq, 4, 32, 1, sc, SymFmt<FMT>::GT);
+        }
+        op += 2 * size_t(row_elems);
+    }
+};
+
 template <int FMT, bool QUANT, bool MOD>
 __device__ __forceinline__ void rotate_stream_body(const float* __restrict__ x, const float* __restrict__ smooth,
                                                    SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
@@ -227,170 +345,109 @@ __device__ __forceinline__ void rotate_stream_body(const float* __restrict__ x, 
     pdl_launch_dependents();
     __syncwarp();
 
-    // this CTA's rows: [r_begin, r_end), sizes differ by at most one row over the grid
+    // this CTA's rows: [r_begin, r_begin + n_mine), sizes differ by at most one row over the grid (the launcher keeps
+    // n_mine below 2^31)
     const size_t per = n_rows / gridDim.x, rem = n_rows % gridDim.x;
     const size_t r_begin = size_t(blockIdx.x) * per + (blockIdx.x < rem ? blockIdx.x : rem);
-    const size_t r_end = r_begin + per + (blockIdx.x < rem ? 1 : 0);
-    const size_t row_elems = size_t(cpr) * 128;
+    const uint32_t n_mine = uint32_t(per) + (blockIdx.x < rem ? 1u : 0u);
+    const uint32_t row_elems = uint32_t(cpr) * 128u;
     const int col0 = 4 * warp;                                          // first chunk column of this warp
     const int ncols = cpr - col0 < 4 ? cpr - col0 : 4;                  // its columns that exist (the last warp may own fewer)
-    // MOD: a step never straddles two batches (its adaLN operands are per batch); `left` = rows to the end of the batch
-    size_t batch = 0, left = ~size_t(0);
+
+    RotStream<FMT, QUANT, MOD> st;
+    const uint32_t smem_base = smem_u32(stage0);
+    // pass 1: 8 lanes per chunk; sub-iteration = row, g4 = column within the warp
+    const int g4 = lane >> 3, l8 = lane & 7;
+    st.colok1 = g4 < ncols;
+    st.lanes8 = 0xFFu << (8 * g4);
+    st.p1 = smem_base + uint32_t(g4) * 512u + uint32_t(l8) * 16u;
+#pragma unroll
+    for (int a = 0; a < 4; ++a)                                         // unit (a, c = l8) at slot c ^ (2a + s), s = column parity
+        st.q1[a] = smem_base + uint32_t(g4) * 512u + uint32_t(a) * 128u + ((uint32_t(l8 ^ (g4 & 1)) ^ uint32_t(2 * a)) << 4);
+    // pass 2: 4 lanes per chunk, lane set g8 = 4 * row + column
+    const int g8 = lane >> 2, c2 = g8 & 3;
+    st.lq = lane & 3;
+    st.row2 = g8 >> 2;
+    st.colok2 = c2 < ncols;
+    {
+        const uint32_t chunk2 = smem_base + uint32_t(st.row2) * 2048u + uint32_t(c2) * 512u + uint32_t(st.lq) * 128u;
+        const uint32_t key2 = uint32_t(2 * st.lq + (g8 & 1));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) st.a2[i] = chunk2 + ((uint32_t(i) ^ key2) << 4);
+    }
+    st.delta = tie_delta_kernel(uint32_t((r_begin + size_t(lane)) >> 44));       // 0, but not provably uniform (fpq_h16.cuh)
+    st.row_elems = row_elems;
+    st.mod_one = mod.one;
+    st.op = out + (r_begin + size_t(st.row2)) * row_elems + size_t(col0 + c2) * 128 + st.lq * 32;
+    st.rp = rotated != nullptr ? rotated + (r_begin + size_t(st.row2)) * row_elems + size_t(col0 + c2) * 128 + st.lq * 32 : nullptr;
+    st.pa = st.psh = nullptr;
+    st.left = st.rpb = 1;
+    st.reload = false;
     if constexpr (MOD) {
-        batch = r_begin / mod.rows_per_batch;
-        left = mod.rows_per_batch - (r_begin - batch * mod.rows_per_batch);
+        const size_t batch = r_begin / mod.rows_per_batch;
+        st.rpb = uint32_t(mod.rows_per_batch);
+        st.left = st.rpb - uint32_t(r_begin - batch * mod.rows_per_batch);
+        const size_t lane_off = batch * row_elems + size_t(col0 + (st.colok1 ? g4 : 0)) * 128 + 4 * l8;
+        st.pa = mod.scale + lane_off;
+        st.psh = mod.shift + lane_off;
+        st.reload = true;
     }
     // Nothing is read from global memory before pdl_wait(): x comes from the previous kernel, and `smooth` may too.
     pdl_wait();
 
     // ---- producer side (lane 0): the copy of step k + 2 is issued when step k has left its buffer ----
-    size_t r_issue = r_begin, left_issue = left;
+    const unsigned char* gsrc = reinterpret_cast<const unsigned char*>(x + r_begin * row_elems + size_t(col0) * 128);
+    const uint32_t row_bytes = uint32_t(ncols) * 512u, row_stride_b = row_elems * 4u;
+    uint32_t issued = 0;
     auto issue = [&](uint32_t s) {
-        if (r_issue >= r_end) return;
-        size_t nr = r_end - r_issue;
-        if (nr > 2) nr = 2;
-        if (MOD && nr > left_issue) nr = left_issue;
-        if (lane == 0) {
-            const uint32_t row_bytes = uint32_t(ncols) * 512u;
-            mbar_arrive_expect_tx(&full[s], uint32_t(nr) * row_bytes);
-            for (size_t j = 0; j < nr; ++j)
-                bulk_load(stage0 + s * ROT_WARP_STAGE_BYTES + j * 2048, x + (r_issue + j) * row_elems + size_t(col0) * 128, row_bytes, &full[s]);
+        if (issued < n_mine) {
+            if (lane == 0) {
+                const bool two = n_mine - issued >= 2u;
+                mbar_arrive_expect_tx(&full[s], two ? 2u * row_bytes : row_bytes);
+                bulk_load(stage0 + s * ROT_WARP_STAGE_BYTES, gsrc, row_bytes, &full[s]);
+                if (two) bulk_load(stage0 + s * ROT_WARP_STAGE_BYTES + 2048, gsrc + row_stride_b, row_bytes, &full[s]);
+            }
+            gsrc += 2 * size_t(row_stride_b);
+            issued += 2u;
         }
-        r_issue += nr;
-        if constexpr (MOD) { left_issue -= nr; if (left_issue == 0) left_issue = mod.rows_per_batch; }
     };
     issue(0);
     issue(1);
 
-    // pass 1: 8 lanes per chunk; sub-iteration `sub` = row, g4 = column within the warp
-    const int g4 = lane >> 3, l8 = lane & 7;
-    const bool colok1 = g4 < ncols;
-    const uint32_t chunk1 = uint32_t(g4) * 512u;                        // + 2048 for the second row
-    const uint32_t slot1 = uint32_t(l8 ^ (g4 & 1));                     // pass-1 store slot before the per-unit ^ 2a
-    // pass 2: 4 lanes per chunk, lane set g8 = 4 * row + column
-    const int g8 = lane >> 2, lq = lane & 3;
-    const int row2 = g8 >> 2, c2 = g8 & 3;
-    const bool colok2 = c2 < ncols;
-    const uint32_t chunk2 = uint32_t(row2) * 2048u + uint32_t(c2) * 512u + uint32_t(lq) * 128u;
-    const uint32_t key2 = uint32_t(2 * lq + (g8 & 1));
-    const uint32_t smem_base = smem_u32(stage0);
-    const float delta = tie_delta_kernel(uint32_t((r_begin + size_t(lane)) >> 44));       // 0, but not provably uniform (fpq_h16.cuh)
-
     // multipliers of this lane's 16 columns (pass 1): units u = 8a + l8, elements 32a + 4*l8 + k
-    uint64_t ms[8];
 #pragma unroll
     for (int a = 0; a < 4; ++a) {
         const int e0 = 32 * a + 4 * l8;
-        if (colok1) load_mult4(smooth, sm, size_t(col0 + g4) * 128 + e0, e0, ms[2 * a], ms[2 * a + 1]);
-        else ms[2 * a] = ms[2 * a + 1] = 0ull;
+        if (st.colok1) load_mult4(smooth, sm, size_t(col0 + g4) * 128 + e0, e0, st.ms[2 * a], st.ms[2 * a + 1]);
+        else st.ms[2 * a] = st.ms[2 * a + 1] = 0ull;
     }
-    uint64_t A[MOD ? 8 : 1], SH[MOD ? 8 : 1];
-    size_t cur_b = ~size_t(0);
 
-    uint32_t s = 0, phase = 0;
-    for (size_t r = r_begin; r < r_end;) {
-        size_t nr_ = r_end - r;
-        if (nr_ > 2) nr_ = 2;
-        if (MOD && nr_ > left) nr_ = left;
-        const int nr = int(nr_);
-        if constexpr (MOD) {
-            if (batch != cur_b) {             // first step of a batch: this lane's (scale + 1) and shift
-                cur_b = batch;
-                if (colok1) {
-#pragma unroll
-                    for (int a = 0; a < 4; ++a)
-                        load_mod4(mod, batch * row_elems + size_t(col0 + g4) * 128 + 32 * a + 4 * l8, A[2 * a], A[2 * a + 1], SH[2 * a], SH[2 * a + 1]);
-                }
-            }
-        }
-        const uint32_t sb = smem_base + s * ROT_WARP_STAGE_BYTES;
+    auto step = [&](uint32_t s, uint32_t done, uint32_t phase) {
+        const int nr = n_mine - done >= 2u ? 2 : 1;
+        const uint32_t buf_off = s * ROT_WARP_STAGE_BYTES;
         mbar_wait(&full[s], phase);
-        // ---- pass 1 ----
-#pragma unroll
-        for (int sub = 0; sub < 2; ++sub) {
-            if (colok1 && sub < nr) {
-                const uint32_t cb = sb + chunk1 + uint32_t(sub) * 2048u;
-                uint64_t P[8];
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    uint4 u;
-                    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(cb + uint32_t(a * 128 + l8 * 16)));
-                    P[2 * a] = (uint64_t(u.y) << 32) | u.x;
-                    P[2 * a + 1] = (uint64_t(u.w) << 32) | u.z;
-                }
-                if constexpr (MOD) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) P[i] = modulate2(P[i], A[i], SH[i]);
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) P[i] = fmul2(P[i], ms[i]);
-                pair_stage(P);          // index bit 0
-                reg_stage(P, 1);        // index bit 1
-                reg_stage(P, 2);        // index bit 5
-                reg_stage(P, 4);        // index bit 6
-                // in place: the 8 lanes of the chunk have all read their units before any of them overwrites one
-                __syncwarp(0xFFu << (8 * g4));
-#pragma unroll
-                for (int a = 0; a < 4; ++a) {
-                    const F2 p0 = unpk(P[2 * a]), p1 = unpk(P[2 * a + 1]);
-                    const uint32_t slot = slot1 ^ uint32_t(2 * a);                      // unit (a, c = l8) at c ^ (2a + s)
-                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(cb + uint32_t(a * 128) + slot * 16u), "f"(p0.lo), "f"(p0.hi), "f"(p1.lo), "f"(p1.hi) : "memory");
-                }
-            }
-        }
+        st.pass1(buf_off, nr);
         __syncwarp();
-        // ---- pass 2 ----
-        const bool valid = colok2 && row2 < nr;
+        const bool valid = st.colok2 && st.row2 < nr;
         uint64_t Q[16];
-        if (valid) {
-            const uint32_t cb = sb + chunk2;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                uint4 u;
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(cb + ((uint32_t(i) ^ key2) << 4)));
-                Q[2 * i] = (uint64_t(u.y) << 32) | u.x;
-                Q[2 * i + 1] = (uint64_t(u.w) << 32) | u.z;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) Q[i] = 0ull;
-        }
+        st.pass2_load(buf_off, valid, Q);
         // the buffer is refilled by the async proxy: order this warp's generic-proxy accesses (reads and the in-place
         // writes of pass 1) before the copy that lane 0 issues next
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         issue(s);                       // step k + 2 into the buffer step k just left
-        reg_stage(Q, 2);                // index bit 2
-        reg_stage(Q, 4);                // index bit 3
-        reg_stage(Q, 8);                // index bit 4
-        // rounded to fp16: the fp16 GEMM output of the reference.  Lane l' holds elements 32*l' .. 32*l' + 31 in order.
-        uint32_t w[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) w[i] = pack_h2_u64(Q[i]);
-        const size_t off = (r + size_t(row2)) * row_elems + size_t(col0 + c2) * 128;
-        if (valid && rotated != nullptr) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) stg_stream(rotated + off + lq * 32 + q * 8, make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));
-        }
-        bool ok = true;
-        float sc = 0.0f;
-        if constexpr (QUANT) ok = sym_quant_tile_h16<FMT, 4, 16>(w, sc, delta);
-        if (valid) {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) stg_stream(out + off + lq * 32 + q * 8, make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));
-            // irregular scale (zero / subnormal / inf / NaN): `out` now holds this lane's rotated values;
-            // quantize them in place with the literal reference sequence
-            if (!ok) literal_sym_h16(out + off, out + off, lq, 4, 32, 1, sc, SymFmt<FMT>::GT);
-        }
-        r += nr_;
-        if constexpr (MOD) { left -= nr_; if (left == 0) { left = mod.rows_per_batch; ++batch; } }
-        s ^= 1u;
-        if (s == 0) phase ^= 1u;
+        st.pass2_finish(valid, Q);
+    };
+    uint32_t phase = 0;
+    for (uint32_t done = 0; done < n_mine; done += 4u) {
+        step(0, done, phase);
+        if (done + 2u < n_mine) step(1, done + 2u, phase);
+        phase ^= 1u;
     }
 }
 
-// Registers: about 20 resident warps per SM at 96 registers; the adaLN variant keeps 32 more operands live and is
-// capped at 112 (18 warps).
+// Registers: about 20 resident warps per SM at 96 registers; the adaLN variant keeps 32 more operands live and gets 128
+// (16 warps).
 template <int FMT, bool QUANT>
 __global__ void __maxnreg__(96) transform_rotate_quant_stream_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
                                                                     SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
@@ -398,7 +455,7 @@ __global__ void __maxnreg__(96) transform_rotate_quant_stream_kernel(const float
     rotate_stream_body<FMT, QUANT, false>(x, smooth, sm, out, rotated, n_rows, cpr, mod);
 }
 template <int FMT, bool QUANT>
-__global__ void __maxnreg__(112) modulate_transform_rotate_quant_stream_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
+__global__ void __maxnreg__(128) modulate_transform_rotate_quant_stream_kernel(const float* __restrict__ x, const float* __restrict__ smooth,
                                                                               SignMask sm, __half* __restrict__ out, __half* __restrict__ rotated,
                                                                               size_t n_rows, int cpr, Modulate mod) {
     rotate_stream_body<FMT, QUANT, true>(x, smooth, sm, out, rotated, n_rows, cpr, mod);
@@ -452,12 +509,16 @@ __global__ void __launch_bounds__(256) transform_rotate_weight_kernel(const floa
 using namespace fpq;
 
 // Launch geometry of the streaming kernel: warps per CTA (one per 4 chunk columns) and CTAs per SM (register budget:
-// about 20 warps, 18 with the adaLN operands).
+// about 20 warps, 16 with the adaLN operands).
 struct RotPlan { int warps; int ctas_per_sm; };
 static bool rot_plan(int cpr, bool mod, RotPlan& p) {
     if (cpr < ROT_MIN_CPR || cpr > ROT_MAX_CPR) return false;
     p.warps = (cpr + 3) / 4;
-    p.ctas_per_sm = (mod ? 18 : 20) / p.warps;
+    p.ctas_per_sm = (mod ? 16 : 20) / p.warps;
+    // shared-memory budget: the carveout every activation kernel asks for (1 KB per CTA is reserved by the system)
+    const int kb = g_tun.smem_kb > 0 ? g_tun.smem_kb : 228;
+    const int by_smem = kb * 1024 / (p.warps * ROT_WARP_SMEM + 1024);
+    if (p.ctas_per_sm > by_smem) p.ctas_per_sm = by_smem;
     if (p.ctas_per_sm < 1) p.ctas_per_sm = 1;
     return true;
 }

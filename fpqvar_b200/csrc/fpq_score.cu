@@ -209,7 +209,7 @@ __device__ __forceinline__ float sse_split_h16(const uint32_t (&p)[16], const ui
     float acc0 = 0.0f, acc1 = 0.0f;
     if (fast) {
         const float sn = __half2float(snh), sp = __half2float(sph);
-        const SplitK k = make_splitk(sn, nbits == 0u ? 0.0f : rcp_rn_normal(sn), sp, pbits == 0u ? 0.0f : rcp_rn_normal(sp));
+        const SplitK k = make_splitk<typename SF::NEG, typename SF::POS>(sn, nbits == 0u ? 0.0f : rcp_rn_normal(sn), sp, pbits == 0u ? 0.0f : rcp_rn_normal(sp));
 #pragma unroll
         for (int i = 0; i < 16; ++i) sq_err_pair(p[i], split_pair_h16_w<typename SF::NEG, typename SF::POS>(xf[i], p[i], k, delta), acc0, acc1);
     } else {

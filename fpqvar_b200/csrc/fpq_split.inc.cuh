@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(1024) signsplit_row_reg_kernel(const InT* __re
         __syncthreads();
         const float sn = red[96], sp = red[97], rn = red[98], rp = red[99];
         const bool fast = red[100] != 0.0f;
-        const SplitK sk = make_splitk(sn, rn, sp, rp);
+        const SplitK sk = make_splitk<typename SF::NEG, typename SF::POS>(sn, rn, sp, rp);
 #pragma unroll
         for (int k = 0; k < V; ++k) {
             const int vi = tid + k * nt;

@@ -21,7 +21,7 @@ def rot_plan(cpr: int, mod: bool = False):
     if cpr < ROT_MIN_CPR or cpr > ROT_MAX_CPR:
         return None
     warps = (cpr + 3) // 4
-    return warps, max(1, (18 if mod else 20) // warps)
+    return warps, max(1, min((16 if mod else 20) // warps, 228 * 1024 // (warps * (2 * 4096 + 16) + 1024)))
 
 
 def pass1_accesses(lane: int, sub: int, ncols: int = 4, nr: int = 2):

@@ -17,6 +17,10 @@ from fpqvar_b200 import ops  # noqa: E402
 from fpqvar_b200.hotpath import seed42_sign_bits  # noqa: E402
 
 lib = L.lib()
+for kv in os.environ.get("FPQ_TUNABLES", "").split(","):        # e.g. FPQ_TUNABLES=smem_kb=100,pdl=0
+    if kv:
+        k, v = kv.split("=")
+        L.set_tunable(k, int(v))
 dev = torch.device("cuda")
 st = torch.cuda.current_stream().cuda_stream
 NBUF = int(os.environ.get("KB_NBUF", "6"))
@@ -60,7 +64,7 @@ def main():
             dict.__setitem__(self, k, v)
     res = R()
     def want(name):
-        return ONLY is None or ONLY in name
+        return ONLY is None or any(o in name for o in ONLY.split("|"))
     # sign-split fc2 input
     x = [torch.nn.functional.gelu(torch.randn(rows, 4 * C, device=dev)).half() for _ in range(NBUF)]
     o = [torch.empty_like(t) for t in x]
