@@ -200,3 +200,15 @@ def gpu_reference_step(hot, dev, iters=2):
             "what": "the reference's own online sequence (basic_var.py:263,266 modulate, .mul(s), dense [C,C] rotation GEMM under fp16 autocast) "
                     "and fp_quant_*_cuda functions (baseline/_ref, unmodified) around its quant_cuda extension compiled for sm_100a, "
                     "same calls and algorithmic bytes as the step above"}
+
+
+if __name__ == "__main__":          # child-process entry used by bench.py: python -m baseline.ref_legs gpu_step <workload>
+    import json
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch
+    from fpqvar_b200.var_workload import WORKLOADS
+    if len(sys.argv) >= 3 and sys.argv[1] == "gpu_step":
+        dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+        torch.cuda.set_device(dev)
+        print(json.dumps(gpu_reference_step(WORKLOADS[sys.argv[2]], dev, iters=2)), flush=True)

@@ -340,36 +340,39 @@ def ncu_traffic(dom_key, bytes_per_avg_launch):
 
 
 def reference_gpu_legs(torch, dev, hot, args):
-    """(reference_gpu_path, generation_reference_model): the UNMODIFIED reference from baseline/_ref on this GPU."""
+    """(reference_gpu_path, generation_reference_model): the UNMODIFIED reference from baseline/_ref on this GPU, each in a
+    child process (the reference's code owns that process: it switches torch's initialisers off, and a device-side assert
+    in it cannot take this run down)."""
     from baseline import ref_env
     if not ref_env.available():
         why = {"unavailable": ref_env.why_unavailable()}
         return why, why
-    gpu = gen = None
+
+    def child(cmd, timeout):
+        r = subprocess.run([sys.executable] + cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+        lines = [json.loads(l) for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 and not lines:
+            raise RuntimeError((r.stderr.strip().splitlines() or ["exit code %d" % r.returncode])[-1][:300])
+        return lines
+
     try:
-        from baseline import ref_legs
-        gpu = ref_legs.gpu_reference_step(hot, dev, iters=2)
+        gpu = child(["-m", "baseline.ref_legs", "gpu_step", hot.name], 600)[-1]
     except Exception as e:  # noqa: BLE001  (reported in the JSON line)
         gpu = {"error": f"{type(e).__name__}: {e}"}
-    torch.cuda.empty_cache()
+    gen = None
     if not args.no_generation and hot.rotate_transform:
-        import importlib.util
-        spec = importlib.util.spec_from_file_location("ref_model_generate", os.path.join(ROOT, "tools", "ref_model_generate.py"))
-        rg = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(rg)
-        ns = ref_env.load(str(dev))
         res = 512 if hot.patch_nums[-1] == 32 else 256
         bits = 6 if hot.act_fmt in ("e2m3", "e3m2") else 4
         gen = {"unit": "images/s", "model": f"the reference's own VAR-d{hot.depth} {res}x{res} (build_vae_var, autoregressive_infer_cfg, fp16 autocast), "
                                              f"B={hot.batch}, W{bits}A{bits}, random init", "harness": "tools/ref_model_generate.py"}
         for mode in ("fp16", "reference", "dropin", "fused"):
             try:
-                r = rg.measure(ns, dev, hot.depth, hot.batch, res, bits, mode, iters=2, warmup=1)
+                r = child([os.path.join(ROOT, "tools", "ref_model_generate.py"), "--depth", str(hot.depth), "--batch", str(hot.batch), "--res", str(res),
+                           "--bits", str(bits), "--iters", "2", "--modes", mode], 900)[-1]
                 gen[mode] = {k: r[k] for k in ("images_per_sec", "ms_per_batch", "finite", "fpq_launches_per_batch")}
                 gen["galt_factors"] = r["galt_factors"]
             except Exception as e:  # noqa: BLE001
                 gen[mode] = {"error": f"{type(e).__name__}: {e}"}
-            torch.cuda.empty_cache()
     return gpu, gen
 
 

@@ -31,6 +31,8 @@ SIGNATURES = {
     "fpq_quant_grid": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_int, _c.c_size_t, _c.c_void_p, _c.c_int, _c.c_void_p]),
     "fpq_fake_quant": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int, _c.c_int,
                                   _c.c_uint, _c.c_void_p]),
+    "fpq_fake_quant_segments": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_size_t, _c.c_size_t, _c.c_size_t,
+                                           _c.c_int, _c.c_void_p]),
     "fpq_fake_quant_signsplit": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_int, _c.c_int,
                                             _c.c_int, _c.c_uint, _c.c_void_p, _c.c_void_p]),
     "fpq_transform_rotate_quant": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_void_p, _c.c_size_t,
@@ -66,7 +68,7 @@ def lib() -> ctypes.CDLL:
             try:
                 fn = getattr(handle, name)    # AttributeError here = header and library out of sync
             except AttributeError:
-                if os.environ.get("FPQ_LIB_PATH") and name in ("fpq_set_tunable", "fpq_rotate_plan"):
+                if os.environ.get("FPQ_LIB_PATH") and name in ("fpq_set_tunable", "fpq_rotate_plan", "fpq_fake_quant_segments"):
                     continue                  # an older build selected for an A/B measurement (tools/): it has no tunables
                 raise
             fn.restype = res

@@ -123,6 +123,53 @@ __global__ void __launch_bounds__(256) fake_quant_group64_h16_kernel(const __hal
 }
 
 // ------------------------------------------------------------------------------------------
+// Segments with a pitch, optionally IN PLACE (fpq_fake_quant_segments): the appended slice [B, lo:cur, H, head_dim] of a
+// KV cache [B, L_max, H, head_dim] is B contiguous segments `pitch` elements apart.  blockIdx.y walks the segments; inside
+// a segment the groups (GS = 64 or 128 halves) are contiguous.  No __restrict__ and plain (coherent) loads: out may be x,
+// every element is read by the lane that later writes it, and nothing is read twice.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 ldg_plain(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+template <int FMT, int GS>
+__global__ void __launch_bounds__(256) fake_quant_segments_h16_kernel(const __half* x, __half* out, size_t groups_per_segment, size_t pitch_x,
+                                                                      size_t pitch_out) {
+    constexpr int LPG = 4, NV = GS / 32, NW = 4 * NV, GPW = 32 / LPG;
+    pdl_launch_dependents();
+    const int lane = threadIdx.x & 31;
+    const int lig = lane % LPG;
+    const size_t warp_in_seg = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
+    const float delta = tie_delta_kernel(uint32_t(warp_in_seg >> 33));
+    x += size_t(blockIdx.y) * pitch_x;
+    out += size_t(blockIdx.y) * pitch_out;
+    pdl_wait();
+    for (size_t g0 = warp_in_seg * GPW; g0 < groups_per_segment; g0 += n_warps * GPW) {
+        const size_t g = g0 + lane / LPG;
+        const bool live = g < groups_per_segment;
+        uint32_t p[NW];
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            uint4 u = make_uint4(0u, 0u, 0u, 0u);
+            if (live) u = ldg_plain(x + g * GS + (j * LPG + lig) * 8);
+            p[4 * j] = u.x; p[4 * j + 1] = u.y; p[4 * j + 2] = u.z; p[4 * j + 3] = u.w;
+        }
+        float s;
+        const bool ok = sym_quant_tile_h16<FMT, LPG, NW>(p, s, delta);
+        if (live) {
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < NV; ++j) stg_stream(out + g * GS + (j * LPG + lig) * 8, make_uint4(p[4 * j], p[4 * j + 1], p[4 * j + 2], p[4 * j + 3]));
+            } else {
+                literal_sym_h16(x + g * GS, out + g * GS, lig, LPG, 8, NV, s, SymFmt<FMT>::GT);      // element-wise: safe in place
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // sign-split
 // ------------------------------------------------------------------------------------------
 template <int SPLIT> struct SplitH16;
@@ -377,4 +424,56 @@ extern "C" int fpq_selftest_f16_flow(int format, unsigned long long* result, voi
         default: return FPQ_ERR_ARG;
     }
     return finish_launch();
+}
+
+template <int GS>
+static int launch_segments_h16(int format, const __half* x, __half* out, size_t n_segments, size_t groups_per_segment, size_t pitch_x,
+                               size_t pitch_out, cudaStream_t st) {
+    // per segment: 8 warps x 8 groups per block and trip; the whole grid fills the SMs' thread slots
+    size_t per_seg = (groups_per_segment + 63) / 64;
+    const size_t cap = (size_t(sm_count()) * 8 + n_segments - 1) / n_segments;
+    if (per_seg > cap) per_seg = cap;
+    if (per_seg < 1) per_seg = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(unsigned(per_seg), unsigned(n_segments), 1);
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = g_tun.pdl ? 1 : 0;
+    switch (format) {
+        case FPQ_FMT_E2M1: cudaLaunchKernelEx(&cfg, fake_quant_segments_h16_kernel<FPQ_FMT_E2M1, GS>, x, out, groups_per_segment, pitch_x, pitch_out); break;
+        case FPQ_FMT_E1M2: cudaLaunchKernelEx(&cfg, fake_quant_segments_h16_kernel<FPQ_FMT_E1M2, GS>, x, out, groups_per_segment, pitch_x, pitch_out); break;
+        case FPQ_FMT_E3M0: cudaLaunchKernelEx(&cfg, fake_quant_segments_h16_kernel<FPQ_FMT_E3M0, GS>, x, out, groups_per_segment, pitch_x, pitch_out); break;
+        case FPQ_FMT_E2M3: cudaLaunchKernelEx(&cfg, fake_quant_segments_h16_kernel<FPQ_FMT_E2M3, GS>, x, out, groups_per_segment, pitch_x, pitch_out); break;
+        case FPQ_FMT_E3M2: cudaLaunchKernelEx(&cfg, fake_quant_segments_h16_kernel<FPQ_FMT_E3M2, GS>, x, out, groups_per_segment, pitch_x, pitch_out); break;
+        default: return FPQ_ERR_ARG;
+    }
+    return finish_launch();
+}
+
+extern "C" int fpq_fake_quant_segments(const void* x, void* out, size_t n_segments, size_t rows_per_segment, size_t row_len, size_t pitch_x,
+                                       size_t pitch_out, int format, void* stream) {
+    if (n_segments && rows_per_segment && (!x || !out)) return FPQ_ERR_ARG;
+    if (row_len != 64 && row_len != 128) return FPQ_ERR_UNSUPPORTED;
+    if (format < 0 || format >= FPQ_NUM_SYM_FORMATS) return FPQ_ERR_ARG;
+    const size_t seg_elems = rows_per_segment * row_len;
+    if (pitch_x < seg_elems || pitch_out < seg_elems || (pitch_x % 8) || (pitch_out % 8)) return FPQ_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) return FPQ_ERR_ARG;
+    if (n_segments > 65535) return FPQ_ERR_UNSUPPORTED;
+    // out == x (in place, same pitch) is allowed; any other overlap is not
+    if (x != out || pitch_x != pitch_out) {
+        const char* a = static_cast<const char*>(x);
+        const char* b = static_cast<const char*>(out);
+        const size_t ea = ((n_segments ? n_segments - 1 : 0) * pitch_x + seg_elems) * 2, eb = ((n_segments ? n_segments - 1 : 0) * pitch_out + seg_elems) * 2;
+        if (a < b + eb && b < a + ea) return FPQ_ERR_ARG;
+    }
+    if (n_segments == 0 || rows_per_segment == 0) return FPQ_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const __half* xi = static_cast<const __half*>(x);
+    __half* oo = static_cast<__half*>(out);
+    if (row_len == 64) return launch_segments_h16<64>(format, xi, oo, n_segments, rows_per_segment, pitch_x, pitch_out, st);
+    return launch_segments_h16<128>(format, xi, oo, n_segments, rows_per_segment, pitch_x, pitch_out, st);
 }

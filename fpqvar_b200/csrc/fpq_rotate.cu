@@ -235,19 +235,21 @@ struct RotStream {
     __half* op;             // this lane's 32 output elements of row `row2` of the current step
     __half* rp;             // same in `rotated` (or nullptr)
 
+    // this lane's (scale + 1) and shift of the batch `pa` / `psh` point at
+    __device__ __forceinline__ void load_operands() {
+        reload = false;
+        if (colok1) {
+            Modulate m{pa, psh, 0, mod_one};
+#pragma unroll
+            for (int a = 0; a < 4; ++a) load_mod4(m, size_t(32 * a), A[2 * a], A[2 * a + 1], SH[2 * a], SH[2 * a + 1]);
+        }
+    }
     __device__ __forceinline__ void pass1(uint32_t buf_off, int nr) {
 #pragma unroll
         for (int sub = 0; sub < 2; ++sub) {
             if (sub < nr) {
                 if constexpr (MOD) {
-                    if (reload) {                                 // first row of a batch: this lane's (scale + 1) and shift
-                        reload = false;
-                        if (colok1) {
-                            Modulate m{pa, psh, 0, mod_one};
-#pragma unroll
-                            for (int a = 0; a < 4; ++a) load_mod4(m, size_t(32 * a), A[2 * a], A[2 * a + 1], SH[2 * a], SH[2 * a + 1]);
-                        }
-                    }
+                    if (reload) load_operands();                  // first row of a batch
                     if (--left == 0) { left = rpb; pa += row_elems; psh += row_elems; reload = true; }
                 }
                 if (colok1) {
@@ -413,6 +415,7 @@ __device__ __forceinline__ void rotate_stream_body(const float* __restrict__ x, 
     };
     issue(0);
     issue(1);
+    if constexpr (MOD) st.load_operands();          // the first batch's adaLN operands travel while the first copy does
 
     // multipliers of this lane's 16 columns (pass 1): units u = 8a + l8, elements 32a + 4*l8 + k
 #pragma unroll

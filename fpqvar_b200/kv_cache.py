@@ -26,7 +26,7 @@ from typing import Optional, Tuple
 
 import torch
 
-from . import quant_utils
+from . import ops, quant_utils
 
 _TINY = 2.0 ** -16          # rows that drift have absmax <= 5.6e-6 (e2m3) / 5.4e-7 (e2m1) before AND after quantization: < 2^-17
 
@@ -74,6 +74,19 @@ class IncrementalKVQuant:
             bad = bad | (((amax < _TINY) & (amax > 0)) | ~torch.isfinite(amax)).any()
         return not bool(bad)
 
+    def _quant_inplace(self, buf: torch.Tensor, lo: int, hi: int) -> None:
+        """basic_var.py:193-197 on buf[:, lo:hi], where the rows lie: one launch, one read and one write of the slice (the
+        slice is B pieces of a larger tensor: fpq_fake_quant_segments walks them with a pitch).  kv_bit=6: per-token rows of
+        head_dim; kv_bit=4: groups of 128 along the flattened [H, head_dim]."""
+        hd = buf.shape[-1]
+        if self.kv_bit == 6 and hd == 64:
+            ops.fake_quant_segments_(buf, lo, hi, "e2m3", 64)
+        elif self.kv_bit == 4:
+            ops.fake_quant_segments_(buf, lo, hi, "e2m1", 128)
+        else:                                   # other head sizes: the general row kernel on a gathered copy
+            part = buf[:, lo:hi]
+            part.copy_(_quant(part, self.kv_bit))
+
     def append(self, k: torch.Tensor, v: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
         if k.shape != v.shape or k.dim() != 4 or k.dtype != torch.float16:
             raise ValueError("IncrementalKVQuant.append: k and v must be fp16 [B, l, H, head_dim] of the same shape")
@@ -89,8 +102,7 @@ class IncrementalKVQuant:
         if self.cur:                                        # basic_var.py:189-203: quantize what is cached, then append
             lo = self.done if self.incremental else 0
             for buf in (self.k, self.v):
-                part = buf[:, lo:self.cur]
-                part.copy_(_quant(part, self.kv_bit))
+                self._quant_inplace(buf, lo, self.cur)
             self.done = self.cur
         self.k[:, self.cur:self.cur + l] = k
         self.v[:, self.cur:self.cur + l] = v

@@ -15,6 +15,33 @@ from . import _lib as L
 
 _DT = {torch.float32: L.FPQ_F32, torch.float16: L.FPQ_F16}
 
+_EXT = None
+
+
+def _ext():
+    """The torch extension over the C ABI (fpqvar_b200/dropin/quant_cuda*.so): the four hot operators do their argument
+    checks, output allocation and launch in C++ (a few microseconds of host time per call).  No fallback: if it is not
+    built, the hot operators raise."""
+    global _EXT
+    if _EXT is None:
+        try:
+            from .dropin import quant_cuda as ext
+        except ImportError as e:
+            raise L.FpqError("the torch extension fpqvar_b200/dropin/quant_cuda is not built (bash fpqvar_b200/csrc/build_torch_ext.sh, "
+                             f"or __graft_entry__.build()): {e}") from None
+        L.lib()                         # same library instance for the ctypes entries (launch counter, tunables)
+        _EXT = ext
+    return _EXT
+
+
+def _call(fn, *args):
+    try:
+        return fn(*args)
+    except RuntimeError as e:           # std::runtime_error / c10::Error from the extension
+        if isinstance(e, L.FpqError):
+            raise
+        raise L.FpqError(str(e).split("\n")[0]) from None
+
 
 def _require_cuda(x: torch.Tensor, what: str) -> None:
     if not isinstance(x, torch.Tensor) or not x.is_cuda:
@@ -92,17 +119,34 @@ def fake_quant(x: torch.Tensor, fmt: str, row_len: Optional[int] = 128, tie: str
     """Symmetric fake-quant (fpq_fake_quant). ``row_len=None``: the last dim shares one scale
     (per_token / per_channel).  Output dtype: the input's for tie="kernel" (the ``*_cuda``
     reference functions), float32 for tie="argmin" (quant_utils.py:308 promotes)."""
-    _require_cuda(x, "fake_quant")
-    x = x.contiguous()
-    if out_dtype is None:
-        out_dtype = x.dtype if tie == "kernel" else torch.float32
-    out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
-    n_rows, rl = _rows(x, row_len)
-    with _on_device(x) as _di:
-        rc = L.lib().fpq_fake_quant(x.data_ptr(), out.data_ptr(), n_rows, rl, _dt(x, "fake_quant"), _dt(out, "fake_quant"),
-                                    L.FMT[fmt], L.TIE[tie], L.FLAG_CLAMP3 if clamp3 else 0, _stream(_di))
-    L.check(rc, "fpq_fake_quant")
-    return out
+    if not isinstance(x, torch.Tensor):
+        raise L.FpqError(f"fake_quant: expected a CUDA tensor; got {type(x)}")
+    od = -1 if out_dtype is None else _DT.get(out_dtype)
+    if od is None:
+        raise L.FpqError(f"fake_quant: out dtype {out_dtype} is not supported (float16 / float32 only)")
+    return _call(_ext().fake_quant, x, L.FMT[fmt], -1 if row_len is None else row_len, L.TIE[tie], L.FLAG_CLAMP3 if clamp3 else 0, od)
+
+
+def fake_quant_segments_(buf: torch.Tensor, lo: int, hi: int, fmt: str, row_len: int) -> None:
+    """In-place symmetric fake-quant (kernel tie rule) of ``buf[:, lo:hi]`` for a contiguous fp16 ``buf`` of shape
+    [B, L, ...]: B segments of (hi - lo) * prod(shape[2:]) halves, L * prod(shape[2:]) apart, quantized where they lie in ONE
+    launch (fpq_fake_quant_segments) -- no gather copy, no scatter copy.  ``row_len`` (64 | 128) halves share a scale."""
+    _require_cuda(buf, "fake_quant_segments_")
+    if buf.dtype != torch.float16 or not buf.is_contiguous() or buf.dim() < 2:
+        raise L.FpqError("fake_quant_segments_: expected a contiguous float16 tensor [B, L, ...]")
+    B, Lmax = buf.shape[0], buf.shape[1]
+    if not (0 <= lo <= hi <= Lmax):
+        raise L.FpqError(f"fake_quant_segments_: bad range [{lo}, {hi}) for length {Lmax}")
+    inner = buf[0, 0].numel()
+    seg = (hi - lo) * inner
+    if seg % row_len:
+        raise L.FpqError(f"fake_quant_segments_: {seg} elements per segment is not a multiple of the row length {row_len}")
+    if seg == 0 or B == 0:
+        return
+    ptr = buf.data_ptr() + lo * inner * 2
+    with _on_device(buf) as _di:
+        rc = L.lib().fpq_fake_quant_segments(ptr, ptr, B, seg // row_len, row_len, Lmax * inner, Lmax * inner, L.FMT[fmt], _stream(_di))
+    L.check(rc, "fpq_fake_quant_segments")
 
 
 _WS = {}
@@ -122,19 +166,14 @@ def fake_quant_signsplit(x: torch.Tensor, split_fmt: str, row_len: Optional[int]
     """Sign-split fake-quant (fpq_fake_quant_signsplit).  ``global_clip=True`` reproduces the
     reference's whole-tensor ``clamp(x, -|x|max, |x|max)`` (quant_utils.py:421-422), which only
     matters when the tensor holds a NaN (then the whole output is zero)."""
-    _require_cuda(x, "fake_quant_signsplit")
-    x = x.contiguous()
-    if out_dtype is None:
-        out_dtype = x.dtype if tie == "kernel" else torch.float32
-    out = torch.empty(x.shape, dtype=out_dtype, device=x.device)
-    n_rows, rl = _rows(x, row_len)
-    ws = _clip_workspace(x.device) if global_clip else None
-    with _on_device(x) as _di:
-        rc = L.lib().fpq_fake_quant_signsplit(x.data_ptr(), out.data_ptr(), n_rows, rl, _dt(x, "signsplit"), _dt(out, "signsplit"),
-                                              L.SPLIT[split_fmt], L.TIE[tie], L.FLAG_GLOBAL_CLIP if global_clip else 0,
-                                              ws.data_ptr() if ws is not None else None, _stream(_di))
-    L.check(rc, "fpq_fake_quant_signsplit")
-    return out
+    if not isinstance(x, torch.Tensor):
+        raise L.FpqError(f"fake_quant_signsplit: expected a CUDA tensor; got {type(x)}")
+    od = -1 if out_dtype is None else _DT.get(out_dtype)
+    if od is None:
+        raise L.FpqError(f"fake_quant_signsplit: out dtype {out_dtype} is not supported (float16 / float32 only)")
+    ws = _clip_workspace(x.device) if (global_clip and x.is_cuda) else None
+    return _call(_ext().fake_quant_signsplit, x, L.SPLIT[split_fmt], -1 if row_len is None else row_len, L.TIE[tie],
+                 L.FLAG_GLOBAL_CLIP if global_clip else 0, ws, od)
 
 
 def quant_grid(x: torch.Tensor, grid: torch.Tensor, tie: str = "kernel") -> torch.Tensor:
@@ -169,21 +208,10 @@ def transform_rotate_quant(x: torch.Tensor, smooth: Optional[torch.Tensor], sign
     """Fused ``(x * smooth) @ Q_block128`` -> fp16 -> per-group fake quant (fpq_transform_rotate_quant).
     x: fp32 [..., C]; returns fp16 of the same shape (and the pre-quantization rotated fp16
     tensor when ``return_rotated``).  ``fmt=None`` skips the quantizer."""
-    _require_cuda(x, "transform_rotate_quant")
-    if x.dtype != torch.float32:
-        raise L.FpqError("transform_rotate_quant: x must be float32 (the adaLN-modulated LayerNorm output)")
-    x = x.contiguous()
-    c = x.shape[-1]
-    smooth = _smooth_f32(smooth, c, "transform_rotate_quant")
-    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
-    rot = torch.empty_like(out) if return_rotated else None
-    n_rows = x.numel() // c if c else 0
-    with _on_device(x) as _di:
-        rc = L.lib().fpq_transform_rotate_quant(x.data_ptr(), smooth.data_ptr() if smooth is not None else None, sign_bits,
-                                                out.data_ptr(), rot.data_ptr() if rot is not None else None, n_rows, c,
-                                                -1 if fmt is None else L.FMT[fmt], _stream(_di))
-    L.check(rc, "fpq_transform_rotate_quant")
-    return (out, rot) if return_rotated else out
+    if not isinstance(x, torch.Tensor):
+        raise L.FpqError(f"transform_rotate_quant: expected a CUDA tensor; got {type(x)}")
+    r = _call(_ext().transform_rotate_quant, x, smooth, list(sign_bits), -1 if fmt is None else L.FMT[fmt], return_rotated)
+    return (r[0], r[1]) if return_rotated else r[0]
 
 
 def modulate_transform_rotate_quant(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, smooth: Optional[torch.Tensor], sign_bits,
@@ -196,32 +224,10 @@ def modulate_transform_rotate_quant(x: torch.Tensor, scale: torch.Tensor, shift:
     (evaluate_fp_quant_transform_rotate.py:195: ada_lin is an autocast Linear): there `scale.add(1)` is an
     fp16 add and only its rounded result meets the fp32 LayerNorm output.  That add is done here with the
     same ATen op on the tiny [B, 1, C] tensor and handed to the kernel as a gain (FPQ_MOD_GAIN)."""
-    _require_cuda(x, "modulate_transform_rotate_quant")
-    if x.dtype != torch.float32 or x.dim() < 2:
-        raise L.FpqError("modulate_transform_rotate_quant: x must be float32 [B, ..., C]")
-    x = x.contiguous()
-    b, c = x.shape[0], x.shape[-1]
-    rows_per_batch = x.numel() // (b * c) if b * c else 0
-    for name, t in (("scale", scale), ("shift", shift)):
-        _require_cuda(t, f"modulate_transform_rotate_quant({name})")
-        if t.numel() != b * c or t.shape[0] != b or t.shape[-1] != c:
-            raise L.FpqError(f"{name} must be [B, 1, C] = [{b}, 1, {c}], got {tuple(t.shape)}")
-        if t.dtype not in (torch.float32, torch.float16):
-            raise L.FpqError(f"{name} must be float32 or float16, got {t.dtype}")
-    flags = 0
-    if scale.dtype == torch.float16:
-        scale, flags = scale.detach().add(1), L.MOD_GAIN
-    mods = [t.detach().to(torch.float32).contiguous() for t in (scale, shift)]
-    smooth = _smooth_f32(smooth, c, "modulate_transform_rotate_quant")
-    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
-    rot = torch.empty_like(out) if return_rotated else None
-    with _on_device(x) as _di:
-        rc = L.lib().fpq_modulate_transform_rotate_quant(x.data_ptr(), mods[0].data_ptr(), mods[1].data_ptr(), rows_per_batch,
-                                                         smooth.data_ptr() if smooth is not None else None, sign_bits, out.data_ptr(),
-                                                         rot.data_ptr() if rot is not None else None, b * rows_per_batch, c,
-                                                         -1 if fmt is None else L.FMT[fmt], flags, _stream(_di))
-    L.check(rc, "fpq_modulate_transform_rotate_quant")
-    return (out, rot) if return_rotated else out
+    if not isinstance(x, torch.Tensor):
+        raise L.FpqError(f"modulate_transform_rotate_quant: expected a CUDA tensor; got {type(x)}")
+    r = _call(_ext().modulate_transform_rotate_quant, x, scale, shift, smooth, list(sign_bits), -1 if fmt is None else L.FMT[fmt], return_rotated)
+    return (r[0], r[1]) if return_rotated else r[0]
 
 
 def transform_rotate_weight(w: torch.Tensor, smooth: Optional[torch.Tensor], sign_bits, inplace: bool = False) -> torch.Tensor:

@@ -122,6 +122,18 @@ FPQ_API int fpq_fake_quant(const void *x, void *out, size_t n_rows, size_t row_l
                    unsigned flags, void *stream);
 
 /*
+ * Symmetric fake-quant of `n_segments` equally long pieces of a larger fp16 tensor, optionally IN PLACE: segment i starts at
+ * x + i * pitch_x (elements) and holds rows_per_segment rows of row_len (64 | 128) contiguous halves; kernel tie rule,
+ * fp16 in and out.  out may equal x (with pitch_out == pitch_x); no other overlap.  This is the KV-cache call: the
+ * reference re-quantizes `self.cached_k` / `self.cached_v` before every append (models_fp_quant_transform_rotate/
+ * basic_var.py:192-197, fp6_quant_e2m3_per_token_cuda rows of head_dim = 64 / fp_quant_e2_per_group_cuda groups of 128);
+ * with a preallocated cache [B, L_max, H, head_dim] the rows appended at one scale are B segments of pitch
+ * L_max * H * head_dim, quantized where they lie (fpqvar_b200/kv_cache.py).
+ */
+FPQ_API int fpq_fake_quant_segments(const void *x, void *out, size_t n_segments, size_t rows_per_segment,
+                   size_t row_len, size_t pitch_x, size_t pitch_out, int format, void *stream);
+
+/*
  * Sign-split fake-quant (fc2 inputs): x<=0 and x>0 get their own grid and their own absmax
  * scale per row; out = q_neg*s_neg + q_pos*s_pos.  Arguments as fpq_fake_quant;
  * `split_format` is FPQ_SPLIT_*.  With FPQ_FLAG_GLOBAL_CLIP, `workspace` must point to 8 bytes

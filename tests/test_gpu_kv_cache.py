@@ -87,3 +87,69 @@ def test_kv_cache_argument_checks():
     c6.append(y, y)
     with pytest.raises(ValueError):
         c6.append(y, y)
+
+
+@pytest.mark.parametrize("kv_bit", [6, 4])
+def test_incremental_kv_quant_equals_the_oracle_run_of_the_reference_schedule(kv_bit):
+    """The whole schedule on the ORACLE side (numpy restatement of fp6_quant_e2m3_per_token_cuda / fp_quant_e2_per_group_cuda,
+    re-quantizing the entire cache before every append exactly as basic_var.py:188-203 does), against the incremental
+    in-place CUDA path at every scale."""
+    import numpy as np
+    from oracle import oracle as O
+    from fpqvar_b200.kv_cache import IncrementalKVQuant
+    rng = np.random.default_rng(40 + kv_bit)
+    B, H, hd = 3, 2, 64
+    patch = PATCH[:7]
+    ks = [rng.standard_normal((B, p * p, H, hd)).astype(np.float16) for p in patch]
+    vs = [(rng.standard_normal((B, p * p, H, hd)) * np.exp(2 * rng.standard_normal((B, p * p, H, 1)))).astype(np.float16) for p in patch]
+    vs[1][0, 2] = 0
+
+    def oq(t):
+        if kv_bit == 6:
+            return O.fake_quant(t.reshape(-1, hd), "e2m3", hd, "kernel").reshape(t.shape)
+        return O.fake_quant(t.reshape(-1, 128), "e2m1", 128, "kernel").reshape(t.shape)
+
+    inc = IncrementalKVQuant(kv_bit, sum(p * p for p in patch))
+    ck = cv = None
+    for k, v in zip(ks, vs):
+        if ck is None:
+            ck, cv = k, v
+        else:
+            ck, cv = np.concatenate((oq(ck), k), axis=1), np.concatenate((oq(cv), v), axis=1)
+        ik, iv = inc.append(torch.from_numpy(k).cuda(), torch.from_numpy(v).cuda())
+        assert np.array_equal(ik.cpu().numpy().view(np.uint16), ck.view(np.uint16))
+        assert np.array_equal(iv.cpu().numpy().view(np.uint16), cv.view(np.uint16))
+
+
+@pytest.mark.parametrize("row_len,fmt", [(64, "e2m3"), (128, "e2m1"), (128, "e3m2"), (64, "e1m2")])
+def test_fake_quant_segments_in_place_and_pitched(row_len, fmt):
+    """fpq_fake_quant_segments: a slice [B, lo:hi] of a larger tensor, in place == the plain kernel on a gathered copy; the
+    rest of the tensor is untouched; out-of-place with a different pitch works too."""
+    from fpqvar_b200 import ops, _lib as L
+    g = torch.Generator(device="cuda").manual_seed(row_len)
+    B, Lmax, inner = 5, 37, 384
+    buf = (torch.randn(B, Lmax, inner, device="cuda", generator=g) * 3).half()
+    buf[1, 9, :128] = 0
+    buf[2, 10, 5] = float("inf")
+    buf[3, 11, 7] = float("nan")
+    orig = buf.clone()
+    lo, hi = 8, 29
+    want = ops.fake_quant(orig[:, lo:hi].contiguous(), fmt, row_len, "kernel")
+    ops.fake_quant_segments_(buf, lo, hi, fmt, row_len)
+    a, b = buf[:, lo:hi].contiguous().view(torch.int16), want.view(torch.int16)
+    nan = torch.isnan(want)
+    assert torch.equal(torch.isnan(buf[:, lo:hi]), nan) and torch.equal(a[~nan], b[~nan])
+    assert torch.equal(buf[:, :lo].view(torch.int16), orig[:, :lo].view(torch.int16))
+    assert torch.equal(buf[:, hi:].view(torch.int16), orig[:, hi:].view(torch.int16))
+    # out of place into a dense tensor (pitch_out = segment size)
+    dense = torch.empty(B, hi - lo, inner, device="cuda", dtype=torch.float16)
+    seg = (hi - lo) * inner
+    rc = L.lib().fpq_fake_quant_segments(orig.data_ptr() + lo * inner * 2, dense.data_ptr(), B, seg // row_len, row_len, Lmax * inner, seg,
+                                         L.FMT[fmt], torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    d = dense.view(torch.int16)
+    assert torch.equal(d[~nan], b[~nan])
+    # partial overlap is refused; so is a row length the packed kernels do not take
+    assert L.lib().fpq_fake_quant_segments(orig.data_ptr(), orig.data_ptr() + 256, B, seg // row_len, row_len, Lmax * inner, Lmax * inner,
+                                           L.FMT[fmt], None) == L.FPQ_ERR_ARG
+    assert L.lib().fpq_fake_quant_segments(orig.data_ptr(), dense.data_ptr(), 1, 4, 96, 4096, 4096, L.FMT[fmt], None) == L.FPQ_ERR_UNSUPPORTED

@@ -4,6 +4,8 @@ import ctypes
 import inspect
 import os
 import re
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -252,6 +254,17 @@ def test_quantized_linear_dispatch_and_errors():
         Q.QuantizedLinear(8, 8, act_quant="per_token", a_bit=8)(torch.zeros(1, 8))
 
 
+def test_quant_cuda_is_an_importable_extension_module_on_sys_path():
+    """`import quant_cuda` with fpqvar_b200/dropin on sys.path loads the torch extension over the C ABI (a real module file,
+    not a sys.modules entry): what replaces the reference's quant/ build directory."""
+    code = ("import sys; sys.path.insert(0, %r); import torch, quant_cuda; "
+            "assert quant_cuda.__file__.endswith('.so') and 'dropin' in quant_cuda.__file__; "
+            "print(quant_cuda.version())") % os.path.join(ROOT, "fpqvar_b200", "dropin")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr
+    assert "fpq_b200" in r.stdout
+
+
 def test_dropin_install_registers_reference_module_names():
     import sys
     import fpqvar_b200.dropin as dropin
@@ -260,7 +273,7 @@ def test_dropin_install_registers_reference_module_names():
     try:
         dropin.install()
         import quant_cuda
-        assert callable(quant_cuda.quant) and list(inspect.signature(quant_cuda.quant).parameters) == ["x", "y"]
+        assert callable(quant_cuda.quant) and "quant(x: torch.Tensor, y: torch.Tensor)" in quant_cuda.quant.__doc__     # quant/quant.cpp:27-29
         import quant_utils
         assert quant_utils.QuantizedLinear.__name__ == "QuantizedLinear"
     finally:

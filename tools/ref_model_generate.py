@@ -68,21 +68,38 @@ def _fused_forward(self, x, cond_BD, attn_bias, step_idx, quant_KV, kv_bit, rota
     return x
 
 
+def _init_vqvae(vae):
+    """The reference's build_vae_var switches torch's built-in initialisers off (models*/__init__.py:23-25: the VQVAE is
+    meant to be filled from a checkpoint) and VAR.init_weights covers the transformer only, so without a checkpoint the VQVAE
+    holds uninitialised memory (measured: conv weights of 4e21).  Give it a plain deterministic init (the decoder's cost
+    does not depend on the values; they only have to stay finite in fp16)."""
+    g = torch.Generator(device="cpu").manual_seed(1)
+    with torch.no_grad():
+        for name, p in list(vae.named_parameters()) + list(vae.named_buffers()):
+            if not p.is_floating_point():
+                p.zero_()
+            elif p.dim() >= 2:
+                fan_in = p[0].numel()
+                p.copy_((torch.randn(p.shape, generator=g) * (0.5 / max(1, fan_in) ** 0.5)).to(p.device, p.dtype))
+            elif "norm" in name and name.endswith("weight"):
+                p.fill_(1.0)
+            else:
+                p.zero_()
+        emb = getattr(getattr(vae, "quantize", None), "embedding", None)
+        if emb is not None:
+            emb.weight.copy_(torch.randn(emb.weight.shape, generator=g).to(emb.weight.device))
+
+
 def build(ns, dev, depth, res, bits, mode):
     patch_nums = PATCH_512 if res == 512 else PATCH_256
     torch.manual_seed(0)
     vae, var = ns.build_vae_var(V=4096, Cvae=32, ch=160, share_quant_resi=4, device=dev, patch_nums=patch_nums,
                                 num_classes=1000, depth=depth, shared_aln=(res == 512))
+    _init_vqvae(vae)
     vae.eval().to(dev)
     var.eval().to(dev)
     for p in list(vae.parameters()) + list(var.parameters()):
         p.requires_grad_(False)
-    with torch.no_grad():        # init_weights zeroes the adaLN projection and the head: give every branch something to do
-        for b in var.blocks:
-            if hasattr(b, "ada_lin"):
-                b.ada_lin[1].weight.normal_(0, 0.02)
-                b.ada_lin[1].bias.normal_(0, 0.2)
-        var.head.weight.normal_(0, 0.02)
     C = var.C
     fmt = {4: ("fp_e2", "fp_e2", "fp_e1m2_neg_e2m1_pos"), 6: ("fp6_e2m3", "fp6_e2m3", "fp6_int_neg_e2m3_pos")}[bits]
     s_qkv, s_fc1, shipped = _load_best_s(ns, depth, C, dev, bits)
