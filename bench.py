@@ -51,6 +51,8 @@ def parse_args():
     ap.add_argument("--no-generation", action="store_true",
                     help="skip the images/sec leg (tools/var_generate.py: a full VAR generation pass around the hot path)")
     ap.add_argument("--gen-iters", type=int, default=3)
+    ap.add_argument("--no-search", action="store_true", help="skip the format-search leg (BASELINE configs[4] on a bounded unit list)")
+    ap.add_argument("--search-blocks", type=int, default=2, help="transformer blocks whose four layers the search leg scores (the full sweep has 30)")
     ap.add_argument("--no-reference-legs", action="store_true",
                     help="skip reference_gpu_path / generation_reference_model (the unmodified reference from baseline/_ref on this GPU)")
     ap.add_argument("--no-other-configs", action="store_true",
@@ -385,13 +387,72 @@ def other_configs(args):
             continue
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--workload", wl, "--steps", "10", "--warmup", "3", "--no-e2e", "--no-cpu",
-                                "--no-generation", "--no-reference-legs", "--no-other-configs"], capture_output=True, text=True, timeout=300)
+                                "--no-generation", "--no-reference-legs", "--no-other-configs", "--no-search"], capture_output=True, text=True, timeout=300)
             d = json.loads(r.stdout.strip().splitlines()[-1])
             out[wl] = {"value": d["value"], "unit": d["unit"], "ms_per_step": d["ms_per_step"], "frac_of_measured_peak": d["value"] / d["roofline"]["peak"],
                        "desc": d["config"]["desc"], "kernels": {k: v["GB/s"] for k, v in d["kernels"].items()}}
         except Exception as e:  # noqa: BLE001
             out[wl] = {"error": f"{type(e).__name__}: {e}"}
     return out
+
+
+def search_leg(torch, dist, dev, rank, world, blocks, depth=30, acts=1000):
+    """BASELINE configs[4] (FP4 format search, search/search_fp4_format.py:781-836) on a BOUNDED unit list: the four layers
+    of `blocks` VAR-d30 blocks (the full sweep has 30), random-init weights, the reference's calibration shapes (per layer 1000
+    tensors [2, pn^2, C_in] = 136 000 rows; N(0,1), GELU-skewed for fc2), candidates {e1m2, e2m1, e3m0} x {e1m2, e2m1, e3m0}.
+    (layer, weight-format) units are dealt round-robin to the ranks (strong scaling: the unit list does not grow with N),
+    every rank scores its units with fpqvar_b200.search.search_layer_batched (fused quantizers, library GEMMs, fused
+    squared-error reduction) and ONE all-reduce of the [layers, 3, 3] float64 table ends the sweep.  CUDA events, max over ranks."""
+    from fpqvar_b200 import search
+    C = 64 * depth
+    patch = (1, 2, 3, 4, 5, 6, 8, 10, 13, 16)
+    rows = [2 * patch[j % 10] ** 2 for j in range(acts)]
+    shapes = {"mat_qkv": (3 * C, C, torch.float32, False), "proj": (C, C, torch.float16, False),
+              "fc1": (4 * C, C, torch.float32, False), "fc2": (C, 4 * C, torch.float16, True)}
+    names = [(b, n) for b in range(blocks) for n in shapes]
+    units = [(li, wi) for li in range(len(names)) for wi in range(len(search.FP4_FORMATS))]
+    mine = [units[u] for u in range(rank, len(units), world)]
+    table = torch.zeros(len(names), 3, 3, dtype=torch.float64, device=dev)
+
+    def layer(li):
+        b, n = names[li]
+        o, i, dt, gelu = shapes[n]
+        g = torch.Generator(device=dev).manual_seed(1000 * b + list(shapes).index(n))       # the same data on whichever rank owns the unit
+        w = (torch.randn(o, i, device=dev, generator=g) * 0.02).to(dt)
+        x = torch.randn(sum(rows), i, device=dev, generator=g)
+        if gelu:
+            x = torch.nn.functional.gelu(x, approximate="tanh")
+        return w, list(x.to(dt).split(rows))
+
+    def run():
+        table.zero_()
+        cur, data = None, None
+        for li, wi in mine:
+            if li != cur:
+                cur, data = li, layer(li)
+            table[li, wi] = search.search_layer_batched(data[0], data[1], [search.FP4_FORMATS[wi]], search.FP4_FORMATS)[0]
+        if world > 1:
+            dist.all_reduce(table)
+
+    run()                                           # warm-up (cuBLAS heuristics, allocator)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs = float(t.item())
+    best = [search.best_formats(table[li], search.FP4_FORMATS, search.FP4_FORMATS) for li in range(len(names))]
+    return {"seconds": secs, "units": len(units), "units_per_sec": len(units) / secs, "layers": len(names), "scaling": "strong",
+            "calibration_rows_per_layer": sum(rows), "activations_per_layer": acts,
+            "desc": f"FP4 format search, {blocks} of {depth} VAR-d30 blocks x 4 layers x 3 weight formats = {len(units)} units over {world} rank(s); "
+                    "per unit: 3 activation formats, output-level loss over 1000 row-stacked calibration tensors",
+            "winners": {f"blocks.{b}.{n}": f"w={best[i]['weight_format']},a={best[i]['activation_format']}" for i, (b, n) in enumerate(names)}}
 
 
 def main():
@@ -522,15 +583,17 @@ def main():
     # ---- e2e: host buffers through HostPipeline ----------------------------------------------
     e2e = None
     if not args.no_e2e:
+        from fpqvar_b200.hotpath import bind_to_gpu_numa
+        numa_cpus = bind_to_gpu_numa(local_rank)          # before the pinned buffers exist: first touch places them on the GPU's node
         max_in = max(c.in_bytes for c in calls)
         max_out = max(c.out_bytes for c in calls)
-        pipe = HostPipeline(dev, max_in, max_out, smooth, modulate=modulate)
+        pipe = HostPipeline(dev, max_in, max_out, smooth, modulate=modulate, slots=3)
         h_f32 = torch.randn(max(c.in_bytes for c in calls if c.in_dtype == "f32") // 4 if any(c.in_dtype == "f32" for c in calls) else 1).pin_memory()
         h_f16 = torch.nn.functional.gelu(torch.randn(max(c.in_bytes for c in calls if c.in_dtype == "f16") // 2), approximate="tanh").to(torch.float16).pin_memory()
-        h_out = [torch.empty(max_out, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        h_out = [torch.empty(max_out, dtype=torch.uint8).pin_memory() for _ in range(3)]
         v32, v16 = h_f32.view(torch.uint8), h_f16.view(torch.uint8)
         hin = [v32 if c.in_dtype == "f32" else v16 for c in calls]
-        hout = [h_out[i % 2] for i in range(len(calls))]
+        hout = [h_out[i % 3] for i in range(len(calls))]
         pipe.run(calls[: 4 * hot.depth], hin, hout)        # warm-up: the first stage
         pipe.synchronize()
         n_e2e = max(1, args.e2e_steps)
@@ -550,13 +613,22 @@ def main():
         e2e = {"value": world * n_e2e * step_bytes / t_e2e / 1e9, "unit": UNIT, "h2d_bytes_per_step": world * in_bytes,
                "d2h_bytes_per_step": world * out_bytes, "steps": n_e2e, "ms_per_step": t_e2e / n_e2e * 1e3,
                "api": "fpqvar_b200.hotpath.HostPipeline.run (pinned host buffers -> C ABI -> pinned host buffers)",
-               "launches": e2e_launches}
+               "launches": e2e_launches, "host_binding": f"rank bound to its GPU's NUMA node (cpus {numa_cpus})" if numa_cpus else "no NUMA information: unbound",
+               "staging_slots": 3}
         del pipe
 
     # ---- images/sec: the caller around the hot path --------------------
     generation = None
     if not args.no_generation:
         generation = generation_leg(torch, dist, dev, hot, args.gen_iters, rank, world)
+
+    # ---- format search (BASELINE configs[4]) on a bounded unit list, sharded over the ranks -------------------------
+    search_res = None
+    if not args.no_search and hot.depth == 30:
+        try:
+            search_res = search_leg(torch, dist, dev, rank, world, args.search_blocks)
+        except Exception as e:  # noqa: BLE001
+            search_res = {"error": f"{type(e).__name__}: {e}"}
 
     # ---- the reference's own GPU path and its own model on this box (rank 0, N=1; outside every timed region above) ----
     reference_gpu = generation_ref = other = None
@@ -584,9 +656,9 @@ def main():
         def kernel_name(key):
             op, fmt, din, dout = key
             if op == "rotate_quant":
-                return f"transform_rotate_quant_{{tma,small}}_kernel<{fmt}> (f32->f16)"
+                return f"transform_rotate_quant_{{stream,small}}_kernel<{fmt}> (f32->f16)"
             if op == "mod_rotate_quant":
-                return f"modulate_transform_rotate_quant_{{tma,small}}_kernel<{fmt}> (adaLN modulate fused, f32->f16)"
+                return f"modulate_transform_rotate_quant_{{stream,small}}_kernel<{fmt}> (adaLN modulate fused, f32->f16)"
             packed = din == "f16" and dout == "f16"
             base = {"group": "fake_quant_group", "signsplit": "signsplit_group"}[op]
             return f"{base}_h16_kernel<{fmt}> (f16->f16)" if packed else f"{base}_kernel<{din}->{dout},{fmt}>"
@@ -617,6 +689,8 @@ def main():
             line["e2e"] = e2e
         if generation is not None:
             line["generation"] = generation
+        if search_res is not None:
+            line["search"] = search_res
         if reference_gpu is not None:
             line["reference_gpu_path"] = reference_gpu
         if generation_ref is not None:

@@ -44,6 +44,9 @@ SIGNATURES = {
                                                _c.c_void_p]),
     "fpq_score_formats": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_void_p, _c.c_int, _c.c_int,
                                      _c.c_void_p, _c.c_void_p]),
+    "fpq_gelu_fake_quant_signsplit": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_int, _c.c_uint, _c.c_void_p, _c.c_void_p]),
+    "fpq_selftest_gelu": (_c.c_int, [_c.c_void_p, _c.c_void_p]),
+    "fpq_sse_rows": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
     "fpq_selftest_rounding": (_c.c_int, [_c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "fpq_selftest_f16_flow": (_c.c_int, [_c.c_int, _c.c_void_p, _c.c_void_p]),
 }
@@ -68,7 +71,7 @@ def lib() -> ctypes.CDLL:
             try:
                 fn = getattr(handle, name)    # AttributeError here = header and library out of sync
             except AttributeError:
-                if os.environ.get("FPQ_LIB_PATH") and name in ("fpq_set_tunable", "fpq_rotate_plan", "fpq_fake_quant_segments"):
+                if os.environ.get("FPQ_LIB_PATH") and name in ("fpq_set_tunable", "fpq_rotate_plan", "fpq_fake_quant_segments", "fpq_sse_rows", "fpq_gelu_fake_quant_signsplit", "fpq_selftest_gelu"):
                     continue                  # an older build selected for an A/B measurement (tools/): it has no tunables
                 raise
             fn.restype = res

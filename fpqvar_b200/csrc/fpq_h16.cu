@@ -239,7 +239,26 @@ __device__ __forceinline__ void poison_epilogue(__half* __restrict__ out, size_t
     if (threadIdx.x == 0) { ws[0] = 0u; ws[1] = 0u; }
 }
 
-template <int SPLIT>
+// GELU(tanh) of an fp16 value the way ATen's CUDA kernel computes it for a Half tensor (ActivationGeluKernel.cu,
+// GeluCUDAKernelImpl, approximate = "tanh": opmath float, the constants below, libdevice tanhf, one rounding to fp16 at the
+// end) -- what `self.act(self.fc1(x))` produces under the reference's fp16 autocast (basic_var.py:108,120).  The expression
+// is written like ATen's so that nvcc contracts it the same way; fpq_selftest_gelu compares it with a tensor of torch's own
+// outputs for all 65 536 fp16 inputs.
+__device__ __forceinline__ float gelu_tanh_f32(float x) {
+    constexpr float kBeta = float(1.4142135623730951 * 1.1283791670955126 * 0.5);     // M_SQRT2 * M_2_SQRTPI * 0.5
+    constexpr float kKappa = 0.044715f;
+    const float x_cube = x * x * x;
+    const float inner = kBeta * (x + kKappa * x_cube);
+    return 0.5f * x * (1.0f + tanhf(inner));
+}
+__device__ __forceinline__ uint32_t gelu_tanh_h2(uint32_t x2) {
+    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&x2));
+    return pack_h2(gelu_tanh_f32(f.x), gelu_tanh_f32(f.y));
+}
+
+// GELU = true: out = signsplit_quant(gelu_tanh(x)) in one pass (fpq_gelu_fake_quant_signsplit): the fc2 input of the
+// reference, `fc2.act_quant(self.act(self.fc1(x)))`, without the round trip of the activation tensor through HBM.
+template <int SPLIT, bool GELU>
 __global__ void __launch_bounds__(256) signsplit_group_h16_kernel(const __half* __restrict__ x, __half* __restrict__ out, size_t n_groups,
                                                                   unsigned* __restrict__ nan_flag) {
     pdl_launch_dependents();
@@ -254,6 +273,10 @@ __global__ void __launch_bounds__(256) signsplit_group_h16_kernel(const __half* 
         const size_t g = gbase + lane / H16_LPG;
         if (g < n_groups) {
             load_tile_h16(x + g * 128, lig, p);
+            if constexpr (GELU) {
+#pragma unroll
+                for (int i = 0; i < H16_NW; ++i) p[i] = gelu_tanh_h2(p[i]);
+            }
         } else {
 #pragma unroll
             for (int i = 0; i < H16_NW; ++i) p[i] = 0u;
@@ -266,9 +289,13 @@ __global__ void __launch_bounds__(256) signsplit_group_h16_kernel(const __half* 
         const int rc = split_quant_tile_h16<SPLIT, H16_LPG, H16_NW>(p, sn, sp, delta);
         if (rc == 2 && nan_flag != nullptr) atomicOr(nan_flag, 1u);
         if (g < n_groups) {
-            if (rc == 0) store_tile_h16(out + g * 128, lig, p);
-            else if (rc == 1) literal_split_h16(x + g * 128, out + g * 128, lig, H16_LPG, 8, H16_NV, sn, sp, SF::GT_N, SF::GT_P);
-            else literal_split_nan_group_h16(x + g * 128, out + g * 128, lig, H16_LPG, 8, H16_NV, SF::NEG::VMAX, SF::POS::VMAX, SF::GT_N, SF::GT_P);
+            // rc != 0 leaves p untouched.  The literal sequences work from memory: with GELU fused in, the activated tile goes
+            // to `out` first and is quantized there in place (all lanes of the group store before any of them rescans it)
+            const __half* src = x + g * 128;
+            if (GELU || rc == 0) store_tile_h16(out + g * 128, lig, p);
+            if (GELU && rc != 0) { __syncwarp(); src = out + g * 128; }
+            if (rc == 1) literal_split_h16(src, out + g * 128, lig, H16_LPG, 8, H16_NV, sn, sp, SF::GT_N, SF::GT_P);
+            else if (rc == 2) literal_split_nan_group_h16(src, out + g * 128, lig, H16_LPG, 8, H16_NV, SF::NEG::VMAX, SF::POS::VMAX, SF::GT_N, SF::GT_P);
         }
     };
     for (size_t gbase = warp_global * H16_GPW; gbase < n_groups; gbase += stride) {
@@ -314,17 +341,27 @@ int launch_sym_h16_g64(int format, const void* x, void* out, size_t n_groups, cu
     return finish_launch();
 }
 
-int launch_split_h16(int split, const void* x, void* out, size_t n_groups, unsigned* nan_flag, cudaStream_t st) {
+template <bool GELU>
+static int launch_split_h16_t(int split, const void* x, void* out, size_t n_groups, unsigned* nan_flag, cudaStream_t st) {
     const __half* xi = static_cast<const __half*>(x);
     __half* oo = static_cast<__half*>(out);
     const unsigned grid = grid_h16(n_groups);
     switch (split) {
-        case FPQ_SPLIT_E1M2NEG_E2M1POS: launch_pdl(signsplit_group_h16_kernel<FPQ_SPLIT_E1M2NEG_E2M1POS>, grid, 256, 0, st, xi, oo, n_groups, nan_flag); break;
-        case FPQ_SPLIT_INTNEG_E2M3POS: launch_pdl(signsplit_group_h16_kernel<FPQ_SPLIT_INTNEG_E2M3POS>, grid, 256, 0, st, xi, oo, n_groups, nan_flag); break;
-        case FPQ_SPLIT_AFPQ_E2M1: launch_pdl(signsplit_group_h16_kernel<FPQ_SPLIT_AFPQ_E2M1>, grid, 256, 0, st, xi, oo, n_groups, nan_flag); break;
+        case FPQ_SPLIT_E1M2NEG_E2M1POS: launch_pdl(signsplit_group_h16_kernel<FPQ_SPLIT_E1M2NEG_E2M1POS, GELU>, grid, 256, 0, st, xi, oo, n_groups, nan_flag); break;
+        case FPQ_SPLIT_INTNEG_E2M3POS: launch_pdl(signsplit_group_h16_kernel<FPQ_SPLIT_INTNEG_E2M3POS, GELU>, grid, 256, 0, st, xi, oo, n_groups, nan_flag); break;
+        case FPQ_SPLIT_AFPQ_E2M1: launch_pdl(signsplit_group_h16_kernel<FPQ_SPLIT_AFPQ_E2M1, GELU>, grid, 256, 0, st, xi, oo, n_groups, nan_flag); break;
         default: return FPQ_ERR_ARG;
     }
     return finish_launch();
+}
+int launch_split_h16(int split, const void* x, void* out, size_t n_groups, unsigned* nan_flag, cudaStream_t st) {
+    return launch_split_h16_t<false>(split, x, out, n_groups, nan_flag, st);
+}
+
+// all 65 536 fp16 inputs through gelu_tanh_f32 -> fp16 (the table the GPU test compares with torch's own GELU output)
+__global__ void gelu_table_kernel(__half* __restrict__ out) {
+    const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 65536u) out[i] = __float2half_rn(gelu_tanh_f32(__half2float(__ushort_as_half(uint16_t(i)))));
 }
 
 // ------------------------------------------------------------------------------------------
@@ -476,4 +513,21 @@ extern "C" int fpq_fake_quant_segments(const void* x, void* out, size_t n_segmen
     __half* oo = static_cast<__half*>(out);
     if (row_len == 64) return launch_segments_h16<64>(format, xi, oo, n_segments, rows_per_segment, pitch_x, pitch_out, st);
     return launch_segments_h16<128>(format, xi, oo, n_segments, rows_per_segment, pitch_x, pitch_out, st);
+}
+
+extern "C" int fpq_gelu_fake_quant_signsplit(const void* x, void* out, size_t n_groups, int split_format, unsigned flags, void* workspace, void* stream) {
+    if (n_groups && (!x || !out || x == out)) return FPQ_ERR_ARG;
+    if (flags & ~FPQ_FLAG_GLOBAL_CLIP) return FPQ_ERR_ARG;
+    if ((flags & FPQ_FLAG_GLOBAL_CLIP) && !workspace) return FPQ_ERR_ARG;
+    if (split_format < 0 || split_format >= FPQ_NUM_SPLIT_FORMATS) return FPQ_ERR_ARG;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) return FPQ_ERR_ARG;
+    if (n_groups == 0) return FPQ_OK;
+    unsigned* flag = (flags & FPQ_FLAG_GLOBAL_CLIP) ? static_cast<unsigned*>(workspace) : nullptr;
+    return launch_split_h16_t<true>(split_format, x, out, n_groups, flag, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int fpq_selftest_gelu(void* table_65536_halves, void* stream) {
+    if (!table_65536_halves) return FPQ_ERR_ARG;
+    gelu_table_kernel<<<256, 256, 0, static_cast<cudaStream_t>(stream)>>>(static_cast<__half*>(table_65536_halves));
+    return finish_launch();
 }

@@ -109,10 +109,10 @@ template <class HG> struct Magic {
 #ifndef FPQ_HWCVT
 #define FPQ_HWCVT 0          // 1: use the conversion hardware (measured: slower, see the header comment); 0: magic-number FFMA
 #endif
-template <class HG> struct HwCvt { static constexpr bool OK = false; static constexpr float PRE = 1.0f; static constexpr uint32_t S_MAX_BITS = 0x7BFFu; };
-#if FPQ_HWCVT
+template <class HG> struct HwCvt { static constexpr bool AVAILABLE = false; static constexpr bool OK = false; static constexpr float PRE = 1.0f; static constexpr uint32_t S_MAX_BITS = 0x7BFFu; };
 template <> struct HwCvt<HG_E2M1> {
-    static constexpr bool OK = true;
+    static constexpr bool AVAILABLE = true;
+    static constexpr bool OK = FPQ_HWCVT != 0;
     static constexpr float PRE = 1.0f;
     static constexpr uint32_t S_MAX_BITS = 0x7BFFu;
     static __device__ __forceinline__ uint32_t round_trip(float w0, float w1) {
@@ -122,7 +122,8 @@ template <> struct HwCvt<HG_E2M1> {
     }
 };
 template <> struct HwCvt<HG_E2M3> {
-    static constexpr bool OK = true;
+    static constexpr bool AVAILABLE = true;
+    static constexpr bool OK = FPQ_HWCVT != 0;
     static constexpr float PRE = 1.0f;
     static constexpr uint32_t S_MAX_BITS = 0x7BFFu;
     static __device__ __forceinline__ uint32_t round_trip(float w0, float w1) {
@@ -132,7 +133,8 @@ template <> struct HwCvt<HG_E2M3> {
     }
 };
 template <> struct HwCvt<HG_E3M2> {
-    static constexpr bool OK = true;
+    static constexpr bool AVAILABLE = true;
+    static constexpr bool OK = FPQ_HWCVT != 0;
     static constexpr float PRE = 1.0f;
     static constexpr uint32_t S_MAX_BITS = 0x7BFFu;
     static __device__ __forceinline__ uint32_t round_trip(float w0, float w1) {
@@ -142,13 +144,12 @@ template <> struct HwCvt<HG_E3M2> {
     }
 };
 template <> struct HwCvt<HG_E1M2> {
-    static constexpr bool OK = true;
+    static constexpr bool AVAILABLE = true;
+    static constexpr bool OK = FPQ_HWCVT != 0;
     static constexpr float PRE = 0.5f;
-    static constexpr uint32_t S_MAX_BITS = 0x77FFu;          // 2 * s stays finite
+    static constexpr uint32_t S_MAX_BITS = 0x77FFu;          // 2 * s stays finite (callers that use the conversion hardware check it)
     static __device__ __forceinline__ uint32_t round_trip(float w0, float w1) { return HwCvt<HG_E2M3>::round_trip(w0, w1); }
 };
-
-#endif
 
 // Any other half grid: q = R_K(w) by a magic-number FFMA, as packed fp32.
 __device__ __forceinline__ uint64_t round_pair_magic(float w0, float w1, float em, float sc) {
@@ -168,10 +169,10 @@ struct SymK {
 template <class HG>
 __device__ __forceinline__ SymK make_symk(float s, float r) {
     SymK k;
-    const float rr = r * HwCvt<HG>::PRE;                                  // power of two: exact
+    const float rr = r * (HwCvt<HG>::OK ? HwCvt<HG>::PRE : 1.0f);                                  // power of two: exact
     k.r2 = pk(rr, rr);
     k.s2 = pk(s, s);
-    k.sh2 = dup_h(__float2half_rn(s * (1.0f / HwCvt<HG>::PRE)));          // s is an fp16 value <= S_MAX_BITS: exact
+    k.sh2 = dup_h(__float2half_rn(s * (1.0f / (HwCvt<HG>::OK ? HwCvt<HG>::PRE : 1.0f))));          // s is an fp16 value <= S_MAX_BITS: exact
     return k;
 }
 
@@ -211,7 +212,7 @@ __device__ __forceinline__ float rcp_rn_normal(float s) {
 }
 // "regular" on fp16 bits: 0x0400 <= bits <= 0x7BFF (normal, finite, positive)
 __device__ __forceinline__ bool scale_bits_regular(uint32_t sb) { return sb - 0x0400u < 0x7800u; }
-template <class HG> __device__ __forceinline__ bool scale_bits_regular_for(uint32_t sb) { return sb - 0x0400u <= HwCvt<HG>::S_MAX_BITS - 0x0400u; }
+template <class HG> __device__ __forceinline__ bool scale_bits_regular_for(uint32_t sb) { return sb - 0x0400u <= (HwCvt<HG>::OK ? HwCvt<HG>::S_MAX_BITS : 0x7BFFu) - 0x0400u; }
 
 // absmax of NW packed words as an fp16 bit pattern, one HMNMX2.NAN on |a|, |b| per word.  A NaN anywhere
 // comes out as a NaN pattern (> 0x7C00), exactly like torch's abs().max().

@@ -175,33 +175,62 @@ __device__ __forceinline__ void sq_err_pair(uint32_t x2, uint32_t o2, float& acc
 }
 
 template <int FMT>
-__device__ __forceinline__ float sse_sym_h16(const uint32_t (&p)[16], const uint64_t (&xf)[16], uint32_t absmax_b, float delta) {
+__device__ __forceinline__ float sse_sym_h16(const uint32_t (&p)[16], const uint64_t (&xf)[16], uint32_t absmax_b, float delta, const __half* src, int lig) {
     using HG = typename SymFmt<FMT>::HG;
     const float a = h2f(uint16_t(absmax_b));
     const __half sh = scale_from_absmax_h16<HG>(a);
     float acc0 = 0.0f, acc1 = 0.0f;
-    if (scale_bits_regular_for<HG>(__half_as_ushort(sh))) {
-        const float s = __half2float(sh);
-        const SymK k = make_symk<HG>(s, rcp_rn_normal(s));
+    const uint32_t sb = __half_as_ushort(sh);
+    if constexpr (HwCvt<HG>::AVAILABLE) {
+        // Formats the FP4 / FP6 conversion hardware knows (e2m1, e2m3, e3m2; e1m2 as the uniform low end of e2m3): 7
+        // instructions per pair and candidate.  The score needs the squared DISTANCE to the nearest grid point, not the grid
+        // point itself, so the fp16 rounding of x/s and the tie shift of the quantizer kernels are skipped: they only decide
+        // which of two EQUIDISTANT neighbours an exact midpoint goes to (the error is the same either way), and a value that the
+        // fp16 rounding would carry across a midpoint is within 2^-11 of it (its squared error changes by < 2^-9 relative on
+        // an element that occurs with probability ~2^-10: far inside the 2e-6 tolerance of the sums).
+        if (sb - 0x0400u <= HwCvt<HG>::S_MAX_BITS - 0x0400u) {
+            const float s = __half2float(sh);
+            const float rr = rcp_rn_normal(s) * HwCvt<HG>::PRE;
+            const uint64_t r2 = pk(rr, rr);
+            const uint32_t sh2 = dup_h(__float2half_rn(s * (1.0f / HwCvt<HG>::PRE)));
 #pragma unroll
-        for (int i = 0; i < 16; ++i) sq_err_pair(p[i], sym_pair_h16_w<HG>(xf[i], k, delta), acc0, acc1);
+            for (int i = 0; i < 16; ++i) {
+                const F2 v = unpk(fmul2(xf[i], r2));
+                sq_err_pair(p[i], hfma2(HwCvt<HG>::round_trip(v.lo, v.hi), sh2, 0u), acc0, acc1);
+            }
+            return acc0 + acc1;
+        }
     } else {
+        if (scale_bits_regular(sb)) {
+            const float s = __half2float(sh);
+            const float r = rcp_rn_normal(s);
+            const uint64_t r2 = pk(r, r), s2 = pk(s, s);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const uint32_t v2 = pack_h2_u64(fmul2(xf[i], r2));                            // half(x/s)
+                const uint64_t q = round_pair_magic(fhadd(uint16_t(v2 & 0xffffu), delta), fhadd(uint16_t(v2 >> 16), delta), Magic<HG>::EM, Magic<HG>::SC);
+                sq_err_pair(p[i], pack_h2_u64(fmul2(q, s2)), acc0, acc1);
+            }
+            return acc0 + acc1;
+        }
+    }
+    {
+        // irregular scale (zero / subnormal / inf / NaN): the literal reference sequence, element by element FROM MEMORY (indexing
+        // the register tile with a loop counter would push it into local memory for the whole kernel)
         const float s = rnd_in<__half>(__fdiv_rn(a, HG::VMAX));
         const GridTable& gt = c_grids[SymFmt<FMT>::GT];
 #pragma unroll 1
-        for (int i = 0; i < 16; ++i) {
-            const F2 f = unpk(xf[i]);
-            const float d0 = f.lo - rnd_in<__half>(quant_elem_literal<__half, TIE_KERNEL>(f.lo, s, gt) * s);
-            const float d1 = f.hi - rnd_in<__half>(quant_elem_literal<__half, TIE_KERNEL>(f.hi, s, gt) * s);
-            acc0 = fmaf(d0, d0, acc0);
-            acc1 = fmaf(d1, d1, acc1);
+        for (int k = 0; k < 32; ++k) {
+            const float f = __half2float(src[((k >> 3) * 4 + lig) * 8 + (k & 7)]);
+            const float d = f - rnd_in<__half>(quant_elem_literal<__half, TIE_KERNEL>(f, s, gt) * s);
+            acc0 = fmaf(d, d, acc0);
         }
     }
     return acc0 + acc1;
 }
 
 template <int SPLIT>
-__device__ __forceinline__ float sse_split_h16(const uint32_t (&p)[16], const uint64_t (&xf)[16], uint32_t pbits, uint32_t nbits, float delta) {
+__device__ __forceinline__ float sse_split_h16(const uint32_t (&p)[16], const uint64_t (&xf)[16], uint32_t pbits, uint32_t nbits, float delta, const __half* src, int lig) {
     using SF = SplitFmtS<SPLIT>;
     const float an = h2f(uint16_t(nbits)), ap = h2f(uint16_t(pbits));
     const __half snh = scale_from_absmax_h16<typename SF::NEG>(an), sph = scale_from_absmax_h16<typename SF::POS>(ap);
@@ -221,11 +250,10 @@ __device__ __forceinline__ float sse_split_h16(const uint32_t (&p)[16], const ui
             return rnd_in<__half>(__fadd_rn(__fmul_rn(qn, sn), __fmul_rn(qp, sp)));
         };
 #pragma unroll 1
-        for (int i = 0; i < 16; ++i) {
-            const F2 f = unpk(xf[i]);
-            const float d0 = f.lo - lit(f.lo), d1 = f.hi - lit(f.hi);
-            acc0 = fmaf(d0, d0, acc0);
-            acc1 = fmaf(d1, d1, acc1);
+        for (int k = 0; k < 32; ++k) {
+            const float f = __half2float(src[((k >> 3) * 4 + lig) * 8 + (k & 7)]);
+            const float d = f - lit(f);
+            acc0 = fmaf(d, d, acc0);
         }
     }
     return acc0 + acc1;
@@ -266,7 +294,7 @@ __global__ void __launch_bounds__(256) score_formats_h16_kernel(const __half* __
         if (amax > 0x7C00u) {
             // a NaN in the group: where() turns it into 0 on both sides of a sign-split format; redo those two maxima
             float an = 0.0f, ap = 0.0f;
-#pragma unroll 1
+#pragma unroll
             for (int i = 0; i < 16; ++i) {
                 const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&p[i]));
                 an = fmaxf(an, fmaxf((f.x <= 0.0f) ? -f.x : 0.0f, (f.y <= 0.0f) ? -f.y : 0.0f));
@@ -278,19 +306,22 @@ __global__ void __launch_bounds__(256) score_formats_h16_kernel(const __half* __
         uint64_t xf[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) xf[i] = widen_h2(p[i]);
+        const bool live = g < n_groups;
+        const __half* src = x + (live ? g : 0) * 128;                // the literal fallbacks read the group from memory; a dead lane set's result is dropped
 #pragma unroll 1
         for (int c = 0; c < cand.n; ++c) {
             float e;
             switch (cand.fmt[c]) {
-                case FPQ_FMT_E2M1: e = sse_sym_h16<FPQ_FMT_E2M1>(p, xf, amax, delta); break;
-                case FPQ_FMT_E1M2: e = sse_sym_h16<FPQ_FMT_E1M2>(p, xf, amax, delta); break;
-                case FPQ_FMT_E3M0: e = sse_sym_h16<FPQ_FMT_E3M0>(p, xf, amax, delta); break;
-                case FPQ_FMT_E2M3: e = sse_sym_h16<FPQ_FMT_E2M3>(p, xf, amax, delta); break;
-                case FPQ_FMT_E3M2: e = sse_sym_h16<FPQ_FMT_E3M2>(p, xf, amax, delta); break;
-                case 16 + FPQ_SPLIT_E1M2NEG_E2M1POS: e = sse_split_h16<FPQ_SPLIT_E1M2NEG_E2M1POS>(p, xf, pbits, nbits, delta); break;
-                case 16 + FPQ_SPLIT_INTNEG_E2M3POS: e = sse_split_h16<FPQ_SPLIT_INTNEG_E2M3POS>(p, xf, pbits, nbits, delta); break;
-                default: e = sse_split_h16<FPQ_SPLIT_AFPQ_E2M1>(p, xf, pbits, nbits, delta); break;
+                case FPQ_FMT_E2M1: e = sse_sym_h16<FPQ_FMT_E2M1>(p, xf, amax, delta, src, lig); break;
+                case FPQ_FMT_E1M2: e = sse_sym_h16<FPQ_FMT_E1M2>(p, xf, amax, delta, src, lig); break;
+                case FPQ_FMT_E3M0: e = sse_sym_h16<FPQ_FMT_E3M0>(p, xf, amax, delta, src, lig); break;
+                case FPQ_FMT_E2M3: e = sse_sym_h16<FPQ_FMT_E2M3>(p, xf, amax, delta, src, lig); break;
+                case FPQ_FMT_E3M2: e = sse_sym_h16<FPQ_FMT_E3M2>(p, xf, amax, delta, src, lig); break;
+                case 16 + FPQ_SPLIT_E1M2NEG_E2M1POS: e = sse_split_h16<FPQ_SPLIT_E1M2NEG_E2M1POS>(p, xf, pbits, nbits, delta, src, lig); break;
+                case 16 + FPQ_SPLIT_INTNEG_E2M3POS: e = sse_split_h16<FPQ_SPLIT_INTNEG_E2M3POS>(p, xf, pbits, nbits, delta, src, lig); break;
+                default: e = sse_split_h16<FPQ_SPLIT_AFPQ_E2M1>(p, xf, pbits, nbits, delta, src, lig); break;
             }
+            if (!live) e = 0.0f;
             // 32 lanes x 32 elements in fp32, then one fp64 add per warp, trip and candidate
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) e += __shfl_xor_sync(0xffffffffu, e, o);
@@ -301,9 +332,86 @@ __global__ void __launch_bounds__(256) score_formats_h16_kernel(const __half* __
     if (threadIdx.x < cand.n) atomicAdd(&sse[threadIdx.x], s_acc[threadIdx.x]);
 }
 
+// ------------------------------------------------------------------------------------------
+// Output-level loss of the search (search_fp4_format.py:472-476 `compute_quant_error(y_fp, y_q)` inside the loop :798-816):
+//     out += sum_r w[r] * sum_c (a[r, c] - b[r, c])^2
+// in ONE read of the two matrices: no difference tensor, no squared tensor, no per-row partial tensor (the ATen sequence
+// sub_ -> float -> square_ -> sum(dim=1) -> dot moves the [rows, C_out] matrix through HBM nine times).  w[r] carries
+// the 1 / (rows_j * C_out * J) of the per-tensor means when the calibration set is row-stacked (search_layer_batched);
+// NULL = 1.  One warp per row slice, 128-bit loads, fp32 within a lane's 8..16 products, fp64 from there on.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) sse_rows_kernel(const T* __restrict__ a, const T* __restrict__ b, size_t n_rows, size_t n_cols,
+                                                       const double* __restrict__ w, double* __restrict__ out) {
+    constexpr int VEC = 16 / sizeof(T);
+    __shared__ double s_acc;
+    if (threadIdx.x == 0) s_acc = 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const size_t warp_global = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+    const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
+    const size_t vecs_per_row = n_cols / VEC;
+    double acc = 0.0;
+    for (size_t r = warp_global; r < n_rows; r += n_warps) {
+        const T* ar = a + r * n_cols;
+        const T* br = b + r * n_cols;
+        double row = 0.0;
+        for (size_t v0 = 0; v0 < vecs_per_row; v0 += 64) {             // two independent 128-bit loads per lane and matrix in flight
+            float part = 0.0f;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+                const size_t v = v0 + size_t(k) * 32 + lane;
+                if (v < vecs_per_row) {
+                    const uint4 ua = ldg_stream(ar + v * VEC), ub = ldg_stream(br + v * VEC);
+                    if constexpr (sizeof(T) == 2) {
+                        const uint32_t wa[4] = {ua.x, ua.y, ua.z, ua.w}, wb[4] = {ub.x, ub.y, ub.z, ub.w};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 fa = __half22float2(*reinterpret_cast<const __half2*>(&wa[i]));
+                            const float2 fb = __half22float2(*reinterpret_cast<const __half2*>(&wb[i]));
+                            const float d0 = fa.x - fb.x, d1 = fa.y - fb.y;
+                            part = fmaf(d0, d0, part);
+                            part = fmaf(d1, d1, part);
+                        }
+                    } else {
+                        const float fa[4] = {__uint_as_float(ua.x), __uint_as_float(ua.y), __uint_as_float(ua.z), __uint_as_float(ua.w)};
+                        const float fb[4] = {__uint_as_float(ub.x), __uint_as_float(ub.y), __uint_as_float(ub.z), __uint_as_float(ub.w)};
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float d = fa[i] - fb[i];
+                            part = fmaf(d, d, part);
+                        }
+                    }
+                }
+            }
+            row += double(part);
+        }
+        acc += row * (w != nullptr ? w[r] : 1.0);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) atomicAdd(&s_acc, acc);
+    __syncthreads();
+    if (threadIdx.x == 0) atomicAdd(out, s_acc);
+}
+
 }  // namespace fpq
 
 using namespace fpq;
+
+extern "C" int fpq_sse_rows(const void* a, const void* b, size_t n_rows, size_t n_cols, int dtype, const double* row_weight, double* out, void* stream) {
+    if (!out || (n_rows && n_cols && (!a || !b))) return FPQ_ERR_ARG;
+    if (dtype != FPQ_F32 && dtype != FPQ_F16) return FPQ_ERR_ARG;
+    const size_t vec = dtype == FPQ_F16 ? 8 : 4;
+    if (n_cols % vec) return FPQ_ERR_UNSUPPORTED;                  // whole 16-byte vectors per row (every C_out of the search is a multiple of 128)
+    if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) & 15) return FPQ_ERR_ARG;
+    if (n_rows == 0 || n_cols == 0) return FPQ_OK;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const unsigned grid = grid_for(n_rows, 8, 8);
+    if (dtype == FPQ_F16) sse_rows_kernel<__half><<<grid, 256, 0, st>>>(static_cast<const __half*>(a), static_cast<const __half*>(b), n_rows, n_cols, row_weight, out);
+    else sse_rows_kernel<float><<<grid, 256, 0, st>>>(static_cast<const float*>(a), static_cast<const float*>(b), n_rows, n_cols, row_weight, out);
+    return finish_launch();
+}
 
 extern "C" int fpq_score_formats(const void* x, size_t n_rows, size_t row_len, int in_dtype, const int* formats_host, int n_formats,
                                  int tie_mode, double* sse, void* stream) {

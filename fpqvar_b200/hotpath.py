@@ -34,6 +34,45 @@ def seed42_sign_bits():
     return ops.pack_sign_bits([1.0 if c == "1" else -1.0 for c in SIGN_BITS_SEED42_128])
 
 
+def gpu_numa_node(device_index: int) -> Optional[int]:
+    """NUMA node of the GPU's PCIe function (sysfs), or None when the kernel does not say (-1, single-node hosts)."""
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = torch.cuda.get_device_properties(device_index).pci_domain_id
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        with open(path) as f:
+            node = int(f.read().strip())
+        return node if node >= 0 else None
+    except Exception:  # noqa: BLE001  (no sysfs, no such attribute: nothing to bind to)
+        return None
+
+
+def bind_to_gpu_numa(device_index: int) -> Optional[str]:
+    """Pin the calling process to the CPUs of the GPU's NUMA node, so that pinned host buffers allocated AFTERWARDS are
+    first-touched on that node and the copy threads run next to it.  With one process per GPU (bench.py under torchrun) this
+    spreads the host side of the HostPipeline over the sockets instead of leaving all ranks on the launcher's node.
+    Returns the cpulist it bound to, or None when there is nothing to bind to."""
+    import os
+    node = gpu_numa_node(device_index)
+    if node is None:
+        return None
+    try:
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpulist = f.read().strip()
+        cpus = set()
+        for part in cpulist.split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0) or cpus          # stay inside the cgroup's set
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpulist
+    except Exception:  # noqa: BLE001
+        return None
+
+
 class DeviceReplay:
     """Launches :class:`Call` s on device pointers.  ``smooth``: dict site -> fp32 CUDA tensor [C]
     (the GALT factor of that site) or None.  ``modulate``: dict site -> (gain, shift), two fp32 CUDA tensors

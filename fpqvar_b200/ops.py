@@ -176,6 +176,30 @@ def fake_quant_signsplit(x: torch.Tensor, split_fmt: str, row_len: Optional[int]
                  L.FLAG_GLOBAL_CLIP if global_clip else 0, ws, od)
 
 
+def gelu_fake_quant_signsplit(x: torch.Tensor, split_fmt: str, global_clip: bool = False) -> torch.Tensor:
+    """``fake_quant_signsplit(gelu(x, approximate="tanh"), split_fmt, 128, "kernel")`` in one pass over an fp16 tensor
+    (fpq_gelu_fake_quant_signsplit): the reference's ``fc2.act_quant(self.act(self.fc1(x)))``, basic_var.py:108,120."""
+    _require_cuda(x, "gelu_fake_quant_signsplit")
+    if x.dtype != torch.float16:
+        raise L.FpqError("gelu_fake_quant_signsplit: x must be float16 (the autocast output of fc1)")
+    x = x.contiguous()
+    n_rows, _ = _rows(x, 128)
+    out = torch.empty_like(x)
+    ws = _clip_workspace(x.device) if global_clip else None
+    with _on_device(x) as _di:
+        rc = L.lib().fpq_gelu_fake_quant_signsplit(x.data_ptr(), out.data_ptr(), n_rows, L.SPLIT[split_fmt], L.FLAG_GLOBAL_CLIP if global_clip else 0,
+                                                   ws.data_ptr() if ws is not None else None, _stream(_di))
+    L.check(rc, "fpq_gelu_fake_quant_signsplit")
+    return out
+
+
+def gelu_table() -> torch.Tensor:
+    """fp16 [65536]: the library's GELU(tanh) of every fp16 bit pattern (fpq_selftest_gelu)."""
+    t = torch.empty(65536, dtype=torch.float16, device="cuda")
+    L.check(L.lib().fpq_selftest_gelu(t.data_ptr(), _stream()), "fpq_selftest_gelu")
+    return t
+
+
 def quant_grid(x: torch.Tensor, grid: torch.Tensor, tie: str = "kernel") -> torch.Tensor:
     """Nearest grid value, reference scan semantics (fpq_quant_grid). fp32 in, fp32 out."""
     _require_cuda(x, "quant_grid")
@@ -269,6 +293,30 @@ def score_formats(x: torch.Tensor, formats: Sequence[str], tie: str = "kernel", 
                                        sse.data_ptr(), _stream(_di))
     L.check(rc, "fpq_score_formats")
     return sse
+
+
+def sse_rows(a: torch.Tensor, b: torch.Tensor, row_weight: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out += sum_r w[r] * sum_c (a[r, c] - b[r, c])^2 in one read of both matrices (fpq_sse_rows): the output-level loss of
+    the format search without a difference tensor.  a, b: [rows, C] of the same dtype (fp16 | fp32); row_weight: float64
+    [rows] or None; returns / accumulates into a float64 scalar tensor."""
+    _require_cuda(a, "sse_rows")
+    _require_cuda(b, "sse_rows")
+    if a.shape != b.shape or a.dtype != b.dtype or a.dim() != 2 or a.device != b.device:
+        raise L.FpqError("sse_rows: a and b must be 2-D tensors of the same shape, dtype and device")
+    a, b = a.contiguous(), b.contiguous()
+    if row_weight is not None:
+        if not (row_weight.is_cuda and row_weight.device == a.device and row_weight.dtype == torch.float64 and row_weight.is_contiguous()
+                and row_weight.numel() == a.shape[0]):
+            raise L.FpqError(f"sse_rows: row_weight must be a contiguous float64 tensor of {a.shape[0]} entries on {a.device}")
+    if out is None:
+        out = torch.zeros((), dtype=torch.float64, device=a.device)
+    elif not (out.is_cuda and out.device == a.device and out.dtype == torch.float64 and out.numel() == 1):
+        raise L.FpqError("sse_rows: out must be one float64 element on the input's device")
+    with _on_device(a) as _di:
+        rc = L.lib().fpq_sse_rows(a.data_ptr(), b.data_ptr(), a.shape[0], a.shape[1], _dt(a, "sse_rows"),
+                                  row_weight.data_ptr() if row_weight is not None else None, out.data_ptr(), _stream(_di))
+    L.check(rc, "fpq_sse_rows")
+    return out
 
 
 def selftest_rounding(fmt_code: int, tie: str) -> tuple[int, int]:

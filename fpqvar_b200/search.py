@@ -133,8 +133,7 @@ def search_layer_batched(weight: torch.Tensor, activations: Sequence[torch.Tenso
         for ai, af in enumerate(act_formats):
             xq = quantize(xs, af, per).to(xs.dtype)
             for wi in range(len(weight_formats)):
-                d = torch.matmul(xq, wq[wi].T).sub_(y_fp)
-                loss[wi, ai] += torch.dot(d.float().square_().sum(dim=1, dtype=torch.float64), ws)
+                ops.sse_rows(torch.matmul(xq, wq[wi].T), y_fp, ws, out=loss[wi, ai])      # one read of y_q and y_fp, nothing written
     return loss
 
 

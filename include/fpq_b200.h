@@ -210,6 +210,28 @@ FPQ_API int fpq_score_formats(const void *x, size_t n_rows, size_t row_len, int 
                       double *sse, void *stream);
 
 /*
+ * GELU(tanh) + sign-split fake-quant of an fp16 tensor in one pass, groups of 128, kernel tie rule:
+ *     out = fp_quant_*_neg_*_pos_per_group_cuda( gelu(x, approximate="tanh") )
+ * i.e. `fc2.act_quant(self.act(self.fc1(x)))` of the reference (models_fp_quant_transform_rotate/basic_var.py:108,120 ->
+ * quant_utils.py:991-996) with x = the fp16 output of fc1.  The GELU reproduces ATen's CUDA kernel for Half tensors bit for bit
+ * (fpq_selftest_gelu: all 65 536 inputs).  flags / workspace as fpq_fake_quant_signsplit.  SURVEY.md section 8 f1.
+ */
+FPQ_API int fpq_gelu_fake_quant_signsplit(const void *x, void *out, size_t n_groups, int split_format,
+                   unsigned flags, void *workspace, void *stream);
+/* table[i] = fp16( gelu_tanh( fp16 bit pattern i ) ) for i in [0, 65536): the device function of the kernel above */
+FPQ_API int fpq_selftest_gelu(void *table_65536_halves, void *stream);
+
+/*
+ * Output-level loss of the format search: *out += sum_r w[r] * sum_c (a[r,c] - b[r,c])^2 over two row-major
+ * [n_rows, n_cols] matrices of the same dtype (FPQ_F32 | FPQ_F16), read once each; row_weight (float64, n_rows entries) may
+ * be NULL (= 1); out is one float64 accumulator the caller zeroes.  n_cols must fill whole 16-byte vectors.  Replaces
+ * compute_quant_error(y_fp, y_q) = mean((y_fp - y_q)^2) inside the reference's search loop
+ * (search/search_fp4_format.py:472-476, :798-816; search_fp6_format.py:807-868).
+ */
+FPQ_API int fpq_sse_rows(const void *a, const void *b, size_t n_rows, size_t n_cols, int dtype,
+                   const double *row_weight, double *out, void *stream);
+
+/*
  * Exhaustive self-check used by the GPU test-suite: for ALL 2^32 fp32 bit patterns compare the
  * closed-form rounding of `format` (FPQ_FMT_* or 16+half-grid id, 16 = int_neg, 17 = e2m3_pos, 18 = e1m2_neg, 19 = e2m1_pos, 20 = e2m1_neg; fpq_grid.cu) under
  * `tie_mode` with the literal reference scan over the same grid.  result[0] = mismatch count,

@@ -73,6 +73,16 @@ def main():
         res["signsplit f16 (fc2)"] = timeit(lambda i: lib.fpq_fake_quant_signsplit(x[i].data_ptr(), o[i].data_ptr(), n // 128, 128, 1, 1, 0, 0, 0, None, st), n * 4)
     if want("signsplit f16 +clip"):
         res["signsplit f16 +clip"] = timeit(lambda i: lib.fpq_fake_quant_signsplit(x[i].data_ptr(), o[i].data_ptr(), n // 128, 128, 1, 1, 0, 0, 2, flag.data_ptr(), st), n * 4)
+    if want("gelu+signsplit f16 fused"):
+        xg = [torch.randn(rows, 4 * C, device=dev).half() for _ in range(NBUF)]
+        res["gelu+signsplit f16 fused (8 B/elem counted)"] = timeit(lambda i: lib.fpq_gelu_fake_quant_signsplit(xg[i].data_ptr(), o[i].data_ptr(), n // 128, 0, 2, flag.data_ptr(), st), n * 8)
+        tmp = [torch.empty_like(t) for t in xg]
+        def unfused(i):
+            tmp[i] = torch.nn.functional.gelu(xg[i], approximate="tanh")
+            lib.fpq_fake_quant_signsplit(tmp[i].data_ptr(), o[i].data_ptr(), n // 128, 128, 1, 1, 0, 0, 2, flag.data_ptr(), st)
+        res["gelu (ATen) then signsplit, 2 launches (8 B/elem)"] = timeit(unfused, n * 8)
+        res["gelu (ATen) alone (4 B/elem)"] = timeit(lambda i: torch.nn.functional.gelu(xg[i], approximate="tanh"), n * 4)
+        del xg, tmp
     if want("group e2m1 f16 (4C)"):
         res["group e2m1 f16 (4C)"] = timeit(lambda i: lib.fpq_fake_quant(x[i].data_ptr(), o[i].data_ptr(), n // 128, 128, 1, 1, 0, 0, 0, st), n * 4)
     if want("group e2m3 f16 (4C)"):

@@ -64,5 +64,34 @@ def rep(path):
             pass
 
 
+def traffic(path, key, algorithmic_bytes, match=""):
+    """traffic <rep> <op:fmt:in->out> <algorithmic bytes of the captured launch> [kernel-name substring]: writes the DRAM
+    bytes of the first matching launch into profiles/r2_traffic.json (what bench.py's roofline.traffic is read from)."""
+    import json
+    import os
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")]
+        if match and match not in name:
+            continue
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        rd, wr = float(r[ir]) * scale[units[ir]], float(r[iw]) * scale[units[iw]]
+        dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r2_traffic.json")
+        table = json.load(open(dst)) if os.path.exists(dst) else {}
+        table[key] = {"kernel": short(name), "dram_bytes_read": rd, "dram_bytes_write": wr, "dram_bytes": rd + wr,
+                      "algorithmic_bytes": float(algorithmic_bytes), "source": f"ncu --set full --clock-control none, {os.path.basename(path)}",
+                      "duration_us_under_ncu": float(r[hdr.index("gpu__time_duration.sum")])}
+        json.dump(table, open(dst, "w"), indent=1, sort_keys=True)
+        print(json.dumps(table[key]))
+        return
+    raise SystemExit("no matching launch")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "rep": rep}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(*sys.argv[2:])
+    else:
+        {"launches": launches, "rep": rep}[sys.argv[1]](sys.argv[2])
