@@ -11,13 +11,24 @@ own batch (weak scaling, no data-path collective; one final gather of the timing
   value     algorithmic GB/s (input bytes read once + output bytes written once), inputs resident
             in HBM, one CUDA-graph replay per step, CUDA events, max over ranks
   e2e       same metric through the HOST-buffer entry (fpqvar_b200.hotpath.HostPipeline): pinned
-            H2D copy of every input and D2H copy of every output inside the timed region
-  roofline  the dominant kernel's launches of the step, timed alone with CUDA events
-  cpu_baseline   oracle/fakequant_port.c (multi-threaded C port of the reference functions) on a
-            bounded sample of the same workload, rank 0 / N=1 only
+            H2D copy of every input and D2H copy of every output inside the timed region; every rank
+            binds to its GPU's NUMA node before it allocates its pinned buffers
+  roofline  the dominant kernel's launches of the step, timed alone with CUDA events; `traffic` from
+            the committed ncu capture (profiles/r2_traffic.json)
+  cpu_baseline   the reference's OWN torch CPU functions (baseline/_ref, installed by
+            baseline/install_ref.sh; kind "reference") on a bounded sample of the same workload, rank 0 /
+            N=1 only; `cpu_port` = the multi-threaded C port of the oracle beside it.  Without an install:
+            the port (kind "port")
+  reference_gpu_path / generation_reference_model   the reference's own GPU path (its fp_quant_*_cuda functions
+            around its extension compiled for sm_100a) over the same step, and images/sec of the reference's
+            own VAR model with its quantizers / this library as a drop-in / the fused call sites -- child
+            processes, outside every timed region
+  search    BASELINE configs[4] on a bounded unit list, (layer, weight-format) units sharded over the ranks,
+            one all-reduce (strong scaling)
+  other_configs   the device-resident step of BASELINE configs[1] and [3] (child runs)
 
-`--impl reference` times that CPU port alone (the reference has no CPU-runnable build of its CUDA
-extension and its Python cannot travel to the GPU box).
+`--impl reference` times the reference's CPU implementation alone, on this arm's config / metric / unit, with
+the steps and warm-up it is given (rank 0 only under torchrun).
 """
 from __future__ import annotations
 

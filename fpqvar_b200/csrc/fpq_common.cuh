@@ -60,7 +60,7 @@ int sm_count();
 struct Tunables {
     int pdl = 1;                               // programmatic dependent launch on (0: plain stream-ordered launches)
     int row_v = 0;                             // values-per-thread of the per-token kernels: 0 = chosen by row_reg_vectors, else 1 | 2 | 4
-    long long rot_small_max_chunks = 24576;    // rotate launches up to this many 128-chunks take the small-launch kernel
+    long long rot_small_max_chunks = 40000;    // rotate launches up to this many 128-chunks take the small-launch kernel (measured: VAR-d30 stage 4, 37 500 chunks, 9.95 vs 11.0 us)
     int smem_kb = 0;                           // shared-memory carveout (KB per SM) every activation kernel asks for; 0 = leave it to the driver
 };
 extern Tunables g_tun;

@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(256) signsplit_group_h16_kernel(const __half* 
             // to `out` first and is quantized there in place (all lanes of the group store before any of them rescans it)
             const __half* src = x + g * 128;
             if (GELU || rc == 0) store_tile_h16(out + g * 128, lig, p);
-            if (GELU && rc != 0) { __syncwarp(); src = out + g * 128; }
+            if (GELU && rc != 0) { __syncwarp(0xFu << (lane & ~3)); src = out + g * 128; }      // rc is uniform over the 4 lanes of a group, not over the warp
             if (rc == 1) literal_split_h16(src, out + g * 128, lig, H16_LPG, 8, H16_NV, sn, sp, SF::GT_N, SF::GT_P);
             else if (rc == 2) literal_split_nan_group_h16(src, out + g * 128, lig, H16_LPG, 8, H16_NV, SF::NEG::VMAX, SF::POS::VMAX, SF::GT_N, SF::GT_P);
         }
@@ -394,7 +394,16 @@ __global__ void selftest_f16_flow_kernel(unsigned long long* result) {
         const uint32_t x2 = uint32_t(xb) | (uint32_t(xb ^ 0x8000u) << 16);
         uint32_t got, want[2];
         bool check[2];
-        if constexpr (CODE < 16) {
+        if constexpr (CODE >= 32) {                              // the conversion-hardware element function (scorer; FPQ_HWCVT builds)
+            using HG = typename SymFmt<CODE - 32>::HG;
+            static_assert(HwCvt<HG>::AVAILABLE, "no conversion hardware for this format");
+            if (!scale_bits_regular_hw<HG>(sb)) continue;
+            check[0] = check[1] = pair_possible<HG>(x, s);
+            const float rr = r * HwCvt<HG>::PRE;
+            got = sym_pair_h16_hw<HG>(widen_h2(x2), pk(rr, rr), dup_h(__float2half_rn(s * (1.0f / HwCvt<HG>::PRE))), delta);
+            want[0] = f2h(quant_elem_literal<__half, TIE_KERNEL>(x, s, c_grids[SymFmt<CODE - 32>::GT]) * s);
+            want[1] = f2h(quant_elem_literal<__half, TIE_KERNEL>(-x, s, c_grids[SymFmt<CODE - 32>::GT]) * s);
+        } else if constexpr (CODE < 16) {
             using HG = typename SymFmt<CODE>::HG;
             if (!scale_bits_regular_for<HG>(sb)) continue;      // scales the kernels send down the literal path
             check[0] = check[1] = pair_possible<HG>(x, s);
@@ -426,8 +435,8 @@ __global__ void selftest_f16_flow_kernel(unsigned long long* result) {
             return fast == exact || (!scale_bits_regular(fast) && !scale_bits_regular(exact));
         };
         bool ok;
-        if constexpr (CODE < 16) {
-            using HG = typename SymFmt<CODE>::HG;
+        if constexpr (CODE >= 32 || CODE < 16) {
+            using HG = typename SymFmt<(CODE >= 32 ? CODE - 32 : CODE)>::HG;
             ok = same(__half_as_ushort(scale_from_absmax_h16<HG>(a)), f2h(__fdiv_rn(a, HG::VMAX)));
         } else {
             using SF = SplitH16<CODE - 16>;
@@ -458,6 +467,10 @@ extern "C" int fpq_selftest_f16_flow(int format, unsigned long long* result, voi
         case 16: selftest_f16_flow_kernel<16><<<grid, 256, 0, st>>>(result); break;
         case 17: selftest_f16_flow_kernel<17><<<grid, 256, 0, st>>>(result); break;
         case 18: selftest_f16_flow_kernel<18><<<grid, 256, 0, st>>>(result); break;
+        case 32 + FPQ_FMT_E2M1: selftest_f16_flow_kernel<32 + FPQ_FMT_E2M1><<<grid, 256, 0, st>>>(result); break;
+        case 32 + FPQ_FMT_E1M2: selftest_f16_flow_kernel<32 + FPQ_FMT_E1M2><<<grid, 256, 0, st>>>(result); break;
+        case 32 + FPQ_FMT_E2M3: selftest_f16_flow_kernel<32 + FPQ_FMT_E2M3><<<grid, 256, 0, st>>>(result); break;
+        case 32 + FPQ_FMT_E3M2: selftest_f16_flow_kernel<32 + FPQ_FMT_E3M2><<<grid, 256, 0, st>>>(result); break;
         default: return FPQ_ERR_ARG;
     }
     return finish_launch();

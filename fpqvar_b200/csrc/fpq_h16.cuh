@@ -106,13 +106,9 @@ template <class HG> struct Magic {
 // PRE: e1m2 (uniform, step 1/4 up to 1.75) is not a hardware format, but HALF of it is the uniform low end of e2m3
 // (step 1/8 up to 0.875): the group's reciprocal scale is halved and its scale doubled, both exact.  The doubled
 // scale must stay a finite fp16 number: S_MAX_BITS bounds the "regular" scales of the format.
-#ifndef FPQ_HWCVT
-#define FPQ_HWCVT 0          // 1: use the conversion hardware (measured: slower, see the header comment); 0: magic-number FFMA
-#endif
-template <class HG> struct HwCvt { static constexpr bool AVAILABLE = false; static constexpr bool OK = false; static constexpr float PRE = 1.0f; static constexpr uint32_t S_MAX_BITS = 0x7BFFu; };
+template <class HG> struct HwCvt { static constexpr bool AVAILABLE = false; static constexpr float PRE = 1.0f; static constexpr uint32_t S_MAX_BITS = 0x7BFFu; };
 template <> struct HwCvt<HG_E2M1> {
     static constexpr bool AVAILABLE = true;
-    static constexpr bool OK = FPQ_HWCVT != 0;
     static constexpr float PRE = 1.0f;
     static constexpr uint32_t S_MAX_BITS = 0x7BFFu;
     static __device__ __forceinline__ uint32_t round_trip(float w0, float w1) {
@@ -123,7 +119,6 @@ template <> struct HwCvt<HG_E2M1> {
 };
 template <> struct HwCvt<HG_E2M3> {
     static constexpr bool AVAILABLE = true;
-    static constexpr bool OK = FPQ_HWCVT != 0;
     static constexpr float PRE = 1.0f;
     static constexpr uint32_t S_MAX_BITS = 0x7BFFu;
     static __device__ __forceinline__ uint32_t round_trip(float w0, float w1) {
@@ -134,7 +129,6 @@ template <> struct HwCvt<HG_E2M3> {
 };
 template <> struct HwCvt<HG_E3M2> {
     static constexpr bool AVAILABLE = true;
-    static constexpr bool OK = FPQ_HWCVT != 0;
     static constexpr float PRE = 1.0f;
     static constexpr uint32_t S_MAX_BITS = 0x7BFFu;
     static __device__ __forceinline__ uint32_t round_trip(float w0, float w1) {
@@ -145,7 +139,6 @@ template <> struct HwCvt<HG_E3M2> {
 };
 template <> struct HwCvt<HG_E1M2> {
     static constexpr bool AVAILABLE = true;
-    static constexpr bool OK = FPQ_HWCVT != 0;
     static constexpr float PRE = 0.5f;
     static constexpr uint32_t S_MAX_BITS = 0x77FFu;          // 2 * s stays finite (callers that use the conversion hardware check it)
     static __device__ __forceinline__ uint32_t round_trip(float w0, float w1) { return HwCvt<HG_E2M3>::round_trip(w0, w1); }
@@ -160,35 +153,37 @@ __device__ __forceinline__ uint64_t round_pair_magic(float w0, float w1, float e
     return ffma2(p, pk(-sc, -sc), y);
 }
 
-// Per-group constants of the symmetric flow: r = RN(1/s) as a packed fp32 pair, s as a packed fp32 pair
-// (magic path) or as an fp16 pair (hardware path); the hardware path folds the format's PRE factor into both.
+// Per-group constants of the symmetric flow of the quantizer kernels: r = RN(1/s) and s as packed fp32 pairs.
 struct SymK {
     uint64_t r2, s2;
-    uint32_t sh2;
 };
 template <class HG>
 __device__ __forceinline__ SymK make_symk(float s, float r) {
     SymK k;
-    const float rr = r * (HwCvt<HG>::OK ? HwCvt<HG>::PRE : 1.0f);                                  // power of two: exact
-    k.r2 = pk(rr, rr);
+    k.r2 = pk(r, r);
     k.s2 = pk(s, s);
-    k.sh2 = dup_h(__float2half_rn(s * (1.0f / (HwCvt<HG>::OK ? HwCvt<HG>::PRE : 1.0f))));          // s is an fp16 value <= S_MAX_BITS: exact
     return k;
 }
+
+// The symmetric element function on the conversion hardware (formats with HwCvt<HG>::AVAILABLE): the format scorer's
+// (fpq_score.cu); exhaustively checked against the literal sequence by fpq_selftest_f16_flow(32 + format).
+// r2 = RN(1/s) * PRE, sh2 = fp16(s / PRE) twice.  The quantizer kernels do NOT use it: measured at equal conditions
+// (profiles/r2_quantizer_rounding_ab.txt) it is no faster there -- the pack runs at a quarter of the issue rate.
+template <class HG>
+__device__ __forceinline__ uint32_t sym_pair_h16_hw(uint64_t xf2, uint64_t r2, uint32_t sh2, float delta) {
+    const uint32_t v2 = pack_h2_u64(fmul2(xf2, r2));                              // half(x/s) (times PRE, exact)
+    const uint32_t q2 = HwCvt<HG>::round_trip(fhadd(uint16_t(v2 & 0xffffu), delta), fhadd(uint16_t(v2 >> 16), delta));
+    return hfma2(q2, sh2, 0u);                                                    // half(q*s), -0 -> +0
+}
+template <class HG> __device__ __forceinline__ bool scale_bits_regular_hw(uint32_t sb) { return sb - 0x0400u <= HwCvt<HG>::S_MAX_BITS - 0x0400u; }
 
 // One packed pair of the symmetric flow: two fp16 inputs (already widened to packed fp32) -> two fp16
 // outputs q*s.
 template <class HG>
 __device__ __forceinline__ uint32_t sym_pair_h16_w(uint64_t xf2, const SymK& k, float delta) {
     const uint32_t v2 = pack_h2_u64(fmul2(xf2, k.r2));                            // half(x/s)
-    const float w0 = fhadd(uint16_t(v2 & 0xffffu), delta);
-    const float w1 = fhadd(uint16_t(v2 >> 16), delta);
-    if constexpr (HwCvt<HG>::OK) {
-        return hfma2(HwCvt<HG>::round_trip(w0, w1), k.sh2, 0u);                   // half(q*s), -0 -> +0
-    } else {
-        const uint64_t q = round_pair_magic(w0, w1, Magic<HG>::EM, Magic<HG>::SC);
-        return pack_h2_u64(fmul2(q, k.s2));                                       // half(q*s)
-    }
+    const uint64_t q = round_pair_magic(fhadd(uint16_t(v2 & 0xffffu), delta), fhadd(uint16_t(v2 >> 16), delta), Magic<HG>::EM, Magic<HG>::SC);
+    return pack_h2_u64(fmul2(q, k.s2));                                           // half(q*s)
 }
 template <class HG>
 __device__ __forceinline__ uint32_t sym_pair_h16(uint32_t x2, const SymK& k, float delta) {
@@ -212,7 +207,7 @@ __device__ __forceinline__ float rcp_rn_normal(float s) {
 }
 // "regular" on fp16 bits: 0x0400 <= bits <= 0x7BFF (normal, finite, positive)
 __device__ __forceinline__ bool scale_bits_regular(uint32_t sb) { return sb - 0x0400u < 0x7800u; }
-template <class HG> __device__ __forceinline__ bool scale_bits_regular_for(uint32_t sb) { return sb - 0x0400u <= (HwCvt<HG>::OK ? HwCvt<HG>::S_MAX_BITS : 0x7BFFu) - 0x0400u; }
+template <class HG> __device__ __forceinline__ bool scale_bits_regular_for(uint32_t sb) { return scale_bits_regular(sb); }
 
 // absmax of NW packed words as an fp16 bit pattern, one HMNMX2.NAN on |a|, |b| per word.  A NaN anywhere
 // comes out as a NaN pattern (> 0x7C00), exactly like torch's abs().max().
@@ -315,55 +310,7 @@ static __device__ __noinline__ void literal_split_nan_group_h16(const __half* sr
 //                   fp16 value reaches or crosses a midpoint (midpoints are fp16 numbers).  The FMA rounds once.
 //                   A non-uniform negative grid (afpq: e2m1 on both sides) goes through the conversion hardware too.
 // A lane of the wrong side computes garbage (possibly inf / NaN) that the select discards.
-#if FPQ_HWCVT
-template <class NEG> struct UniformNeg {
-    // NEG uniform <=> all of its values lie in its own subnormal region or first binade with the same step
-    static constexpr bool OK = (NEG::M - NEG::EMIN == 2 && NEG::VNUM * 4 == 7 * NEG::VDEN) || (NEG::M == NEG::EMIN);
-    static constexpr float STEP = Magic<NEG>::EM / float(1u << NEG::M);
-    static constexpr float C = 1536.0f * STEP;                 // 1.5 * 2^10 * step
-};
-
-struct SplitK {
-    uint64_t rn2, rp2;          // RN(1/s) of each side as packed fp32 pairs (0 for a side without elements)
-    uint32_t snh2, sph2;        // the two scales as fp16 pairs
-};
-template <class NEG, class POS>
-__device__ __forceinline__ SplitK make_splitk(float sn, float rn, float sp, float rp) {
-    SplitK k;
-    k.rn2 = pk(rn, rn);
-    k.rp2 = pk(rp, rp);
-    k.snh2 = dup_h(__float2half_rn(sn));
-    k.sph2 = dup_h(__float2half_rn(sp));
-    return k;
-}
-
-template <class NEG, class POS>
-__device__ __forceinline__ uint32_t split_pair_h16_w(uint64_t xf2, uint32_t x2, const SplitK& k, float delta) {
-    static_assert(HwCvt<POS>::OK, "the positive side of every sign-split format is e2m1 or e2m3");
-    const uint32_t vp2 = pack_h2_u64(fmul2(xf2, k.rp2));                           // half(x/sp)
-    const uint32_t vn2 = pack_h2_u64(fmul2(xf2, k.rn2));                           // half(x/sn)
-    const uint32_t qp2 = HwCvt<POS>::round_trip(fhadd(uint16_t(vp2 & 0xffffu), delta), fhadd(uint16_t(vp2 >> 16), delta));
-    uint32_t qn2;
-    if constexpr (UniformNeg<NEG>::OK) {
-        const uint32_t c2 = dup_h(__float2half_rn(UniformNeg<NEG>::C));
-        qn2 = hadd2(hfma2(vn2, 0x3BFF3BFFu, c2), c2 ^ 0x80008000u);                // (v * (1 - 2^-11) + C) - C
-    } else {
-        static_assert(HwCvt<NEG>::OK, "non-uniform negative grids must be hardware formats");
-        qn2 = HwCvt<NEG>::round_trip(fhadd(uint16_t(vn2 & 0xffffu), delta), fhadd(uint16_t(vn2 >> 16), delta));
-    }
-    uint32_t neg;                                                                  // 0xFFFF in every half whose sign bit is set
-    asm("prmt.b32 %0, %1, 0, 0xBB99;" : "=r"(neg) : "r"(x2));
-    const uint32_t q2 = (qp2 & ~neg) | (qn2 & neg);
-    const uint32_t s2 = (k.sph2 & ~neg) | (k.snh2 & neg);
-    return hfma2(q2, s2, 0u);                                                      // half(q*s), -0 -> +0
-}
-template <class NEG, class POS>
-__device__ __forceinline__ uint32_t split_pair_h16(uint32_t x2, const SplitK& k, float delta) {
-    return split_pair_h16_w<NEG, POS>(widen_h2(x2), x2, k, delta);
-}
-
-#else
-// (default build) Per-element constants picked with integer multiply-adds on the FMA pipe (ncu r1b: the ALU pipe, where
+// Per-element constants picked with integer multiply-adds on the FMA pipe (ncu r1b: the ALU pipe, where
 // FSEL / LOP3 / FMNMX / F2FP live, is the busy one; measured 5.40 -> 6.15 TB/s against LOP3 selects).  Sides with a
 // UNIFORM negative grid (e1m2: step 1/4 up to 1.75; int: step 1 up to 32) share the positive side's rounding constants:
 // the negative side is rescaled by the power of two K that maps its step onto the positive format's subnormal step
@@ -418,6 +365,4 @@ template <class NEG, class POS>
 __device__ __forceinline__ uint32_t split_pair_h16(uint32_t x2, const SplitK& k, float delta) {
     return split_pair_h16_w<NEG, POS>(widen_h2(x2), x2, k, delta);
 }
-#endif
-
 }  // namespace fpq

@@ -252,7 +252,9 @@ struct RotStream {
                     if (reload) load_operands();                  // first row of a batch
                     if (--left == 0) { left = rpb; pa += row_elems; psh += row_elems; reload = true; }
                 }
-                if (colok1) {
+                {
+                    // every lane runs (no branch, no partial-warp barrier): a lane whose column does not exist (the last warp
+                    // may own fewer than four) has zero multipliers and works on its own, unused slice of the buffer
                     const uint32_t off = buf_off + uint32_t(sub) * 2048u;
                     uint64_t P[8];
 #pragma unroll
@@ -273,7 +275,7 @@ struct RotStream {
                     reg_stage(P, 2);        // index bit 5
                     reg_stage(P, 4);        // index bit 6
                     // in place: the 8 lanes of the chunk have all read their units before any of them overwrites one
-                    __syncwarp(lanes8);
+                    __syncwarp();
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
                         const F2 p0 = unpk(P[2 * a]), p1v = unpk(P[2 * a + 1]);
@@ -288,17 +290,15 @@ struct RotStream {
 
     // returns after the loads of pass 2 (the caller then hands the buffer back to the producer) -- Q holds the values
     __device__ __forceinline__ void pass2_load(uint32_t buf_off, bool valid, uint64_t (&Q)[16]) {
-        if (valid) {
+        // unconditional: a lane set without a chunk (missing column, or the odd last row) reads its own stale slice of the
+        // buffer and its results are never stored
+        (void)valid;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                uint4 u;
-                asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(a2[i] + buf_off));
-                Q[2 * i] = (uint64_t(u.y) << 32) | u.x;
-                Q[2 * i + 1] = (uint64_t(u.w) << 32) | u.z;
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 16; ++i) Q[i] = 0ull;
+        for (int i = 0; i < 8; ++i) {
+            uint4 u;
+            asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(a2[i] + buf_off));
+            Q[2 * i] = (uint64_t(u.y) << 32) | u.x;
+            Q[2 * i + 1] = (uint64_t(u.w) << 32) | u.z;
         }
     }
     __device__ __forceinline__ void pass2_finish(bool valid, uint64_t (&Q)[16]) {
@@ -385,6 +385,10 @@ __device__ __forceinline__ void rotate_stream_body(const float* __restrict__ x, 
     st.pa = st.psh = nullptr;
     st.left = st.rpb = 1;
     st.reload = false;
+    if constexpr (MOD) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) st.A[i] = st.SH[i] = 0ull;
+    }
     if constexpr (MOD) {
         const size_t batch = r_begin / mod.rows_per_batch;
         st.rpb = uint32_t(mod.rows_per_batch);

@@ -182,22 +182,18 @@ __device__ __forceinline__ float sse_sym_h16(const uint32_t (&p)[16], const uint
     float acc0 = 0.0f, acc1 = 0.0f;
     const uint32_t sb = __half_as_ushort(sh);
     if constexpr (HwCvt<HG>::AVAILABLE) {
-        // Formats the FP4 / FP6 conversion hardware knows (e2m1, e2m3, e3m2; e1m2 as the uniform low end of e2m3): 7
-        // instructions per pair and candidate.  The score needs the squared DISTANCE to the nearest grid point, not the grid
-        // point itself, so the fp16 rounding of x/s and the tie shift of the quantizer kernels are skipped: they only decide
-        // which of two EQUIDISTANT neighbours an exact midpoint goes to (the error is the same either way), and a value that the
-        // fp16 rounding would carry across a midpoint is within 2^-11 of it (its squared error changes by < 2^-9 relative on
-        // an element that occurs with probability ~2^-10: far inside the 2e-6 tolerance of the sums).
-        if (sb - 0x0400u <= HwCvt<HG>::S_MAX_BITS - 0x0400u) {
+        // Formats the FP4 / FP6 conversion hardware knows (e2m1, e2m3, e3m2; e1m2 as the uniform low end of e2m3): the
+        // quantizer's element function with the hardware round trip (exhaustively bit-exact, fpq_selftest_f16_flow of the
+        // FPQ_HWCVT=1 build), 10 instructions per pair and candidate with the error term.  (Skipping the fp16 rounding of
+        // x/s and the tie shift would save three of them, but values that the fp16 rounding carries across a midpoint change
+        // the sums by 1e-5 relative -- measured -- which is outside the 2e-6 the scorer promises.)
+        if (scale_bits_regular_hw<HG>(sb)) {
             const float s = __half2float(sh);
             const float rr = rcp_rn_normal(s) * HwCvt<HG>::PRE;
             const uint64_t r2 = pk(rr, rr);
             const uint32_t sh2 = dup_h(__float2half_rn(s * (1.0f / HwCvt<HG>::PRE)));
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const F2 v = unpk(fmul2(xf[i], r2));
-                sq_err_pair(p[i], hfma2(HwCvt<HG>::round_trip(v.lo, v.hi), sh2, 0u), acc0, acc1);
-            }
+            for (int i = 0; i < 16; ++i) sq_err_pair(p[i], sym_pair_h16_hw<HG>(xf[i], r2, sh2, delta), acc0, acc1);
             return acc0 + acc1;
         }
     } else {

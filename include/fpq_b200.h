@@ -90,7 +90,7 @@ FPQ_API uint64_t fpq_launch_count(void);
  * GPU tests; never through the environment).  Process-wide; not meant to be changed while other threads launch.
  *   "pdl"                  1 (default) | 0: programmatic dependent launch of the activation kernels on / off
  *   "row_v"                0 (default: chosen per row length) | 1 | 2 | 4: 16-byte vectors per thread of the per-token kernels
- *   "rot_small_max_chunks" rotate launches of up to this many 128-chunks take the small-launch kernel (default 24576)
+ *   "rot_small_max_chunks" rotate launches of up to this many 128-chunks take the small-launch kernel (default 40000)
  * Results never depend on a tunable (tests/test_gpu_shapes.py).  Returns FPQ_ERR_ARG for an unknown name or value.
  */
 FPQ_API int fpq_set_tunable(const char *name, long long value);
@@ -243,8 +243,9 @@ FPQ_API int fpq_selftest_rounding(int format, int tie_mode, unsigned long long *
  * Exhaustive self-check of the packed fp16 activation path (fp16 in, fp16 out, FPQ_TIE_KERNEL):
  * for EVERY pair (x, scale) of fp16 values that can meet in a group with a normal scale, compare
  * the division-free element function of the fast kernels with the literal reference sequence
- * divide -> half -> scan -> multiply -> half (qu.py:320-329 / :432-451).  `format`: FPQ_FMT_* or
- * 16+FPQ_SPLIT_*.  result as in fpq_selftest_rounding.
+ * divide -> half -> scan -> multiply -> half (qu.py:320-329 / :432-451).  `format`: FPQ_FMT_*,
+ * 16+FPQ_SPLIT_*, or 32+FPQ_FMT_{E2M1,E1M2,E2M3,E3M2} for the element function on the FP4/FP6 conversion
+ * hardware (the format scorer's).  result as in fpq_selftest_rounding.
  */
 FPQ_API int fpq_selftest_f16_flow(int format, unsigned long long *result, void *stream);
 

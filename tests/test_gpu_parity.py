@@ -44,10 +44,11 @@ def test_rounding_exhaustive(ops, code, tie):
     assert bad == 0, f"format code {code} tie {tie}: {bad} mismatches, first at bits 0x{first:08x}"
 
 
-@pytest.mark.parametrize("code", [0, 1, 2, 3, 4, 16, 17, 18])
+@pytest.mark.parametrize("code", [0, 1, 2, 3, 4, 16, 17, 18, 32 + 0, 32 + 1, 32 + 3, 32 + 4])
 def test_f16_flow_exhaustive(ops, code):
     """Packed fp16 fast path (division-free, magic-number rounding) == literal reference sequence
-    for every (x, scale) pair of fp16 values that can occur in a regular group."""
+    for every (x, scale) pair of fp16 values that can occur in a regular group.  Codes 32 + format: the element function on
+    the FP4 / FP6 conversion hardware (e2m1, e1m2, e2m3, e3m2), which the format scorer uses."""
     bad, first = ops.selftest_f16_flow(code)
     assert bad == 0, (f"format code {code}: {bad} mismatches, first at scale bits 0x{0x0400 + (first >> 16):04x}, "
                       f"x bits 0x{first & 0xffff:04x}")

@@ -310,10 +310,10 @@ def test_rotation_bits_do_not_depend_on_the_launch_size(ops, sign_bits):
     """The launcher picks a different kernel layout for small tensors; a row must rotate and quantize to the same
     bits whether it is processed alone, in a small batch or in a large one."""
     torch.manual_seed(9)
-    x = torch.randn(40000, 256, device="cuda")                      # 80000 chunks: second layout
+    x = torch.randn(40000, 256, device="cuda")                      # 80000 chunks: the streaming kernel
     s = torch.exp(torch.rand(256, device="cuda") * 2 - 1)
     big, big_rot = ops.transform_rotate_quant(x, s, sign_bits, "e2m1", return_rotated=True)
-    for n in (1, 7, 500, 12288):                                     # <= 24576 chunks: first layout
+    for n in (1, 7, 500, 12288):                                     # <= 40000 chunks: the small-launch kernel
         small, small_rot = ops.transform_rotate_quant(x[:n].contiguous(), s, sign_bits, "e2m1", return_rotated=True)
         assert torch.equal(small_rot.view(torch.int16), big_rot[:n].view(torch.int16)), n
         assert torch.equal(small.view(torch.int16), big[:n].view(torch.int16)), n

@@ -192,7 +192,7 @@ def test_rotate_kernel_choice_does_not_change_results(ops):
             for u, v in zip(*res):
                 assert bits_equal(u, v), (cols, rows, rpb)
     finally:
-        L.set_tunable("rot_small_max_chunks", 24576)
+        L.set_tunable("rot_small_max_chunks", 40000)
 
 
 def test_randomized_differential_against_oracle(ops):

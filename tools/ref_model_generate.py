@@ -15,7 +15,8 @@ modes is only who does the fake quantization:
               quantize_VAR (fpqvar_b200.quant_utils: one fused launch per quantizer call)
   fused       level (c): additionally AdaLNSelfAttn.forward calls adaln_transform_rotate_quant_activation (adaLN modulate +
               GALT multiply + block rotation + quantizer in ONE launch) instead of the modulate / .mul(s) / matmul / act_quant
-              sequence -- the three-line change a maintainer would make at basic_var.py:263,266
+              sequence -- the three-line change a maintainer would make at basic_var.py:263,266 -- and FFN.forward calls
+              gelu_fake_quant_signsplit (GELU + fc2's activation quantizer in one launch, basic_var.py:120)
 
   python tools/ref_model_generate.py --depth 30 --batch 50 --modes fp16,reference,dropin,fused --iters 2
 """
@@ -90,6 +91,15 @@ def _init_vqvae(vae):
             emb.weight.copy_(torch.randn(emb.weight.shape, generator=g).to(emb.weight.device))
 
 
+def _fused_ffn_forward(self, x, block_idx, step_idx):
+    """FFN.forward (basic_var.py:110-121) with `self.act` and fc2's activation quantizer in one pass
+    (fpq_gelu_fake_quant_signsplit) followed by the bare GEMM on fc2's quantized weight."""
+    from fpqvar_b200 import ops
+    h = self.fc1(x)                                    # QuantizedLinear: its act_quant is the identity in this mode
+    hq = ops.gelu_fake_quant_signsplit(h, self._fpq_fc2_split, global_clip=True)
+    return self.drop(torch.nn.functional.linear(hq, self.fc2.weight, self.fc2.bias))
+
+
 def build(ns, dev, depth, res, bits, mode):
     patch_nums = PATCH_512 if res == 512 else PATCH_256
     torch.manual_seed(0)
@@ -133,6 +143,8 @@ def build(ns, dev, depth, res, bits, mode):
                 b.forward = types.MethodType(_fused_forward, b)
                 b.attn.mat_qkv.act_quant = lambda t: t
                 b.ffn.fc1.act_quant = lambda t: t
+                b.ffn._fpq_fc2_split = {"fp_e1m2_neg_e2m1_pos": "e1m2_neg_e2m1_pos", "fp6_int_neg_e2m3_pos": "int_neg_e2m3_pos"}[fmt[2]]
+                b.ffn.forward = types.MethodType(_fused_ffn_forward, b.ffn)
             Q = None
     return vae, var, Q, s_qkv, s_fc1, info
 

@@ -134,6 +134,7 @@ class Var(nn.Module):
         self.codebook = nn.Embedding(V, Cvae)
         self.phi = nn.ModuleList(nn.Conv2d(Cvae, Cvae, 3, padding=1) for _ in range(4))
         self.mode = "fp16"
+        self.fc2_split_fmt = None
         self.kv_bit, self.kv_incremental = 0, True
         self.smooth_qkv = self.smooth_fc1 = None
         self.Q = None
@@ -176,8 +177,13 @@ class Var(nn.Module):
         ln = F.layer_norm(x, (self.C,), eps=1e-6)
         if self.mode == "fused":
             xq = rotation_utils.adaln_transform_rotate_quant_activation(ln, scale2, shift2, self.smooth_fc1[i], self.act_fp_type)
-            h = F.gelu(F.linear(xq, b.ffn.fc1.weight, b.ffn.fc1.bias.view(-1)), approximate="tanh")
-            f = b.ffn.fc2(h)
+            h1 = F.linear(xq, b.ffn.fc1.weight, b.ffn.fc1.bias.view(-1))
+            if self.fc2_split_fmt is not None and h1.dtype == torch.float16:
+                # GELU + the fc2 quantizer in one pass (fpq_gelu_fake_quant_signsplit), then the bare GEMM
+                hq = ops.gelu_fake_quant_signsplit(h1, self.fc2_split_fmt, global_clip=True)
+                f = F.linear(hq, b.ffn.fc2.weight, b.ffn.fc2.bias)
+            else:
+                f = b.ffn.fc2(F.gelu(h1, approximate="tanh"))
         else:
             x2 = ln.mul(scale2.add(1)).add_(shift2)
             if self.Q is None:
@@ -301,6 +307,7 @@ def prepare(model: Var, mode: str, bits: int, seed=0, rotate=True):
     act = "fp_e2" if bits == 4 else "fp6_e2m3"
     fc2 = ("fp_e1m2_neg_e2m1_pos" if bits == 4 else "fp6_int_neg_e2m3_pos") if rotate else act
     model.act_fp_type = act
+    model.fc2_split_fmt = {"fp_e1m2_neg_e2m1_pos": "e1m2_neg_e2m1_pos", "fp6_int_neg_e2m3_pos": "int_neg_e2m3_pos"}.get(fc2) if mode == "fused" else None
     if mode != "fp16" and not rotate:
         if mode == "fused":
             raise SystemExit("mode fused needs --rotate (it fuses the online transform + rotation)")
