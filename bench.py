@@ -445,6 +445,11 @@ def search_leg(torch, dist, dev, rank, world, blocks, depth=30, acts=1000):
         if world > 1:
             dist.all_reduce(table)
 
+    # the reference's search scripts never enable TF32: the fp32 GEMMs of the mat_qkv / fc1 layers run at full precision
+    # (the generation harness above switches TF32 on, like evaluate_fp_quant_transform_rotate.py:171-175 -- undo that here)
+    tf32_saved = (torch.backends.cuda.matmul.allow_tf32, torch.get_float32_matmul_precision())
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.set_float32_matmul_precision("highest")
     run()                                           # warm-up (cuBLAS heuristics, allocator)
     if world > 1:
         dist.barrier()
@@ -458,6 +463,8 @@ def search_leg(torch, dist, dev, rank, world, blocks, depth=30, acts=1000):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     secs = float(t.item())
+    torch.backends.cuda.matmul.allow_tf32 = tf32_saved[0]
+    torch.set_float32_matmul_precision(tf32_saved[1])
     best = [search.best_formats(table[li], search.FP4_FORMATS, search.FP4_FORMATS) for li in range(len(names))]
     return {"seconds": secs, "units": len(units), "units_per_sec": len(units) / secs, "layers": len(names), "scaling": "strong",
             "calibration_rows_per_layer": sum(rows), "activations_per_layer": acts,

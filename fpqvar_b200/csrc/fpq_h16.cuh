@@ -227,9 +227,30 @@ __device__ __forceinline__ uint32_t absmax_bits(const uint32_t (&p)[NW]) {
 // Returns true when the group was handled (regular scale).  Otherwise p is untouched and the caller
 // runs literal_sym_h16 on the group's memory: keeping the rare literal path out of line (and out of
 // the register tile) keeps the hot loop small.
-template <int FMT, int LPG, int NW>
+// HW = true: the element function on the FP4 / FP6 conversion hardware (formats that have it): 5 instructions per pair
+// instead of 10 after the division.  Chosen per kernel from measurements: the register-tile kernels are no faster with it
+// (profiles/r2_quantizer_rounding_ab.txt); the streaming rotate kernel, which is issue-bound, is.
+template <int FMT, int LPG, int NW, bool HW = false>
 __device__ __forceinline__ bool sym_quant_tile_h16(uint32_t (&p)[NW], float& s, float delta) {
     using HG = typename SymFmt<FMT>::HG;
+    if constexpr (HW && HwCvt<HG>::AVAILABLE) {
+        uint32_t m = absmax_bits<NW>(p);
+#pragma unroll
+        for (int o = LPG / 2; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        const float a = h2f(uint16_t(m));
+        const __half sh = scale_from_absmax_h16<HG>(a);
+        s = __half2float(sh);
+        if (!scale_bits_regular_hw<HG>(__half_as_ushort(sh))) {
+            s = rnd_in<__half>(__fdiv_rn(a, HG::VMAX));
+            return false;
+        }
+        const float rr = rcp_rn_normal(s) * HwCvt<HG>::PRE;
+        const uint64_t r2 = pk(rr, rr);
+        const uint32_t sh2 = dup_h(__float2half_rn(s * (1.0f / HwCvt<HG>::PRE)));
+#pragma unroll
+        for (int i = 0; i < NW; ++i) p[i] = sym_pair_h16_hw<HG>(widen_h2(p[i]), r2, sh2, delta);
+        return true;
+    }
     uint32_t m = absmax_bits<NW>(p);
 #pragma unroll
     for (int o = LPG / 2; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));

@@ -51,8 +51,9 @@ __device__ __forceinline__ void load_mod4(const Modulate& mod, size_t off, uint6
     s23 = pk(sh.z, sh.w);
 }
 // .mul(scale.add(1)).add_(shift): the product with the SCALAR mul.rn.f32 (never contracted; ptxas fuses
-// mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 -- even through a *1 -- which would skip the rounding of the product
-// that the reference's separate ATen kernels perform)
+// mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 -- even through a *1, and even when the product is written as
+// fma(x, a, -0.0): measured, the parity tests fail -- which would skip the rounding of the product that the reference's
+// separate ATen kernels perform)
 __device__ __forceinline__ uint64_t modulate2(uint64_t x, uint64_t a, uint64_t sh) {
     const F2 xv = unpk(x), av = unpk(a);
     return fadd2(pk(__fmul_rn(xv.lo, av.lo), __fmul_rn(xv.hi, av.hi)), sh);
@@ -206,6 +207,10 @@ __global__ void __launch_bounds__(256, MOD ? 1 : 0) transform_rotate_quant_small
 //                Both the swizzled pass-1 stores and the pass-2 loads then touch 8 distinct 16-byte slots per phase
 //                (tests/rotate_layout_model.py replays the choreography on the host).
 // ------------------------------------------------------------------------------------------------------------
+// The streaming kernel's quantizer runs on the FP4 / FP6 conversion hardware (sym_pair_h16_hw, exhaustively checked by
+// fpq_selftest_f16_flow(32 + format)).  Measured against the magic-number path in the same kernel (same box, same run):
+// VAR-d30 step 24.89 vs 25.29 ms, VAR-d36 step 24.19 vs 24.82 ms; the largest launch alone is 2 % slower (5.66 vs 5.79 TB/s).
+constexpr bool ROT_HW_QUANT = true;
 constexpr int ROT_MIN_CPR = 4, ROT_MAX_CPR = 36;       // rows the streaming kernel takes, in chunks
 constexpr int ROT_WARP_STAGE_BYTES = 4096;             // 2 rows x 4 chunks x 512 B
 constexpr int ROT_WARP_SMEM = 2 * ROT_WARP_STAGE_BYTES + 16;      // + the two mbarriers
@@ -318,7 +323,7 @@ struct RotStream {
         }
         bool ok = true;
         float sc = 0.0f;
-        if constexpr (QUANT) ok = sym_quant_tile_h16<FMT, 4, 16>(w, sc, delta);
+        if constexpr (QUANT) ok = sym_quant_tile_h16<FMT, 4, 16, ROT_HW_QUANT>(w, sc, delta);
         if (valid) {
 #pragma unroll
             for (int q = 0; q < 4; ++q) stg_stream(op + q * 8, make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]));

@@ -91,6 +91,8 @@ FPQ_API uint64_t fpq_launch_count(void);
  *   "pdl"                  1 (default) | 0: programmatic dependent launch of the activation kernels on / off
  *   "row_v"                0 (default: chosen per row length) | 1 | 2 | 4: 16-byte vectors per thread of the per-token kernels
  *   "rot_small_max_chunks" rotate launches of up to this many 128-chunks take the small-launch kernel (default 40000)
+ *   "smem_kb"              0 (default: the driver chooses per kernel) | 1..228: the shared-memory carveout (KB per SM) every
+ *                          activation kernel asks for, and the streaming rotate kernel's shared-memory budget
  * Results never depend on a tunable (tests/test_gpu_shapes.py).  Returns FPQ_ERR_ARG for an unknown name or value.
  */
 FPQ_API int fpq_set_tunable(const char *name, long long value);

@@ -138,6 +138,37 @@ def test_side_stream_and_graph_replay(ops):
     assert bits_equal(host(y2), want), "workspace not reset after a poisoned call"
 
 
+@pytest.mark.parametrize("kb", [64, 100, 228])
+def test_results_identical_under_a_fixed_shared_memory_carveout(ops, kb):
+    """The tunable smem_kb (one L1 / shared-memory split for every activation kernel instead of the driver's choice; it also
+    bounds the streaming rotate kernel's CTAs per SM) is a performance knob only: same bits as the default."""
+    from fpqvar_b200 import _lib as L
+    from fpqvar_b200.hotpath import seed42_sign_bits
+    torch.manual_seed(3)
+    x = torch.randn(6000, 1920, device="cuda")                      # 90 000 chunks: the streaming kernel
+    h = torch.nn.functional.gelu(x).half()
+    s_ = torch.exp(torch.rand(1920, device="cuda") * 2 - 1)
+    sc = torch.randn(60, 1, 1920, device="cuda") * 0.3
+    sh = torch.randn(60, 1, 1920, device="cuda") * 0.5
+
+    def run():
+        a = ops.transform_rotate_quant(x, s_, seed42_sign_bits(), "e2m1")
+        m = ops.modulate_transform_rotate_quant(x.view(60, 100, 1920), sc, sh, s_, seed42_sign_bits(), "e2m1")
+        b = ops.fake_quant_signsplit(h, "e1m2_neg_e2m1_pos", 128, "kernel", global_clip=True)
+        c = ops.fake_quant(h, "e2m1", 128, "kernel")
+        torch.cuda.synchronize()
+        return [host(t) for t in (a, m, b, c)]
+
+    default = run()
+    L.set_tunable("smem_kb", kb)
+    try:
+        fixed = run()
+    finally:
+        L.set_tunable("smem_kb", 0)
+    for u, v in zip(default, fixed):
+        assert bits_equal(u, v)
+
+
 def test_results_identical_without_pdl(ops):
     """Plain stream-ordered launches (tunable pdl = 0) must give the same bits as programmatic dependent launches."""
     from fpqvar_b200 import _lib as L
