@@ -217,26 +217,35 @@ __device__ __forceinline__ int split_quant_tile_h16(uint32_t (&p)[NW], float& sn
     return 0;
 }
 
-// Whole-tensor clip of the reference (qu.py:421-422) when the tensor holds a NaN: every output becomes
-// +0.  workspace = {flag, ticket}: every CTA takes a ticket when its stores are done; the last one looks
-// at the flag, rewrites `out` if it is set (rare, slow, correct) and leaves the workspace zeroed for the
-// next call -- no second launch, no memset between calls.
-__device__ __forceinline__ void poison_epilogue(__half* __restrict__ out, size_t n, unsigned* __restrict__ ws) {
-    __shared__ unsigned s_last;
+// Whole-tensor clip of the reference (qu.py:421-422) when the tensor holds a NaN: every output becomes +0.
+// workspace = {flag, ticket}, zero between calls.  The common path must not wait for anything: a CTA whose stores are
+// issued fences them and bumps the ticket with a fire-and-forget wrapping increment (atomicInc modulo the grid size: after
+// gridDim.x increments the ticket is 0 again by itself -- no reset, no memset between calls, and no CTA ever waits for the
+// value).  The rare path: the ONE thread whose atomicOr turned the flag from 0 to 1 makes its CTA the owner of the
+// rewrite; the owner waits until every other CTA has bumped the ticket (they are all resident or done: the grid calls
+// launch_dependents first thing, and a single spinning CTA cannot starve the others), rewrites `out`, clears the flag and
+// bumps the ticket last.  (Round 1 had every CTA take a RETURNING ticket and the last one look at the flag: one more
+// atomic round trip and a second barrier at the end of every CTA, ~2 us on the launch-bound early stages.)
+__device__ __forceinline__ void poison_epilogue(__half* out, size_t n, unsigned* ws, bool owner) {
+    const int own = __syncthreads_or(owner ? 1 : 0);            // also: every warp of the CTA has issued its stores
+    if (!own) {
+        if (threadIdx.x == 0)               // release: this CTA's stores (made visible to this thread by the barrier) before the ticket
+            asm volatile("red.release.gpu.global.inc.u32 [%0], %1;" ::"l"(ws + 1), "r"(gridDim.x - 1) : "memory");
+        return;
+    }
+    if (threadIdx.x == 0) {
+        while (*reinterpret_cast<volatile unsigned*>(ws + 1) != gridDim.x - 1) {}
+        __threadfence();
+    }
+    __syncthreads();
+    for (size_t i = threadIdx.x; i < n / 8; i += blockDim.x) reinterpret_cast<uint4*>(out)[i] = make_uint4(0u, 0u, 0u, 0u);
+    for (size_t i = (n / 8) * 8 + threadIdx.x; i < n; i += blockDim.x) out[i] = __ushort_as_half(0);
     __syncthreads();
     if (threadIdx.x == 0) {
+        ws[0] = 0u;
         __threadfence();
-        s_last = (atomicAdd(ws + 1, 1u) == gridDim.x - 1) ? 1u : 0u;
+        atomicInc(ws + 1, gridDim.x - 1);
     }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    if (*reinterpret_cast<volatile unsigned*>(ws) != 0u) {
-        for (size_t i = threadIdx.x; i < n / 8; i += blockDim.x) reinterpret_cast<uint4*>(out)[i] = make_uint4(0u, 0u, 0u, 0u);
-        for (size_t i = (n / 8) * 8 + threadIdx.x; i < n; i += blockDim.x) out[i] = __ushort_as_half(0);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) { ws[0] = 0u; ws[1] = 0u; }
 }
 
 // GELU(tanh) of an fp16 value the way ATen's CUDA kernel computes it for a Half tensor (ActivationGeluKernel.cu,
@@ -268,6 +277,7 @@ __global__ void __launch_bounds__(256) signsplit_group_h16_kernel(const __half* 
     const size_t n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
     const float delta = tie_delta_kernel(uint32_t(warp_global >> 33));
     const size_t stride = n_warps * H16_GPW;
+    bool owner = false;                     // this thread turned the NaN flag from 0 to 1 (poison_epilogue)
     pdl_wait();
     auto load = [&](size_t gbase, uint32_t (&p)[H16_NW]) {
         const size_t g = gbase + lane / H16_LPG;
@@ -287,7 +297,7 @@ __global__ void __launch_bounds__(256) signsplit_group_h16_kernel(const __half* 
         const size_t g = gbase + lane / H16_LPG;
         float sn, sp;
         const int rc = split_quant_tile_h16<SPLIT, H16_LPG, H16_NW>(p, sn, sp, delta);
-        if (rc == 2 && nan_flag != nullptr) atomicOr(nan_flag, 1u);
+        if (rc == 2 && nan_flag != nullptr) owner |= (atomicOr(nan_flag, 1u) == 0u);     // exactly one thread of the grid sees the 0
         if (g < n_groups) {
             // rc != 0 leaves p untouched.  The literal sequences work from memory: with GELU fused in, the activated tile goes
             // to `out` first and is quantized there in place (all lanes of the group store before any of them rescans it)
@@ -303,7 +313,7 @@ __global__ void __launch_bounds__(256) signsplit_group_h16_kernel(const __half* 
         load(gbase, p);
         work(gbase, p);
     }
-    if (nan_flag != nullptr) poison_epilogue(out, n_groups * 128, nan_flag);
+    if (nan_flag != nullptr) poison_epilogue(out, n_groups * 128, nan_flag, owner);
 }
 
 static unsigned grid_h16(size_t n_groups) {

@@ -230,7 +230,7 @@ __device__ __forceinline__ uint32_t absmax_bits(const uint32_t (&p)[NW]) {
 // HW = true: the element function on the FP4 / FP6 conversion hardware (formats that have it): 5 instructions per pair
 // instead of 10 after the division.  Chosen per kernel from measurements: the register-tile kernels are no faster with it
 // (profiles/r2_quantizer_rounding_ab.txt); the streaming rotate kernel, which is issue-bound, is.
-template <int FMT, int LPG, int NW, bool HW = false>
+template <int FMT, int LPG, int NW, bool HW = true>
 __device__ __forceinline__ bool sym_quant_tile_h16(uint32_t (&p)[NW], float& s, float delta) {
     using HG = typename SymFmt<FMT>::HG;
     if constexpr (HW && HwCvt<HG>::AVAILABLE) {
@@ -317,73 +317,63 @@ static __device__ __noinline__ void literal_split_nan_group_h16(const __half* sr
 }
 
 // ---- sign-split ----------------------------------------------------------------------------
-// Elements > 0 use (rp, sp, POS grid), elements < 0 use (rn, sn, NEG grid); +0 / -0 give +0 on either side,
-// so the sign bit alone picks the side.  No NaN can reach these functions (groups that hold a NaN take the
-// literal path).  BOTH sides are evaluated for the whole pair with packed instructions and uniform constants,
-// and the sign bits pick the result per half with two LOP3 (ncu r1b had the per-element selects of the first
-// version as the busiest part: 72 % ALU pipe):
-//   positive side   w = half(x * rp) + 2^-17 -> conversion hardware (e2m1 / e2m3), as in the symmetric flow
-//   negative side   a UNIFORM grid (e1m2: step 1/4 up to 1.75; int: step 1 up to 32) is rounded entirely in packed
-//                   fp16 with a magic constant C = 1.5 * 2^10 * step, whose ulp is the step:
-//                       y = fma.rn.f16x2(v, 1 - 2^-11, C);   q = y - C
-//                   The factor 1 - 2^-11 moves v towards zero by less than one fp16 ulp: exact midpoints fall to the
-//                   side the kernel rule sends them to (the larger value, i.e. towards zero for v <= 0) and no other
-//                   fp16 value reaches or crosses a midpoint (midpoints are fp16 numbers).  The FMA rounds once.
-//                   A non-uniform negative grid (afpq: e2m1 on both sides) goes through the conversion hardware too.
+// Elements > 0 use (rp, sp, POS grid), elements < 0 use (rn, sn, NEG grid); +0 / -0 give +0 on either side, so the sign bit
+// alone picks the side.  No NaN can reach these functions (groups that hold a NaN take the literal path).
+// BOTH sides are evaluated for the whole pair with packed instructions and uniform constants, and the sign bits pick the
+// result per half at the end:
+//   positive side   w = half(x * rp) + 2^-17 -> conversion hardware (e2m1 / e2m3), as in sym_pair_h16_hw
+//   negative side   a UNIFORM grid (e1m2: step 1/4 up to 1.75; int: step 1 up to 32) is rounded entirely in packed fp16 with
+//                   a magic constant C = 1.5 * 2^10 * step, whose ulp is the step:  y = fma.rn.f16x2(v, 1 - 2^-11, C);
+//                   q = y - C.  The factor 1 - 2^-11 moves v towards zero by less than one fp16 ulp: exact midpoints fall
+//                   to the side the kernel rule sends them to (the larger value, i.e. towards zero for v <= 0) and no other
+//                   fp16 value reaches or crosses a midpoint.  A non-uniform negative grid (afpq: e2m1 on both sides) goes
+//                   through the conversion hardware too.
 // A lane of the wrong side computes garbage (possibly inf / NaN) that the select discards.
-// Per-element constants picked with integer multiply-adds on the FMA pipe (ncu r1b: the ALU pipe, where
-// FSEL / LOP3 / FMNMX / F2FP live, is the busy one; measured 5.40 -> 6.15 TB/s against LOP3 selects).  Sides with a
-// UNIFORM negative grid (e1m2: step 1/4 up to 1.75; int: step 1 up to 32) share the positive side's rounding constants:
-// the negative side is rescaled by the power of two K that maps its step onto the positive format's subnormal step
-// 2^(EMIN-M) (rn' = rn*K, sn' = sn/K, both exact), and p = 2^exponent(max(w, 2^EMIN)) is taken WITHOUT the absolute
-// value, so every negative w gets the constant p = 2^EMIN -- exactly the uniform grid.
-template <class NEG, class POS> struct SplitScale {
-    static constexpr bool UNIFORM_NEG = (NEG::M - NEG::EMIN == 2 && NEG::VNUM * 4 == 7 * NEG::VDEN) || (NEG::M == NEG::EMIN);
-    static constexpr float K = UNIFORM_NEG ? (Magic<POS>::EM / float(1u << POS::M)) / (Magic<NEG>::EM / float(1u << NEG::M)) : 1.0f;
+// Measured against the round-1 element function (per-element constants selected with integer multiply-adds, magic-number
+// rounding on both sides; profiles/r2_signsplit_ab.txt): 10 % slower on one isolated launch at full clocks (5.73 vs 6.36 TB/s),
+// 7 % faster sustained under the 1000 W cap (6.07 vs 5.68 TB/s at 487 vs 592 W), 8 % faster inside the step (5.59 vs 5.18).
+template <class NEG> struct UniformNeg {
+    static constexpr bool OK = (NEG::M - NEG::EMIN == 2 && NEG::VNUM * 4 == 7 * NEG::VDEN) || (NEG::M == NEG::EMIN);
+    static constexpr float STEP = Magic<NEG>::EM / float(1u << NEG::M);
+    static constexpr float C = 1536.0f * STEP;                 // 1.5 * 2^10 * step
 };
 struct SplitK {
-    int rp, rd, sp, sd;          // bit patterns: positive-side constant and (positive - negative) difference, for r and s
+    uint64_t rn2, rp2;          // RN(1/s) of each side as packed fp32 pairs (0 for a side without elements)
+    uint32_t snh2, sph2;        // the two scales as fp16 pairs
 };
 template <class NEG, class POS>
 __device__ __forceinline__ SplitK make_splitk(float sn, float rn, float sp, float rp) {
-    constexpr float K = SplitScale<NEG, POS>::K;
     SplitK k;
-    k.rp = __float_as_int(rp);
-    k.rd = __float_as_int(rp) - __float_as_int(rn * K);
-    k.sp = __float_as_int(sp);
-    k.sd = __float_as_int(sp) - __float_as_int(sn * (1.0f / K));
+    k.rn2 = pk(rn, rn);
+    k.rp2 = pk(rp, rp);
+    k.snh2 = dup_h(__float2half_rn(sn));
+    k.sph2 = dup_h(__float2half_rn(sp));
     return k;
-}
-// pos for m = 0, neg for m = -1
-__device__ __forceinline__ float sel_imad(int m, int pos, int pos_minus_neg) {
-    int d;
-    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(m), "r"(pos_minus_neg), "r"(pos));
-    return __int_as_float(d);
 }
 template <class NEG, class POS>
 __device__ __forceinline__ uint32_t split_pair_h16_w(uint64_t xf2, uint32_t x2, const SplitK& k, float delta) {
-    const F2 x = unpk(xf2);
-    const int m0 = __float_as_int(x.lo) >> 31, m1 = __float_as_int(x.hi) >> 31;      // -1: negative side
-    const float r0 = sel_imad(m0, k.rp, k.rd), r1 = sel_imad(m1, k.rp, k.rd);
-    const float s0 = sel_imad(m0, k.sp, k.sd), s1 = sel_imad(m1, k.sp, k.sd);
-    const uint32_t v2 = pack_h2_u64(fmul2(xf2, pk(r0, r1)));
-    const float w0 = fhadd(uint16_t(v2 & 0xffffu), delta);
-    const float w1 = fhadd(uint16_t(v2 >> 16), delta);
-    uint64_t q;
-    if constexpr (SplitScale<NEG, POS>::UNIFORM_NEG) {
-        const float p0 = __uint_as_float(__float_as_uint(fmaxf(w0, Magic<POS>::EM)) & 0x7F800000u);     // signed max
-        const float p1 = __uint_as_float(__float_as_uint(fmaxf(w1, Magic<POS>::EM)) & 0x7F800000u);
-        const uint64_t p = pk(p0, p1), w = pk(w0, w1);
-        const uint64_t y = ffma2(p, pk(Magic<POS>::SC, Magic<POS>::SC), w);
-        q = ffma2(p, pk(-Magic<POS>::SC, -Magic<POS>::SC), y);
+    static_assert(HwCvt<POS>::AVAILABLE && HwCvt<POS>::PRE == 1.0f, "the positive side of every sign-split format is e2m1 or e2m3");
+    const uint32_t vp2 = pack_h2_u64(fmul2(xf2, k.rp2));                           // half(x/sp)
+    const uint32_t vn2 = pack_h2_u64(fmul2(xf2, k.rn2));                           // half(x/sn)
+    const uint32_t qp2 = HwCvt<POS>::round_trip(fhadd(uint16_t(vp2 & 0xffffu), delta), fhadd(uint16_t(vp2 >> 16), delta));
+    uint32_t qn2;
+    if constexpr (UniformNeg<NEG>::OK) {
+        const uint32_t c2 = dup_h(__float2half_rn(UniformNeg<NEG>::C));
+        qn2 = hadd2(hfma2(vn2, 0x3BFF3BFFu, c2), c2 ^ 0x80008000u);                // (v * (1 - 2^-11) + C) - C
     } else {
-        static_assert(Magic<NEG>::EM == Magic<POS>::EM && Magic<NEG>::SC == Magic<POS>::SC, "non-uniform negative grids must share the positive format");
-        q = round_pair_magic(w0, w1, Magic<POS>::EM, Magic<POS>::SC);
+        static_assert(HwCvt<NEG>::AVAILABLE && HwCvt<NEG>::PRE == 1.0f, "non-uniform negative grids must be hardware formats");
+        qn2 = HwCvt<NEG>::round_trip(fhadd(uint16_t(vn2 & 0xffffu), delta), fhadd(uint16_t(vn2 >> 16), delta));
     }
-    return pack_h2_u64(fmul2(q, pk(s0, s1)));
+    uint32_t neg;                                                                  // 0xFFFF in every half whose sign bit is set
+    asm("prmt.b32 %0, %1, 0, 0xBB99;" : "=r"(neg) : "r"(x2));
+    const uint32_t q2 = (qp2 & ~neg) | (qn2 & neg);
+    const uint32_t s2 = (k.sph2 & ~neg) | (k.snh2 & neg);
+    return hfma2(q2, s2, 0u);                                                      // half(q*s), -0 -> +0
 }
+
 template <class NEG, class POS>
 __device__ __forceinline__ uint32_t split_pair_h16(uint32_t x2, const SplitK& k, float delta) {
     return split_pair_h16_w<NEG, POS>(widen_h2(x2), x2, k, delta);
 }
+
 }  // namespace fpq

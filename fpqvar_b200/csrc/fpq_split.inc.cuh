@@ -253,6 +253,7 @@ __global__ void __launch_bounds__(1024) signsplit_row_reg_kernel(const InT* __re
         const float sn = red[96], sp = red[97], rn = red[98], rp = red[99];
         const bool fast = red[100] != 0.0f;
         const SplitK sk = make_splitk<typename SF::NEG, typename SF::POS>(sn, rn, sp, rp);
+        auto pair = [&](uint32_t w2) { return split_pair_h16<typename SF::NEG, typename SF::POS>(w2, sk, delta); };
 #pragma unroll
         for (int k = 0; k < V; ++k) {
             const int vi = tid + k * nt;
@@ -263,10 +264,10 @@ __global__ void __launch_bounds__(1024) signsplit_row_reg_kernel(const InT* __re
                 // registers are not addressable), so the loop the hardware fetches stays small
                 uint4 o;
                 if (fast) {
-                    o.x = split_pair_h16<typename SF::NEG, typename SF::POS>(w[0], sk, delta);
-                    o.y = split_pair_h16<typename SF::NEG, typename SF::POS>(w[1], sk, delta);
-                    o.z = split_pair_h16<typename SF::NEG, typename SF::POS>(w[2], sk, delta);
-                    o.w = split_pair_h16<typename SF::NEG, typename SF::POS>(w[3], sk, delta);
+                    o.x = pair(w[0]);
+                    o.y = pair(w[1]);
+                    o.z = pair(w[2]);
+                    o.w = pair(w[3]);
                 } else {
                     o = signsplit_vec_literal_h16<SPLIT>(u[k], sn, sp);
                 }

@@ -48,7 +48,9 @@ def test_rounding_exhaustive(ops, code, tie):
 def test_f16_flow_exhaustive(ops, code):
     """Packed fp16 fast path (division-free, magic-number rounding) == literal reference sequence
     for every (x, scale) pair of fp16 values that can occur in a regular group.  Codes 32 + format: the element function on
-    the FP4 / FP6 conversion hardware (e2m1, e1m2, e2m3, e3m2), which the format scorer uses."""
+    the FP4 / FP6 conversion hardware (e2m1, e1m2, e2m3, e3m2) that the group, rotate and scoring kernels use; codes 0..4: the
+    magic-number element function (e3m0 everywhere, and the per-token row kernels); 16 + split format: the sign-split element
+    function (conversion hardware on the positive side, packed fp16 magic constant on a uniform negative side)."""
     bad, first = ops.selftest_f16_flow(code)
     assert bad == 0, (f"format code {code}: {bad} mismatches, first at scale bits 0x{0x0400 + (first >> 16):04x}, "
                       f"x bits 0x{first & 0xffff:04x}")

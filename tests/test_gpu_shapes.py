@@ -307,3 +307,34 @@ def test_concurrent_host_threads_and_streams(ops):
         th.join()
     assert not errors, errors
     assert counts == [3 * iters] * n_threads
+
+
+def test_whole_tensor_clip_protocol_under_stress(ops):
+    """The {flag, ticket} protocol of the packed sign-split kernel (fire-and-forget wrapping tickets, one owner CTA for the
+    rewrite): clean and poisoned calls of different sizes back to back on one stream and workspace, NaNs in one group, in
+    many groups and in EVERY group (every CTA sees one: still exactly one owner), single-CTA grids -- every output is what
+    the reference's clamp gives, and the workspace is zero afterwards."""
+    from fpqvar_b200 import ops as OPS
+    g = torch.Generator(device="cuda").manual_seed(77)
+    ws = OPS._clip_workspace(torch.device("cuda", torch.cuda.current_device()))
+    sizes = [(1, 128), (3, 256), (100, 7680), (4096, 1024), (25600, 1920), (7, 128 * 9)]
+    results = []
+    for rnd in range(3):
+        for rows, cols in sizes:
+            x = torch.nn.functional.gelu(torch.randn(rows, cols, device="cuda", generator=g)).half()
+            kind = (rnd + rows) % 4
+            if kind == 1:
+                x[rows // 2, 3] = float("nan")
+            elif kind == 2:
+                x[:, ::128] = float("nan")                             # a NaN in every group
+            elif kind == 3:
+                x[torch.rand(rows, cols, device="cuda", generator=g) < 1e-4] = float("nan")
+            y = ops.fake_quant_signsplit(x, "e1m2_neg_e2m1_pos", 128, "kernel", global_clip=True)
+            results.append((x, y, bool(torch.isnan(x).any())))
+    torch.cuda.synchronize()
+    assert ws.tolist() == [0, 0], "workspace not left zeroed"
+    for x, y, poisoned in results:
+        if poisoned:
+            assert float(y.abs().max()) == 0.0 and not bool(torch.isnan(y).any())
+        else:
+            assert bits_equal(host(y), O.fake_quant_signsplit(host(x), "e1m2_neg_e2m1_pos", 128, "kernel"))
