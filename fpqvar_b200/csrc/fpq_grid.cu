@@ -122,13 +122,16 @@ void prefer_carveout(const void* kernel) {
 }
 
 int sm_count() {
-    static int n = 0;
-    if (n == 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    // per device ordinal (a process may drive several GPUs; the occupancy caches of the row kernels are per kernel only:
+    // they depend on the kernel's registers and the architecture, and this library runs on B200s alone)
+    static int n[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int& c = n[dev & 63];
+    if (c == 0) {
+        if (cudaDeviceGetAttribute(&c, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || c <= 0) c = 148;
     }
-    return n;
+    return c;
 }
 
 }  // namespace fpq
