@@ -156,6 +156,12 @@ extern "C" int fpq_set_tunable(const char* name, long long value) {
         g_tun.smem_kb = int(value);
         return FPQ_OK;
     }
+    if (strcmp(name, "gemm_stages") == 0) {
+        if (value < 2 || value > 6) return FPQ_ERR_ARG;
+        g_tun.gemm_stages = int(value);
+        return FPQ_OK;
+    }
+    if (strcmp(name, "gemm_desc_swap") == 0) { g_tun.gemm_desc_swap = value != 0; return FPQ_OK; }
     return FPQ_ERR_ARG;
 }
 

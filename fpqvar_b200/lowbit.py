@@ -1,0 +1,153 @@
+"""Packed low-bit operands and the real low-bit linear layer.
+
+The reference's QuantizedLinear.forward is `act_quant(x)` -> `F.linear(q_x, W_q, b)` on fp16 tensors
+(models_fp_quant_transform_rotate/quant_utils.py:764-769).  Here the quantizer emits (grid value, scale per row and
+128-group) -- `PackedCodes` -- and `linear_codes` multiplies two of them on the tensor cores (csrc/fpq_gemm.cu, tcgen05.mma
+kind::f8f6f4).  `QuantizedLinearLowBit` is the module form: `from_quantized(QuantizedLinear)` packs the weight once, forward
+packs the activation and runs the GEMM.  No fallback: without the CUDA library every call raises.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from .ops import _on_device, _require_cuda, _stream
+
+_DT = {torch.float32: L.FPQ_F32, torch.float16: L.FPQ_F16}
+GROUP = 128
+FP4_FORMATS = ("e2m1", "e1m2", "e3m0")
+
+
+def rows_padded(rows: int) -> int:
+    return (rows + 127) // 128 * 128
+
+
+@dataclass
+class PackedCodes:
+    """rows x k values as one e4m3 byte per element (the grid value, exact) and one fp32 scale per (row, 128-group), in the
+    tile order of include/fpq_b200.h: codes [k/128][rows_pad/8][8][8][16] bytes, scales [k/128][rows_pad]."""
+    codes: torch.Tensor        # uint8 [rows_pad * k]
+    scales: torch.Tensor       # float32 [k / 128, rows_pad]
+    rows: int
+    k: int
+    fmt: str
+
+    @property
+    def rows_pad(self) -> int:
+        return rows_padded(self.rows)
+
+    def dequantize(self, dtype=torch.float16) -> torch.Tensor:
+        """The fake-quantized tensor these codes stand for ([rows, k]); bit-identical to ops.fake_quant of the packed input
+        when `dtype` is the input's dtype."""
+        out = torch.empty((self.rows, self.k), dtype=dtype, device=self.codes.device)
+        with _on_device(self.codes) as dev:
+            L.check(L.lib().fpq_unpack_codes(self.codes.data_ptr(), self.scales.data_ptr(), self.rows, self.k, _DT[dtype],
+                                             out.data_ptr(), _stream(dev)), "fpq_unpack_codes")
+        return out
+
+    def to_nibbles(self) -> torch.Tensor:
+        """4-bit storage (FP4 formats only): uint8 [rows_pad * k / 2]."""
+        nib = torch.empty(self.codes.numel() // 2, dtype=torch.uint8, device=self.codes.device)
+        with _on_device(self.codes) as dev:
+            L.check(L.lib().fpq_codes_to_nibbles(self.codes.data_ptr(), self.codes.numel(), L.FMT[self.fmt], nib.data_ptr(),
+                                                 _stream(dev)), f"fpq_codes_to_nibbles({self.fmt})")
+        return nib
+
+    @staticmethod
+    def from_nibbles(nib: torch.Tensor, scales: torch.Tensor, rows: int, k: int, fmt: str) -> "PackedCodes":
+        _require_cuda(nib, "from_nibbles")
+        codes = torch.empty(nib.numel() * 2, dtype=torch.uint8, device=nib.device)
+        with _on_device(nib) as dev:
+            L.check(L.lib().fpq_nibbles_to_codes(nib.data_ptr(), codes.numel(), L.FMT[fmt], codes.data_ptr(), _stream(dev)),
+                    f"fpq_nibbles_to_codes({fmt})")
+        return PackedCodes(codes, scales, rows, k, fmt)
+
+
+def pack_codes(x: torch.Tensor, fmt: str) -> PackedCodes:
+    """fp_quant_*_per_group_cuda (groups of 128 along the last dim, kernel tie rule) with the codes kept instead of multiplied
+    back.  x: [..., k] float16 / float32 CUDA tensor; leading dims are flattened into rows."""
+    _require_cuda(x, "pack_codes")
+    if x.dtype not in _DT:
+        raise L.FpqError(f"pack_codes: dtype {x.dtype} is not supported (float16 / float32 only)")
+    if fmt not in L.FMT:
+        raise ValueError("Unsupported fp_type.")
+    k = x.shape[-1]
+    if k % GROUP != 0:
+        raise L.FpqError(f"pack_codes: last dim {k} is not a multiple of {GROUP}")
+    x2 = x.reshape(-1, k)
+    if not x2.is_contiguous():
+        x2 = x2.contiguous()
+    rows = x2.shape[0]
+    rp = rows_padded(rows)
+    codes = torch.empty(rp * k, dtype=torch.uint8, device=x.device)
+    scales = torch.empty((k // GROUP, rp), dtype=torch.float32, device=x.device)
+    with _on_device(x2) as dev:
+        L.check(L.lib().fpq_pack_codes(x2.data_ptr(), rows, k, _DT[x2.dtype], L.FMT[fmt], codes.data_ptr(), scales.data_ptr(),
+                                       _stream(dev)), f"fpq_pack_codes({fmt})")
+    return PackedCodes(codes, scales, rows, k, fmt)
+
+
+def linear_codes(a: PackedCodes, w: PackedCodes, bias: Optional[torch.Tensor] = None, out_dtype=torch.float16,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """F.linear(a, w, bias) for packed operands: [a.rows, w.rows] in `out_dtype`."""
+    if a.k != w.k:
+        raise L.FpqError(f"linear_codes: inner sizes differ ({a.k} vs {w.k})")
+    if a.codes.device != w.codes.device:
+        raise L.FpqError("linear_codes: operands on different devices")
+    if out_dtype not in _DT:
+        raise L.FpqError(f"linear_codes: output dtype {out_dtype} is not supported")
+    m, n = a.rows, w.rows
+    if n % 8 != 0:
+        raise L.FpqError(f"linear_codes: out_features {n} must be a multiple of 8")
+    if out is None:
+        out = torch.empty((m, n), dtype=out_dtype, device=a.codes.device)
+    elif out.shape != (m, n) or out.dtype != out_dtype or not out.is_contiguous() or out.device != a.codes.device:
+        raise L.FpqError("linear_codes: `out` must be a contiguous [m, n] tensor of out_dtype on the operands' device")
+    b = None
+    if bias is not None:
+        _require_cuda(bias, "linear_codes(bias)")
+        if bias.numel() != n:
+            raise L.FpqError(f"linear_codes: bias has {bias.numel()} entries, expected {n}")
+        b = bias.detach().to(torch.float32).contiguous()
+    with _on_device(a.codes) as dev:
+        L.check(L.lib().fpq_gemm_codes(a.codes.data_ptr(), a.scales.data_ptr(), m, w.codes.data_ptr(), w.scales.data_ptr(), n, a.k,
+                                       None if b is None else b.data_ptr(), _DT[out_dtype], out.data_ptr(), n, _stream(dev)),
+                "fpq_gemm_codes")
+    return out
+
+
+class QuantizedLinearLowBit(torch.nn.Module):
+    """QuantizedLinear (qu.py:649-867) with the fake-quantized weight held as codes and the product computed from codes:
+    forward(x) = linear_codes(pack_codes(x, act_fmt), weight_codes, bias).  Symmetric per-group formats only (mat_qkv, proj,
+    fc1 of the README configuration; the sign-split fc2 input has two scales per group and stays on the fake-quant path)."""
+
+    def __init__(self, weight: PackedCodes, bias: Optional[torch.Tensor], act_fmt: str, out_dtype=torch.float16):
+        super().__init__()
+        self.in_features, self.out_features = weight.k, weight.rows
+        self.weight_fmt, self.act_fmt, self.out_dtype = weight.fmt, act_fmt, out_dtype
+        self.register_buffer("weight_codes", weight.codes)
+        self.register_buffer("weight_scales", weight.scales)
+        self.register_buffer("bias", None if bias is None else bias.detach().to(torch.float32).contiguous())
+
+    @classmethod
+    def from_float(cls, module: torch.nn.Linear, weight_fmt: str = "e2m1", act_fmt: str = "e2m1", out_dtype=torch.float16):
+        """module.weight: [out, in] on a CUDA device; quantized exactly as QuantizedLinear.from_float does for
+        weight_quant='per_group' (qu.py:772-813: fp_quant_*_per_group_cuda on the fp32 weight)."""
+        w = module.weight.detach()
+        _require_cuda(w, "QuantizedLinearLowBit.from_float")
+        return cls(pack_codes(w.to(torch.float32), weight_fmt), module.bias, act_fmt, out_dtype)
+
+    def weight_packed(self) -> PackedCodes:
+        return PackedCodes(self.weight_codes, self.weight_scales, self.out_features, self.in_features, self.weight_fmt)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        a = pack_codes(x, self.act_fmt)
+        y = linear_codes(a, self.weight_packed(), self.bias, self.out_dtype)
+        return y.reshape(*x.shape[:-1], self.out_features)
+
+    def extra_repr(self) -> str:
+        return (f"{self.in_features}, {self.out_features}, bias={self.bias is not None}, weight={self.weight_fmt} codes, "
+                f"act={self.act_fmt} per_group(128), tcgen05 e4m3-container GEMM")

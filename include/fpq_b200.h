@@ -26,6 +26,7 @@
  *                             rotate_utils/rotation_utils.py:129-154
  *   fpq_score_formats         search/search_fp4_format.py:340-374,472-476,840-893 and
  *                             search/search_fp6_format.py:547-554 (tensor-level quantize + MSE)
+ *   fpq_pack_codes / fpq_gemm_codes   QuantizedLinear.forward qu.py:764-769 (act_quant + F.linear) as a real low-bit GEMM
  */
 #ifndef FPQ_B200_H
 #define FPQ_B200_H
@@ -250,6 +251,45 @@ FPQ_API int fpq_selftest_rounding(int format, int tie_mode, unsigned long long *
  * hardware (the format scorer's).  result as in fpq_selftest_rounding.
  */
 FPQ_API int fpq_selftest_f16_flow(int format, unsigned long long *result, void *stream);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Packed low-bit operands and the real low-bit GEMM.  NOT in the reference: QuantizedLinear.forward
+ * (qu.py:764-769, :991-996) fake-quantizes the activation and calls F.linear on fp16 tensors whose values happen to lie on
+ * scale * grid.  Here the same quantizer emits what those tensors ARE -- one grid value per element and one scale per
+ * (row, 128-group) -- and the product runs on the tensor cores in 8-bit containers (tcgen05.mma kind::f8f6f4), the scales
+ * applied per 128-deep K slab.  Numerics contract: fpq_unpack_codes(fpq_pack_codes(x)) is bit-identical to
+ * fp_quant_*_per_group_cuda(x) (qu.py:265-378, :537-574; the reference's dtype rules: an fp16 input has an fp16-rounded scale);
+ * fpq_gemm_codes is bit-identical to oracle/gemm_codes.c (fixed fp32 operation order) and differs from the reference's fp16
+ * GEMM of the fake-quantized tensors only by that GEMM's own roundings (each product term fp16-rounded once in the reference,
+ * never here; tolerance stated in tests/test_gpu_gemm_codes.py).
+ *
+ * Layout of an operand of `rows` x k (k % 128 == 0), rows_pad = fpq_codes_rows_padded(rows) = rows rounded up to 128:
+ *   codes  : rows_pad * k bytes, [k/128 slabs][rows_pad/8][8 chunks of 16 K][8 rows][16 bytes]; byte = e4m3 encoding of the grid
+ *            value (every FP4 / FP6 grid of the reference is a subset of e4m3); padding rows hold 0
+ *   scales : fp32 [k/128][rows_pad]; 0 for the padding rows
+ * so that a 128-row x 128-K tile is 16 KB of contiguous memory in the tensor core's K-major core-matrix order.
+ * ------------------------------------------------------------------------------------------------------------------ */
+FPQ_API size_t fpq_codes_rows_padded(size_t rows);
+/* x: [rows, k] contiguous, FPQ_F16 | FPQ_F32, 16-byte aligned; format: FPQ_FMT_*; groups of 128 along k; kernel tie rule. */
+FPQ_API int fpq_pack_codes(const void *x, size_t rows, size_t k, int in_dtype, int format, uint8_t *codes, float *scales,
+                   void *stream);
+/* out[r, c] = out_dtype( fl32(q) * scale ): the fake-quantized tensor the codes stand for, [rows, k] contiguous. */
+FPQ_API int fpq_unpack_codes(const uint8_t *codes, const float *scales, size_t rows, size_t k, int out_dtype, void *out,
+                   void *stream);
+/* 4-bit storage of the FP4 formats (FPQ_FMT_E2M1 | E1M2 | E3M0): nibble = sign << 3 | index of |q| in the ascending
+ * non-negative half grid; byte i of `nibbles` holds codes 2i (low nibble) and 2i+1.  n_codes % 8 == 0.  Lossless both ways. */
+FPQ_API int fpq_codes_to_nibbles(const uint8_t *codes, size_t n_codes, int format, uint8_t *nibbles, void *stream);
+FPQ_API int fpq_nibbles_to_codes(const uint8_t *nibbles, size_t n_codes, int format, uint8_t *codes, void *stream);
+/*
+ * C[i, j] = bias[j] + sum_t fma-chain over the k/128 slabs t (ascending) of  (P_t[i, j] * sa[t, i]) * sw[t, j],
+ *           P_t[i, j] = sum over the slab's 128 k of qa[i, k] * qw[j, k]      (exact; fp32 accumulate in tensor memory)
+ * i.e. F.linear(A, W, bias) for A = [m, k] and W = [n, k] given as codes.  c: [m, ldc] row-major, FPQ_F16 | FPQ_F32, 16-byte
+ * aligned, n % 8 == 0, ldc % 8 == 0; bias: fp32 [n] or NULL.  One 128 x 128 tile per CTA, 203 KB of shared memory.
+ * Tunables: "gemm_stages" (2..6, default 6), "gemm_desc_swap" (bring-up aid, default 0).
+ */
+FPQ_API int fpq_gemm_codes(const uint8_t *a_codes, const float *a_scales, size_t m, const uint8_t *b_codes,
+                   const float *b_scales, size_t n, size_t k, const float *bias, int out_dtype, void *c, size_t ldc,
+                   void *stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,164 @@
+"""GPU parity of the packed low-bit operands and the low-bit GEMM (csrc/fpq_gemm.cu) through the C ABI, against
+oracle/lowbit.py + oracle/gemm_codes.c.  Bars: codes, scales and dequantized tensors bit-exact; GEMM bit-exact against the
+fixed-order oracle (the slab sums are exact, the fp32 scale chain has a defined order); against the reference's own expression
+-- F.linear on the fake-quantized fp16 tensors, QuantizedLinear.forward qu.py:764-769 -- within the tolerance written below."""
+import numpy as np
+import pytest
+import torch
+
+from fpqvar_b200 import _lib as L, lowbit, ops
+from oracle import lowbit as LB, oracle as O          # checker only
+
+pytestmark = pytest.mark.gpu
+FMTS = ["e2m1", "e1m2", "e3m0", "e2m3", "e3m2"]
+
+
+def bits(a):
+    return a.view({1: np.uint8, 2: np.uint16, 4: np.uint32}[a.dtype.itemsize])
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def same_bits(a, b):
+    """bit-identical, NaN payloads aside (signed zeros and NaN positions count)"""
+    a, b = np.asarray(a), np.asarray(b)
+    na, nb = np.isnan(a), np.isnan(b)
+    return a.shape == b.shape and np.array_equal(na, nb) and np.array_equal(bits(a)[~na], bits(b)[~nb])
+
+
+def adversarial(rng, rows, k, dtype):
+    x = rng.standard_normal((rows, k)).astype(dtype)
+    x[0, :128] = 0
+    x[1, 5] = np.inf
+    x[2, 130] = np.nan
+    x[3, :128] = (x[3, :128].astype(np.float32) * 2.0 ** -20).astype(dtype)
+    x[4, :8] = np.asarray([0.25, 0.75, 1.25, 1.75, 2.5, 3.5, 5.0, 6.0], dtype=dtype)
+    return x
+
+
+@pytest.mark.parametrize("fmt", FMTS)
+@pytest.mark.parametrize("dtype", [np.float16, np.float32])
+@pytest.mark.parametrize("rows", [1, 300])
+def test_pack_codes_bit_exact(fmt, dtype, rows):
+    rng = np.random.default_rng(rows)
+    x = adversarial(rng, max(rows, 5), 384, dtype)[:rows] if rows >= 5 else rng.standard_normal((rows, 384)).astype(dtype)
+    p = lowbit.pack_codes(torch.from_numpy(x).to(dev()), fmt)
+    wc, ws = LB.pack_codes(x, fmt)
+    assert np.array_equal(p.codes.cpu().numpy(), wc)
+    assert same_bits(p.scales.cpu().numpy(), ws)
+    # and the codes stand for exactly the tensor the fake-quant kernels (and the reference) produce
+    out_dt = torch.float16 if dtype == np.float16 else torch.float32
+    got = p.dequantize(out_dt)
+    want = ops.fake_quant(torch.from_numpy(x).to(dev()), fmt, 128, "kernel")
+    if want.dtype != out_dt:                        # the FP6 functions force fp16 (qu.py:553,573)
+        got = p.dequantize(want.dtype)
+    assert same_bits(got.cpu().numpy(), want.cpu().numpy())
+    assert same_bits(got.cpu().numpy(), O.fake_quant(x, fmt, 128, "kernel", out_dtype=got.cpu().numpy().dtype))
+
+
+@pytest.mark.parametrize("fmt", ["e2m1", "e1m2", "e3m0"])
+def test_nibble_storage_round_trip(fmt):
+    rng = np.random.default_rng(7)
+    x = rng.standard_normal((200, 256)).astype(np.float16)
+    p = lowbit.pack_codes(torch.from_numpy(x).to(dev()), fmt)
+    nib = p.to_nibbles()
+    assert nib.numel() * 2 == p.codes.numel()
+    assert np.array_equal(nib.cpu().numpy(), LB.codes_to_nibbles(p.codes.cpu().numpy(), fmt))
+    back = lowbit.PackedCodes.from_nibbles(nib, p.scales, p.rows, p.k, fmt)
+    assert torch.equal(back.codes, p.codes)
+
+
+def test_nibble_storage_rejects_fp6():
+    p = lowbit.pack_codes(torch.randn(8, 128, device=dev(), dtype=torch.float16), "e2m3")
+    with pytest.raises(L.FpqError):
+        p.to_nibbles()
+
+
+def _operands(rng, m, n, k, fmt_a, fmt_w, dtype_a=np.float16):
+    x = rng.standard_normal((m, k)).astype(dtype_a)
+    w = (rng.standard_normal((n, k)) * 0.05).astype(np.float32)
+    return x, w, LB.quantize_codes(x, fmt_a), LB.quantize_codes(w, fmt_w)
+
+
+@pytest.mark.parametrize("m,n,k", [(128, 128, 128), (128, 128, 256), (1, 8, 128), (100, 136, 384), (300, 384, 1920), (257, 128, 7680)])
+@pytest.mark.parametrize("stages", [6, 2])
+def test_gemm_codes_bit_exact_against_the_fixed_order_oracle(m, n, k, stages):
+    rng = np.random.default_rng(m + n + k)
+    x, w, (qa, sa), (qw, sw) = _operands(rng, m, n, k, "e2m1", "e2m1")
+    bias = rng.standard_normal(n).astype(np.float32)
+    a = lowbit.pack_codes(torch.from_numpy(x).to(dev()), "e2m1")
+    ww = lowbit.pack_codes(torch.from_numpy(w).to(dev()), "e2m1")
+    L.set_tunable("gemm_stages", stages)
+    try:
+        c32 = lowbit.linear_codes(a, ww, torch.from_numpy(bias).to(dev()), torch.float32).cpu().numpy()
+        c16 = lowbit.linear_codes(a, ww, None, torch.float16).cpu().numpy()
+    finally:
+        L.set_tunable("gemm_stages", 6)
+    assert np.array_equal(bits(c32), bits(LB.gemm_codes(qa, sa, qw, sw, bias)))
+    assert np.array_equal(bits(c16), bits(LB.gemm_codes(qa, sa, qw, sw).astype(np.float16)))
+
+
+@pytest.mark.parametrize("fmt_a,fmt_w", [("e1m2", "e3m0"), ("e2m3", "e2m3"), ("e3m2", "e2m1"), ("e3m2", "e3m2")])
+def test_gemm_codes_other_formats(fmt_a, fmt_w):
+    rng = np.random.default_rng(11)
+    x, w, (qa, sa), (qw, sw) = _operands(rng, 130, 256, 640, fmt_a, fmt_w, np.float32)
+    a = lowbit.pack_codes(torch.from_numpy(x).to(dev()), fmt_a)
+    ww = lowbit.pack_codes(torch.from_numpy(w).to(dev()), fmt_w)
+    c = lowbit.linear_codes(a, ww, None, torch.float32).cpu().numpy()
+    assert np.array_equal(bits(c), bits(LB.gemm_codes(qa, sa, qw, sw)))
+
+
+def test_gemm_codes_against_the_reference_expression_fp16_linear():
+    """QuantizedLinear.forward (qu.py:764-769): F.linear(act_quant(x), W_q, b) under fp16 autocast.  The fp16 GEMM rounds every
+    activation value q*s to fp16 (done by the quantizer, qu.py:329), the weight to fp16 (autocast), accumulates in fp32 and rounds
+    the output to fp16.  Stated tolerance: |diff| <= 2^-10 * sum_k |x_q w_q| (operand roundings) + 1 fp16 ulp of the result."""
+    torch.manual_seed(0)
+    m, n, k = 1000, 384, 1920
+    x = torch.randn(m, k, device=dev(), dtype=torch.float16)
+    lin = torch.nn.Linear(k, n, bias=True, device=dev())
+    mod = lowbit.QuantizedLinearLowBit.from_float(lin, "e2m1", "e2m1")
+    y = mod(x)
+    xq = ops.fake_quant(x, "e2m1", 128, "kernel")
+    wq = ops.fake_quant(lin.weight.detach(), "e2m1", 128, "kernel")
+    ref = torch.nn.functional.linear(xq, wq.half(), lin.bias.detach().half())
+    mag = xq.abs().double() @ wq.abs().double().T + lin.bias.detach().abs().double()
+    tol = 2.0 ** -10 * mag + 2.0 ** -10 * ref.abs().double() + 1e-7
+    assert y.shape == ref.shape and y.dtype == torch.float16
+    assert bool(((y.double() - ref.double()).abs() <= tol).all())
+    # and against float64 on the exact operand values the codes stand for: fp32-chain accuracy
+    exact = xq.double() @ wq.double().T + lin.bias.detach().double()
+    y32 = lowbit.linear_codes(lowbit.pack_codes(x, "e2m1"), mod.weight_packed(), lin.bias.detach(), torch.float32)
+    assert bool(((y32.double() - exact).abs() <= 2.0 ** -11 * mag + 1e-7).all())        # q*s fp16-rounded in xq, exact in the codes
+
+
+def test_gemm_codes_full_size_properties():
+    """BASELINE configs[2] largest mat_qkv call (25 600 token rows of stage 9, C = 1920 -> 5760): exact power-of-two scale
+    equivariance, row-block independence, and agreement with the fp16 library GEMM on the fake-quantized tensors."""
+    torch.manual_seed(1)
+    m, n, k = 25600, 5760, 1920
+    x = torch.randn(m, k, device=dev(), dtype=torch.float16)
+    w = torch.randn(n, k, device=dev()) * 0.02
+    a, ww = lowbit.pack_codes(x, "e2m1"), lowbit.pack_codes(w, "e2m1")
+    y = lowbit.linear_codes(a, ww, None, torch.float32)
+    a4 = lowbit.PackedCodes(a.codes, a.scales * 4.0, a.rows, a.k, a.fmt)
+    assert torch.equal(lowbit.linear_codes(a4, ww, None, torch.float32), y * 4.0)
+    sub = lowbit.linear_codes(lowbit.pack_codes(x[5000:5300], "e2m1"), ww, None, torch.float32)
+    assert torch.equal(sub, y[5000:5300])
+    ref = torch.nn.functional.linear(ops.fake_quant(x, "e2m1", 128, "kernel"), ops.fake_quant(w, "e2m1", 128, "kernel").half())
+    err = (y - ref.float()).abs().max().item()
+    assert err <= 2.0 ** -8 * ref.float().abs().max().item()
+
+
+def test_gemm_codes_argument_errors():
+    a = lowbit.pack_codes(torch.randn(8, 256, device=dev(), dtype=torch.float16), "e2m1")
+    w = lowbit.pack_codes(torch.randn(16, 128, device=dev()), "e2m1")
+    with pytest.raises(L.FpqError):
+        lowbit.linear_codes(a, w)
+    with pytest.raises(L.FpqError):
+        lowbit.pack_codes(torch.randn(8, 100, device=dev()), "e2m1")
+    with pytest.raises(L.FpqError):
+        lowbit.pack_codes(torch.randn(8, 128), "e2m1")
+    with pytest.raises(ValueError):
+        lowbit.pack_codes(torch.randn(8, 128, device=dev()), "fp_e9")
