@@ -50,12 +50,15 @@ SIGNATURES = {
     "fpq_selftest_rounding": (_c.c_int, [_c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "fpq_selftest_f16_flow": (_c.c_int, [_c.c_int, _c.c_void_p, _c.c_void_p]),
     "fpq_codes_rows_padded": (_c.c_size_t, [_c.c_size_t]),
-    "fpq_pack_codes": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
-    "fpq_unpack_codes": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_void_p, _c.c_void_p]),
+    "fpq_pack_codes": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_int, _c.c_void_p, _c.c_void_p,
+                                  _c.c_void_p]),
+    "fpq_unpack_codes": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t, _c.c_size_t, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "fpq_codes_to_nibbles": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "fpq_nibbles_to_codes": (_c.c_int, [_c.c_void_p, _c.c_size_t, _c.c_int, _c.c_void_p, _c.c_void_p]),
     "fpq_gemm_codes": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t,
-                                  _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+                                  _c.c_size_t, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
+    "fpq_gemm_codes_sse": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t,
+                                      _c.c_size_t, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p]),
 }
 
 _lib = None

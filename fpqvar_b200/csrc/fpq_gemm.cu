@@ -13,12 +13,18 @@
 // GEMM: C[m, n] = sum over slabs t of  sa[t, m] * sw[t, n] * P_t[m, n],   P_t = sum over the slab's 128 k of qa * qw,
 // P_t by tcgen05.mma kind::f8f6f4 (e4m3 x e4m3, fp32 accumulate in tensor memory; exact: every product is a multiple of 2^-8
 // and the sums stay far below 2^24 of them), the scale product by the epilogue warps on the CUDA cores while the tensor core
-// works on the next slab (two accumulators in tensor memory).  The fp32 operation order is fixed -- acc = fma(P*sa, sw, acc),
+// works on the next slabs (512 columns of tensor memory: four 128-column or two 256-column accumulators).  The fp32 operation order is fixed -- acc = fma(P*sa, sw, acc),
 // slabs ascending -- so that oracle/gemm_codes.c reproduces C bit for bit.
 //
-// One CTA per 128 x 128 tile of C, six warps: 0 = bulk-copy producer, 1 = MMA issuer (one lane), 2..5 = epilogue (each owns the
-// 32 tensor-memory lanes of its warp-id quarter).  Ring of shared-memory stages {A tile, B tile, sa, sw} with full / empty
-// mbarriers; tcgen05.commit hands a stage back and publishes an accumulator.
+// Persistent kernel, one CTA per SM, 128 x 256 (or 128 x 128) tiles of C: warp 0 = bulk-copy producer, warp 1 = MMA issuer (one
+// lane), warps 2.. = epilogue (each owns 32 tensor-memory lanes -- its warp-id quarter -- and 128 columns).  Ring of shared-memory
+// stages {A tile, B tile} and a ring of scale sets {sa, sw}, full / empty mbarriers; tcgen05.commit hands a stage back and
+// publishes an accumulator; the epilogue hands the accumulator back as soon as it is in registers.  With one scale per row
+// (per_token x per_channel) the whole K accumulates in tensor memory and the epilogue runs once per tile.
+// Measured (B200, profiles/r2_gemm_codes.txt): row scales 2.0-2.5 PFLOP/s, at the ~6.3 KB/clk L2 -> SM cap with 128 x 256 tiles; groups of
+// 128: 1.1-1.4 PFLOP/s.  What the per-slab hand-over costs is NOT the epilogue's work: with its tensor-memory loads, scale loads
+// and arithmetic all compiled out the kernel still runs at 1.2-1.7 PFLOP/s (tensor-memory loads alone reach ~1 KB/clk per SM,
+// tools/tmem_ldbench.cu).  Switching the accumulator every four MMAs and committing it every slab is what the tensor pipe pays for.
 #include "fpq_common.cuh"
 #include "fpq_stream.cuh"
 #include <cuda_fp8.h>
@@ -28,13 +34,9 @@ namespace fpq {
 namespace {
 
 constexpr int GK = 128;                      // K slab: the reference's quantization group
-constexpr int TM = 128, TN = 128;            // C tile
+constexpr int TM = 128;                      // C tile rows (columns: 128 or 256, GemmCfg)
 constexpr uint32_t BLK_BYTES = 1024;         // one (8 rows x 128 K) block of codes
-constexpr uint32_t A_BYTES = TM * GK, B_BYTES = TN * GK, SA_BYTES = TM * 4, SW_BYTES = TN * 4;
-constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES + SA_BYTES + SW_BYTES;       // 33 792 = 33 * 1024
-constexpr int MAX_STAGES = 6;
-constexpr int GEMM_THREADS = 192;
-constexpr uint32_t TMEM_COLS = 256;          // two 128-column fp32 accumulators
+constexpr uint32_t A_BYTES = TM * GK, SA_BYTES = TM * 4;
 
 // ---------------------------------------------------------------------------------------------------------------------
 // quantizer -> codes.  One warp per (8 rows x 128 K) block: lane = (row & 7) + 8 * (chunk & 3), two chunks of 16 elements per
@@ -127,10 +129,63 @@ __global__ void __launch_bounds__(256) pack_codes_kernel(const T* __restrict__ x
     }
 }
 
+// Row-wise scales (the reference's per_token / per_channel functions, qu.py:503-534: absmax over the whole last dim): one warp
+// per 8-row block, two passes over the rows (absmax, then quantize; the second pass reads what the first left in L1 / L2).
+// scales: [1][rows_pad].
+template <typename T, class HG>
+__global__ void __launch_bounds__(256) pack_codes_row_kernel(const T* __restrict__ x, size_t rows, size_t rows_pad, size_t k,
+                                                             uint8_t* __restrict__ codes, float* __restrict__ scales) {
+    const int lane = threadIdx.x & 31;
+    const int r = lane & 7, kq = lane >> 3;
+    const size_t slabs = k / GK, row_blocks = rows_pad / 8;
+    const size_t warp0 = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5, n_warps = (size_t(gridDim.x) * blockDim.x) >> 5;
+    for (size_t rb = warp0; rb < row_blocks; rb += n_warps) {
+        const size_t row = rb * 8 + r;
+        const bool live = row < rows;
+        float amax = 0.0f;
+        bool nan = false;
+        if (live) {
+            for (size_t c = kq; c < slabs * 8; c += 4) {
+                float v[16];
+                Chunk16<T>::load(x + row * k + c * 16, v);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    amax = fmaxf(amax, fabsf(v[i]));
+                    nan |= v[i] != v[i];
+                }
+            }
+        }
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 8));
+        amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, 16));
+        unsigned nanmask = __ballot_sync(0xffffffffu, nan);
+        nanmask |= nanmask >> 16;
+        nanmask |= nanmask >> 8;
+        if ((nanmask >> r) & 1u) amax = __int_as_float(0x7fc00000);
+        const float s = Chunk16<T>::scale(amax, HG::VMAX);
+        for (size_t c = kq; c < slabs * 8; c += 4) {
+            float v[16], q[16];
+            if (live) Chunk16<T>::load(x + row * k + c * 16, v);
+            else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) q[i] = round_any_sym<HG, TIE_KERNEL>(Chunk16<T>::norm(v[i], s));
+            uint4 o;
+            o.x = e4m3x4(q[0], q[1], q[2], q[3]);
+            o.y = e4m3x4(q[4], q[5], q[6], q[7]);
+            o.z = e4m3x4(q[8], q[9], q[10], q[11]);
+            o.w = e4m3x4(q[12], q[13], q[14], q[15]);
+            *reinterpret_cast<uint4*>(codes + ((c >> 3) * row_blocks + rb) * BLK_BYTES + (c & 7) * 128 + r * 16) = o;
+        }
+        if (kq == 0) scales[row] = live ? s : 0.0f;
+    }
+}
+
 // codes -> values: out[row, c] = T( fl32(q) * scale ), the reference's last step (qu.py:328-329).  One thread per 16-byte chunk.
 template <typename T>
 __global__ void __launch_bounds__(256) unpack_codes_kernel(const uint8_t* __restrict__ codes, const float* __restrict__ scales, size_t rows,
-                                                           size_t rows_pad, size_t k, T* __restrict__ out) {
+                                                           size_t rows_pad, size_t k, bool row_scale, T* __restrict__ out) {
     const size_t slabs = k / GK, row_blocks = rows_pad / 8;
     const size_t n_chunks = slabs * row_blocks * 64;
     for (size_t c = size_t(blockIdx.x) * blockDim.x + threadIdx.x; c < n_chunks; c += size_t(gridDim.x) * blockDim.x) {
@@ -140,7 +195,7 @@ __global__ void __launch_bounds__(256) unpack_codes_kernel(const uint8_t* __rest
         const size_t row = rb * 8 + r;
         if (row >= rows) continue;
         const uint4 u = *reinterpret_cast<const uint4*>(codes + c * 16);
-        const float s = scales[slab * rows_pad + row];
+        const float s = scales[(row_scale ? 0 : slab) * rows_pad + row];
         const uint32_t w[4] = {u.x, u.y, u.z, u.w};
         T* o = out + row * k + slab * GK + kc * 16;
 #pragma unroll
@@ -210,18 +265,6 @@ __device__ __forceinline__ void tc_mma_f8(uint32_t d_tmem, uint64_t desc_a, uint
         "}\n" ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-// 32 lanes x 32 consecutive fp32 columns: thread t of the warp gets lane (base lane + t)
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&v)[32]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-          "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-          "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr));
-}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major, no swizzle: core matrix = 8 rows x 16 bytes (128 contiguous bytes); `lbo` = byte step between the two core
@@ -230,8 +273,21 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo, 
     return uint64_t((smem_addr >> 4) & 0x3fffu) | (uint64_t((lbo >> 4) & 0x3fffu) << 16) | (uint64_t((sbo >> 4) & 0x3fffu) << 32) |
            (uint64_t(1) << 46);
 }
-// instruction descriptor: D fp32 (bits 4-5 = 1), A / B e4m3 (format 0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-constexpr uint32_t IDESC_E4M3_128x128 = (1u << 4) | (uint32_t(TN >> 3) << 17) | (uint32_t(TM >> 4) << 24);
+// instruction descriptor (GemmCfg::IDESC): D fp32 (bits 4-5 = 1), A / B e4m3 (format 0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+
+// 16 lanes x 32 consecutive fp32 columns in the layout of the classic 16 x 8 accumulator fragment, four 8-column blocks i:
+// thread t gets v[4i], v[4i+1] = (lane t/4, columns 8i + 2(t%4), +1) and v[4i+2], v[4i+3] = (lane t/4 + 8, same columns)
+// (profiles/r2_tmem_layout.txt: the mapping as measured)
+__device__ __forceinline__ void tc_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
+          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr));
+}
+
+enum : int { OUT_F16 = 0, OUT_F32 = 1, OUT_SSE_F16 = 2, OUT_SSE_F32 = 3 };
 
 struct GemmArgs {
     const uint8_t* a_codes;
@@ -239,42 +295,70 @@ struct GemmArgs {
     const uint8_t* b_codes;
     const float* b_scales;
     const float* bias;       // fp32 [n] or null
-    void* c;
+    void* c;                 // output matrix, or the reference matrix of the SSE modes
+    double* sse;             // SSE modes: one accumulator
     size_t ldc;              // elements
     size_t m, n;             // valid rows / columns of C
     size_t m_pad, n_pad;     // padded row counts of the two code arrays (multiples of 128)
     uint32_t slabs;          // K / 128
+    uint32_t group_slabs;    // slabs that share one scale pair: 1 (groups of 128) or `slabs` (per_token x per_channel)
     uint32_t stages;
-    uint32_t lbo, sbo;
+    uint32_t n_tiles, tiles_n;
 };
 
-template <typename OutT>
-__global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_codes_kernel(const GemmArgs g) {
+template <int TN_, int EC_>
+struct GemmCfg {
+    static constexpr int TN = TN_;
+    static constexpr int EC = EC_;                                // columns of C per epilogue warp (x 32 rows: its tensor-memory lanes)
+    static constexpr int EPI_WARPS = 4 * (TN / EC);               // each: 32 rows x EC columns
+    static constexpr int THREADS = 128 + 32 * EPI_WARPS;          // warps 0..3: producer, MMA issuer, two idle (one warpgroup)
+    // (tried: setmaxnreg.dec / .inc between the control warpgroup and the epilogue warps -- ptxas keeps compiling the epilogue for the
+    // launch bound and spills more; removed)
+    static constexpr uint32_t B_BYTES = TN * GK;
+    static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;    // 32 KB | 48 KB
+    static constexpr int MAX_STAGES = TN == 128 ? 6 : 4;
+    static constexpr uint32_t SC_BYTES = SA_BYTES + TN * 4;       // one scale pair set: sa[128], sw[TN]
+    static constexpr int SC_DEPTH = 8;                            // >= stages + 2: the producer never waits on the scale ring first
+    static constexpr int ACC = 512 / TN;                          // accumulators in tensor memory: 4 x 128 or 2 x 256 columns
+    static constexpr uint32_t TMEM_COLS = 512;
+    static constexpr uint32_t IDESC = (1u << 4) | (uint32_t(TN >> 3) << 17) | (uint32_t(TM >> 4) << 24);
+    static constexpr size_t smem_bytes(int stages) { return size_t(stages) * STAGE_BYTES + SC_DEPTH * SC_BYTES + 1024; }
+};
+
+// Persistent: CTA b works on tiles b, b + gridDim.x, ...; tile t = (t / tiles_n, t % tiles_n), so that the CTAs running at the same
+// time share A panels and the whole of B through L2.  Warp 0 = producer, warp 1 = MMA issuer, warps 4.. = epilogue.
+template <int TN_, int EC_, int OUT>
+__global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kernel(const GemmArgs g) {
+    using Cfg = GemmCfg<TN_, EC_>;
+    constexpr int TN = Cfg::TN, EC = Cfg::EC;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_full[MAX_STAGES], bar_empty[MAX_STAGES], bar_tfull[2], bar_tempty[2];
+    __shared__ uint64_t bar_full[Cfg::MAX_STAGES], bar_empty[Cfg::MAX_STAGES], bar_tfull[Cfg::ACC], bar_tempty[Cfg::ACC];
+    __shared__ uint64_t bar_sfull[Cfg::SC_DEPTH], bar_sempty[Cfg::SC_DEPTH];
     __shared__ uint32_t tmem_base_slot;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;                 // stage bases on 1 KB
     uint8_t* const stage0 = smem_raw + (smem0 - smem_u32(smem_raw));
-    const uint32_t stages = g.stages, slabs = g.slabs;
-
-    const size_t tiles_n = g.n_pad / TN;
-    const size_t tm = blockIdx.x / tiles_n, tn = blockIdx.x % tiles_n;            // consecutive CTAs share the A panel
+    const uint32_t stages = g.stages, slabs = g.slabs, gs = g.group_slabs;
+    uint8_t* const sc0 = stage0 + size_t(stages) * Cfg::STAGE_BYTES;
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < stages; ++s) {
             mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_empty[s], 1 + 4);          // the MMA's commit + one arrive per epilogue warp (scales read)
+            mbar_init(&bar_empty[s], 1);               // the MMA's commit
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < Cfg::ACC; ++a) {
             mbar_init(&bar_tfull[a], 1);
-            mbar_init(&bar_tempty[a], 4);
+            mbar_init(&bar_tempty[a], Cfg::EPI_WARPS);
+        }
+        for (int q = 0; q < Cfg::SC_DEPTH; ++q) {
+            mbar_init(&bar_sfull[q], 1);
+            mbar_init(&bar_sempty[q], Cfg::EPI_WARPS);
         }
         mbar_fence_init();
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(TMEM_COLS)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(Cfg::TMEM_COLS)
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -284,91 +368,153 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_codes_kernel(const GemmA
     const uint32_t tmem_base = tmem_base_slot;
 
     if (warp == 0) {
-        // ===== producer: four bulk copies per slab =====
+        // ===== producer: two operand copies per slab, two scale copies per scale group =====
         if (lane == 0) {
             const size_t a_blocks = g.m_pad / 8, b_blocks = g.n_pad / 8;
-            for (uint32_t i = 0; i < slabs; ++i) {
-                const uint32_t s = i % stages, n = i / stages;
-                if (n > 0) mbar_wait(&bar_empty[s], (n - 1) & 1);
-                uint8_t* st = stage0 + size_t(s) * STAGE_BYTES;
-                mbar_arrive_expect_tx(&bar_full[s], STAGE_BYTES);
-                bulk_load(st, g.a_codes + (size_t(i) * a_blocks + tm * (TM / 8)) * BLK_BYTES, A_BYTES, &bar_full[s]);
-                bulk_load(st + A_BYTES, g.b_codes + (size_t(i) * b_blocks + tn * (TN / 8)) * BLK_BYTES, B_BYTES, &bar_full[s]);
-                bulk_load(st + A_BYTES + B_BYTES, g.a_scales + size_t(i) * g.m_pad + tm * TM, SA_BYTES, &bar_full[s]);
-                bulk_load(st + A_BYTES + B_BYTES + SA_BYTES, g.b_scales + size_t(i) * g.n_pad + tn * TN, SW_BYTES, &bar_full[s]);
+            uint32_t it = 0, gi = 0;
+            for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+                const size_t tm = tile / g.tiles_n, tn = tile % g.tiles_n;
+                const size_t b_left = g.n_pad - tn * TN;
+                const uint32_t b_rows = b_left < size_t(TN) ? uint32_t(b_left) : uint32_t(TN);        // last tile column may be half
+                for (uint32_t i = 0; i < slabs; ++i, ++it) {
+                    if (i % gs == 0) {
+                        const uint32_t q = gi % Cfg::SC_DEPTH, qn = gi / Cfg::SC_DEPTH;
+                        if (qn > 0) mbar_wait(&bar_sempty[q], (qn - 1) & 1);
+                        uint8_t* sc = sc0 + size_t(q) * Cfg::SC_BYTES;
+                        mbar_arrive_expect_tx(&bar_sfull[q], SA_BYTES + b_rows * 4);
+                        bulk_load(sc, g.a_scales + size_t(i / gs) * g.m_pad + tm * TM, SA_BYTES, &bar_sfull[q]);
+                        bulk_load(sc + SA_BYTES, g.b_scales + size_t(i / gs) * g.n_pad + tn * TN, b_rows * 4, &bar_sfull[q]);
+                        ++gi;
+                    }
+                    const uint32_t s = it % stages, n = it / stages;
+                    if (n > 0) mbar_wait(&bar_empty[s], (n - 1) & 1);
+                    uint8_t* st = stage0 + size_t(s) * Cfg::STAGE_BYTES;
+                    mbar_arrive_expect_tx(&bar_full[s], A_BYTES + b_rows * GK);
+                    bulk_load(st, g.a_codes + (size_t(i) * a_blocks + tm * (TM / 8)) * BLK_BYTES, A_BYTES, &bar_full[s]);
+                    bulk_load(st + A_BYTES, g.b_codes + (size_t(i) * b_blocks + tn * (TN / 8)) * BLK_BYTES, b_rows * GK, &bar_full[s]);
+                }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===== MMA issuer: four 128 x 128 x 32 MMAs per slab into accumulator (slab & 1) =====
-        for (uint32_t i = 0; i < slabs; ++i) {
-            const uint32_t s = i % stages, n = i / stages, a = i & 1, u = i >> 1;
-            if (u > 0) mbar_wait(&bar_tempty[a], (u - 1) & 1);
-            mbar_wait(&bar_full[s], n & 1);
-            tc_fence_after();
-            if (lane == 0) {
-                const uint32_t sa_addr = smem0 + s * STAGE_BYTES;
-                const uint64_t da = umma_desc(sa_addr, g.lbo, g.sbo), db = umma_desc(sa_addr + A_BYTES, g.lbo, g.sbo);
+        // ===== MMA issuer: four 128 x TN x 32 MMAs per slab; a scale group accumulates in tensor memory =====
+        uint32_t it = 0, gi = 0;
+        for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+            for (uint32_t i = 0; i < slabs; ++i, ++it) {
+                const uint32_t s = it % stages, n = it / stages, a = gi % Cfg::ACC, u = gi / Cfg::ACC;
+                const bool first = i % gs == 0, last = i % gs == gs - 1;
+                if (first && u > 0) mbar_wait(&bar_tempty[a], (u - 1) & 1);
+                mbar_wait(&bar_full[s], n & 1);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t st_addr = smem0 + s * Cfg::STAGE_BYTES;
+                    const uint64_t da = umma_desc(st_addr, 128u, 1024u), db = umma_desc(st_addr + A_BYTES, 128u, 1024u);
 #pragma unroll
-                for (uint32_t kk = 0; kk < GK / 32; ++kk)      // 32 K = two core matrices = 256 bytes further on
-                    tc_mma_f8(tmem_base + a * TN, da + kk * (256u >> 4), db + kk * (256u >> 4), IDESC_E4M3_128x128, kk);
-                tc_commit(&bar_empty[s]);
-                tc_commit(&bar_tfull[a]);
+                    for (uint32_t kk = 0; kk < GK / 32; ++kk)      // 32 K = two core matrices = 256 bytes further on
+                        tc_mma_f8(tmem_base + a * TN, da + kk * (256u >> 4), db + kk * (256u >> 4), Cfg::IDESC, (first && kk == 0) ? 0u : 1u);
+                    tc_commit(&bar_empty[s]);
+                    if (last) tc_commit(&bar_tfull[a]);
+                }
+                __syncwarp();
+                if (last) ++gi;
             }
-            __syncwarp();
         }
-    } else {
-        // ===== epilogue: acc = fma(P * sa, sw, acc), one C row per thread =====
+    } else if (warp >= 4) {
+        // ===== epilogue: acc = fma(P * sa, sw, acc) per scale group.  A warp owns 32 rows (its tensor-memory lane quarter) x EC
+        // columns and reads them as 16 x 8 fragments: a thread holds FOUR rows (tr, tr+8, tr+16, tr+24) x EC/4 columns (the pair
+        // 2 tq, 2 tq + 1 of every 8-column block), so that per 128-K slab it needs 4 row scales and EC/4 column scales from shared
+        // memory instead of 1 + EC with one row per thread: the column-scale loads (a 16-byte load per lane costs the full 512
+        // bytes of return bandwidth even when every lane reads the same address) were what bounded the first version, on the
+        // same 128 B/clk shared-memory pipe that carries the operand tiles in and out. =====
         const int quarter = warp & 3;                         // the tensor-memory lanes this warp may touch
-        const int row_in_tile = quarter * 32 + lane;
-        float acc[TN];
+        const int col_off = ((warp - 4) >> 2) * EC;           // its columns of the tile
+        const int tq = lane & 3, tr = lane >> 2;
+        constexpr int NB = EC / 8;                            // 8-column blocks per thread row
+        const uint32_t n_groups = slabs / gs;
+        uint32_t gi = 0;
+        double sse_thread = 0.0;
+        for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+            uint64_t acc[4 * NB];                              // [row slot rr][block b]: columns (8 b + 2 tq, + 1) of row tr + 8 rr
 #pragma unroll
-        for (int j = 0; j < TN; ++j) acc[j] = 0.0f;
-        for (uint32_t i = 0; i < slabs; ++i) {
-            const uint32_t s = i % stages, n = i / stages, a = i & 1, u = i >> 1;
-            const uint8_t* st = stage0 + size_t(s) * STAGE_BYTES;
-            mbar_wait(&bar_full[s], n & 1);                   // the scales of this slab are in shared memory
-            const float sa = reinterpret_cast<const float*>(st + A_BYTES + B_BYTES)[row_in_tile];
-            const float4* sw4 = reinterpret_cast<const float4*>(st + A_BYTES + B_BYTES + SA_BYTES);
-            mbar_wait(&bar_tfull[a], u & 1);
-            tc_fence_after();
+            for (int j = 0; j < 4 * NB; ++j) acc[j] = 0ull;
+            for (uint32_t grp = 0; grp < n_groups; ++grp, ++gi) {
+                const uint32_t q = gi % Cfg::SC_DEPTH, a = gi % Cfg::ACC;
+                const uint8_t* sc = sc0 + size_t(q) * Cfg::SC_BYTES;
+                mbar_wait(&bar_sfull[q], (gi / Cfg::SC_DEPTH) & 1);
+                uint64_t sa2[4];
 #pragma unroll
-            for (int c = 0; c < TN / 32; ++c) {
-                uint32_t v[32];
-                tc_ld32(tmem_base + (uint32_t(quarter * 32) << 16) + a * TN + c * 32, v);
-                tc_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 w = sw4[c * 8 + j / 4];
-                    acc[c * 32 + j + 0] = __fmaf_rn(__fmul_rn(__uint_as_float(v[j + 0]), sa), w.x, acc[c * 32 + j + 0]);
-                    acc[c * 32 + j + 1] = __fmaf_rn(__fmul_rn(__uint_as_float(v[j + 1]), sa), w.y, acc[c * 32 + j + 1]);
-                    acc[c * 32 + j + 2] = __fmaf_rn(__fmul_rn(__uint_as_float(v[j + 2]), sa), w.z, acc[c * 32 + j + 2]);
-                    acc[c * 32 + j + 3] = __fmaf_rn(__fmul_rn(__uint_as_float(v[j + 3]), sa), w.w, acc[c * 32 + j + 3]);
+                for (int rr = 0; rr < 4; ++rr) {
+                    const float sa = reinterpret_cast<const float*>(sc)[quarter * 32 + tr + 8 * rr];
+                    sa2[rr] = pk(sa, sa);
                 }
+                const uint64_t* swp = reinterpret_cast<const uint64_t*>(sc + SA_BYTES + col_off * 4) + tq;     // block b: swp[4 b]
+                mbar_wait(&bar_tfull[a], (gi / Cfg::ACC) & 1);
+                tc_fence_after();
+                const uint32_t t0 = tmem_base + (uint32_t(quarter * 32) << 16) + a * TN + col_off;
+#pragma unroll
+                for (int cb = 0; cb < EC / 32; ++cb) {         // 32 columns: four blocks, both 16-lane halves
+                    uint32_t v[2][16];
+                    tc_ld_16x256b_x4(t0 + cb * 32, v[0]);
+                    tc_ld_16x256b_x4(t0 + (16u << 16) + cb * 32, v[1]);
+                    tc_wait_ld();
+                    if (cb == EC / 32 - 1) {
+                        // every column of this accumulator has been read: hand it back before the arithmetic
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&bar_tempty[a]);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int bl = cb * 4 + i;
+                        const uint64_t w = swp[4 * bl];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            acc[(2 * h) * NB + bl] = ffma2(fmul2(pk(__uint_as_float(v[h][4 * i]), __uint_as_float(v[h][4 * i + 1])), sa2[2 * h]), w, acc[(2 * h) * NB + bl]);
+                            acc[(2 * h + 1) * NB + bl] = ffma2(fmul2(pk(__uint_as_float(v[h][4 * i + 2]), __uint_as_float(v[h][4 * i + 3])), sa2[2 * h + 1]), w, acc[(2 * h + 1) * NB + bl]);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&bar_sempty[q]);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&bar_tempty[a]);
-                mbar_arrive(&bar_empty[s]);
+            const size_t row0 = size_t(tile / g.tiles_n) * TM + quarter * 32 + tr, col0 = size_t(tile % g.tiles_n) * TN + col_off + 2 * tq;
+#pragma unroll
+            for (int bl = 0; bl < NB; ++bl) {
+                const size_t col = col0 + 8 * bl;
+                if (col >= g.n) break;                         // n is a multiple of 8: whole blocks
+                uint64_t bias2 = 0ull;
+                if (g.bias) { const float2 bb = __ldg(reinterpret_cast<const float2*>(g.bias + col)); bias2 = pk(bb.x, bb.y); }
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const size_t row = row0 + 8 * rr;
+                    if (row >= g.m) continue;
+                    const F2 o = unpk(g.bias ? fadd2(acc[rr * NB + bl], bias2) : acc[rr * NB + bl]);
+                    if constexpr (OUT == OUT_F16) {
+                        *reinterpret_cast<uint32_t*>(static_cast<__half*>(g.c) + row * g.ldc + col) = pack_h2(o.lo, o.hi);
+                    } else if constexpr (OUT == OUT_F32) {
+                        *reinterpret_cast<float2*>(static_cast<float*>(g.c) + row * g.ldc + col) = make_float2(o.lo, o.hi);
+                    } else {
+                        // squared distance to the reference matrix: fp32 differences, rows of the tile in fp64
+                        float r0, r1;
+                        if constexpr (OUT == OUT_SSE_F16) {
+                            const uint32_t u = *reinterpret_cast<const uint32_t*>(static_cast<const __half*>(g.c) + row * g.ldc + col);
+                            r0 = h2f(uint16_t(u & 0xffffu));
+                            r1 = h2f(uint16_t(u >> 16));
+                        } else {
+                            const float2 u = *reinterpret_cast<const float2*>(static_cast<const float*>(g.c) + row * g.ldc + col);
+                            r0 = u.x;
+                            r1 = u.y;
+                        }
+                        const float d0 = r0 - o.lo, d1 = r1 - o.hi;
+                        sse_thread += double(__fmaf_rn(d1, d1, __fmul_rn(d0, d0)));
+                    }
+                }
             }
         }
-        const size_t row = tm * TM + row_in_tile, col0 = tn * TN;
-        if (row < g.m) {
-            OutT* crow = static_cast<OutT*>(g.c) + row * g.ldc + col0;
+        if constexpr (OUT == OUT_SSE_F16 || OUT == OUT_SSE_F32) {
 #pragma unroll
-            for (int j = 0; j < TN; j += 8) {
-                if (col0 + j >= g.n) break;                   // n is a multiple of 8 (checked by the launcher)
-                float o[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = acc[j + e] + (g.bias ? __ldg(g.bias + col0 + j + e) : 0.0f);
-                if constexpr (sizeof(OutT) == 2) {
-                    *reinterpret_cast<uint4*>(crow + j) = make_uint4(pack_h2(o[0], o[1]), pack_h2(o[2], o[3]), pack_h2(o[4], o[5]), pack_h2(o[6], o[7]));
-                } else {
-                    *reinterpret_cast<float4*>(crow + j) = make_float4(o[0], o[1], o[2], o[3]);
-                    *reinterpret_cast<float4*>(crow + j + 4) = make_float4(o[4], o[5], o[6], o[7]);
-                }
-            }
+            for (int off = 16; off > 0; off >>= 1) sse_thread += __shfl_xor_sync(0xffffffffu, sse_thread, off);
+            if (lane == 0) atomicAdd(g.sse, sse_thread);
         }
     }
 
@@ -376,7 +522,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_codes_kernel(const GemmA
     __syncthreads();
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
     }
 }
 
@@ -393,6 +539,20 @@ bool half_grid_e4m3(int format, NibbleLut& lut) {
     }
     lut.e4m3[8] = 0x00;           // the quantizer never produces -0 (the grids' zero is +0.0); decode nibble 8 as +0 too
     return true;
+}
+
+template <typename T>
+int launch_pack_rows(int format, const T* x, size_t rows, size_t rows_pad, size_t k, uint8_t* codes, float* scales, cudaStream_t st) {
+    const unsigned grid = grid_for(rows_pad / 8, 8, 8);
+    switch (format) {
+        case FPQ_FMT_E2M1: pack_codes_row_kernel<T, HG_E2M1><<<grid, 256, 0, st>>>(x, rows, rows_pad, k, codes, scales); break;
+        case FPQ_FMT_E1M2: pack_codes_row_kernel<T, HG_E1M2><<<grid, 256, 0, st>>>(x, rows, rows_pad, k, codes, scales); break;
+        case FPQ_FMT_E3M0: pack_codes_row_kernel<T, HG_E3M0><<<grid, 256, 0, st>>>(x, rows, rows_pad, k, codes, scales); break;
+        case FPQ_FMT_E2M3: pack_codes_row_kernel<T, HG_E2M3><<<grid, 256, 0, st>>>(x, rows, rows_pad, k, codes, scales); break;
+        case FPQ_FMT_E3M2: pack_codes_row_kernel<T, HG_E3M2><<<grid, 256, 0, st>>>(x, rows, rows_pad, k, codes, scales); break;
+        default: return FPQ_ERR_ARG;
+    }
+    return finish_launch();
 }
 
 template <typename T>
@@ -420,24 +580,34 @@ using namespace fpq;
 
 extern "C" size_t fpq_codes_rows_padded(size_t rows) { return (rows + TM - 1) / TM * TM; }
 
-extern "C" int fpq_pack_codes(const void* x, size_t rows, size_t k, int in_dtype, int format, uint8_t* codes, float* scales, void* stream) {
-    if (k == 0 || k % GK != 0 || (rows && (!x || !codes || !scales)) || !aligned16(x) || !aligned16(codes) || !aligned16(scales)) return FPQ_ERR_ARG;
+extern "C" int fpq_pack_codes(const void* x, size_t rows, size_t k, size_t scale_group, int in_dtype, int format, uint8_t* codes, float* scales,
+                              void* stream) {
+    if (k == 0 || k % GK != 0 || (scale_group != GK && scale_group != k)) return FPQ_ERR_ARG;
+    if ((rows && (!x || !codes || !scales)) || !aligned16(x) || !aligned16(codes) || !aligned16(scales)) return FPQ_ERR_ARG;
     if (rows == 0) return FPQ_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t rows_pad = fpq_codes_rows_padded(rows);
-    if (in_dtype == FPQ_F16) return launch_pack<__half>(format, static_cast<const __half*>(x), rows, rows_pad, k, codes, scales, st);
-    if (in_dtype == FPQ_F32) return launch_pack<float>(format, static_cast<const float*>(x), rows, rows_pad, k, codes, scales, st);
+    if (scale_group == GK) {
+        if (in_dtype == FPQ_F16) return launch_pack<__half>(format, static_cast<const __half*>(x), rows, rows_pad, k, codes, scales, st);
+        if (in_dtype == FPQ_F32) return launch_pack<float>(format, static_cast<const float*>(x), rows, rows_pad, k, codes, scales, st);
+    } else {
+        if (in_dtype == FPQ_F16) return launch_pack_rows<__half>(format, static_cast<const __half*>(x), rows, rows_pad, k, codes, scales, st);
+        if (in_dtype == FPQ_F32) return launch_pack_rows<float>(format, static_cast<const float*>(x), rows, rows_pad, k, codes, scales, st);
+    }
     return FPQ_ERR_ARG;
 }
 
-extern "C" int fpq_unpack_codes(const uint8_t* codes, const float* scales, size_t rows, size_t k, int out_dtype, void* out, void* stream) {
-    if (k == 0 || k % GK != 0 || (rows && (!out || !codes || !scales)) || !aligned16(codes)) return FPQ_ERR_ARG;
+extern "C" int fpq_unpack_codes(const uint8_t* codes, const float* scales, size_t rows, size_t k, size_t scale_group, int out_dtype, void* out,
+                                void* stream) {
+    if (k == 0 || k % GK != 0 || (scale_group != GK && scale_group != k)) return FPQ_ERR_ARG;
+    if ((rows && (!out || !codes || !scales)) || !aligned16(codes)) return FPQ_ERR_ARG;
     if (rows == 0) return FPQ_OK;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const size_t rows_pad = fpq_codes_rows_padded(rows);
     const unsigned grid = grid_for(rows_pad * k / 16, 256, 8);
-    if (out_dtype == FPQ_F16) unpack_codes_kernel<__half><<<grid, 256, 0, st>>>(codes, scales, rows, rows_pad, k, static_cast<__half*>(out));
-    else if (out_dtype == FPQ_F32) unpack_codes_kernel<float><<<grid, 256, 0, st>>>(codes, scales, rows, rows_pad, k, static_cast<float*>(out));
+    const bool row_scale = scale_group != GK;
+    if (out_dtype == FPQ_F16) unpack_codes_kernel<__half><<<grid, 256, 0, st>>>(codes, scales, rows, rows_pad, k, row_scale, static_cast<__half*>(out));
+    else if (out_dtype == FPQ_F32) unpack_codes_kernel<float><<<grid, 256, 0, st>>>(codes, scales, rows, rows_pad, k, row_scale, static_cast<float*>(out));
     else return FPQ_ERR_ARG;
     return finish_launch();
 }
@@ -460,38 +630,78 @@ extern "C" int fpq_nibbles_to_codes(const uint8_t* nibbles, size_t n_codes, int 
     return finish_launch();
 }
 
-extern "C" int fpq_gemm_codes(const uint8_t* a_codes, const float* a_scales, size_t m, const uint8_t* b_codes, const float* b_scales,
-                              size_t n, size_t k, const float* bias, int out_dtype, void* c, size_t ldc, void* stream) {
-    if (k == 0 || k % GK != 0 || k / GK > 0xffffffffull) return FPQ_ERR_ARG;
-    if (m == 0 || n == 0) return FPQ_OK;
-    if (!a_codes || !a_scales || !b_codes || !b_scales || !c) return FPQ_ERR_ARG;
-    if (!aligned16(a_codes) || !aligned16(a_scales) || !aligned16(b_codes) || !aligned16(b_scales) || !aligned16(c)) return FPQ_ERR_ARG;
-    if (n % 8 != 0 || ldc % 8 != 0 || ldc < n) return FPQ_ERR_ARG;
-    if (out_dtype != FPQ_F16 && out_dtype != FPQ_F32) return FPQ_ERR_ARG;
-    GemmArgs g;
-    g.a_codes = a_codes; g.a_scales = a_scales; g.b_codes = b_codes; g.b_scales = b_scales; g.bias = bias;
-    g.c = c; g.ldc = ldc; g.m = m; g.n = n;
-    g.m_pad = fpq_codes_rows_padded(m); g.n_pad = fpq_codes_rows_padded(n);
-    g.slabs = uint32_t(k / GK);
-    g.stages = uint32_t(g_tun.gemm_stages);
-    g.lbo = g_tun.gemm_desc_swap ? 1024u : 128u;
-    g.sbo = g_tun.gemm_desc_swap ? 128u : 1024u;
-    const size_t tiles = (g.m_pad / TM) * (g.n_pad / TN);
+namespace {
+
+template <int TN_, int EC_, int OUT>
+int launch_gemm(GemmArgs& g, cudaStream_t st) {
+    using Cfg = GemmCfg<TN_, EC_>;
+    if (int(g.stages) > Cfg::MAX_STAGES) g.stages = Cfg::MAX_STAGES;
+    const size_t tiles_n = (g.n_pad + TN_ - 1) / TN_;
+    const size_t tiles = (g.m_pad / TM) * tiles_n;
     if (tiles > 0x7fffffffull) return FPQ_ERR_UNSUPPORTED;
-    const size_t smem = size_t(g.stages) * STAGE_BYTES + 1024;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    static bool attr_set[64][2] = {};
+    g.n_tiles = uint32_t(tiles);
+    g.tiles_n = uint32_t(tiles_n);
+    static bool attr_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    const int oi = out_dtype == FPQ_F16 ? 0 : 1;
-    if (!attr_set[dev & 63][oi]) {
-        const size_t max_smem = size_t(MAX_STAGES) * STAGE_BYTES + 1024;
-        cudaError_t e = oi == 0 ? cudaFuncSetAttribute(gemm_codes_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(max_smem))
-                                : cudaFuncSetAttribute(gemm_codes_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(max_smem));
-        if (e != cudaSuccess) return finish_launch();
-        attr_set[dev & 63][oi] = true;
+    if (!attr_set[dev & 63]) {
+        if (cudaFuncSetAttribute(gemm_codes_kernel<TN_, EC_, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::smem_bytes(Cfg::MAX_STAGES))) != cudaSuccess)
+            return finish_launch();
+        attr_set[dev & 63] = true;
     }
-    if (oi == 0) gemm_codes_kernel<__half><<<unsigned(tiles), GEMM_THREADS, smem, st>>>(g);
-    else gemm_codes_kernel<float><<<unsigned(tiles), GEMM_THREADS, smem, st>>>(g);
+    const size_t resident = size_t(sm_count());
+    const unsigned grid = unsigned(tiles < resident ? tiles : resident);
+    gemm_codes_kernel<TN_, EC_, OUT><<<grid, Cfg::THREADS, Cfg::smem_bytes(int(g.stages)), st>>>(g);
     return finish_launch();
+}
+
+template <int OUT>
+int launch_gemm_tn(GemmArgs& g, cudaStream_t st) {
+    const int ec = g_tun.gemm_epi_cols;
+    if (g_tun.gemm_tile_n == 128) {
+        if (ec == 32) return launch_gemm<128, 32, OUT>(g, st);
+        if (ec == 64) return launch_gemm<128, 64, OUT>(g, st);
+        return launch_gemm<128, 128, OUT>(g, st);
+    }
+    if (ec == 64) return launch_gemm<256, 64, OUT>(g, st);
+    return launch_gemm<256, 128, OUT>(g, st);
+}
+
+int gemm_common(GemmArgs& g, const uint8_t* a_codes, const float* a_scales, size_t m, const uint8_t* b_codes, const float* b_scales, size_t n,
+                size_t k, size_t scale_group, const float* bias, void* c, size_t ldc) {
+    if (k == 0 || k % GK != 0 || k / GK > 0xffffffffull || (scale_group != GK && scale_group != k)) return FPQ_ERR_ARG;
+    if (!a_codes || !a_scales || !b_codes || !b_scales || !c) return FPQ_ERR_ARG;
+    if (!aligned16(a_codes) || !aligned16(a_scales) || !aligned16(b_codes) || !aligned16(b_scales) || !aligned16(c)) return FPQ_ERR_ARG;
+    if (n % 8 != 0 || ldc % 8 != 0 || ldc < n || (reinterpret_cast<uintptr_t>(bias) & 7u)) return FPQ_ERR_ARG;
+    g.a_codes = a_codes; g.a_scales = a_scales; g.b_codes = b_codes; g.b_scales = b_scales; g.bias = bias;
+    g.c = c; g.sse = nullptr; g.ldc = ldc; g.m = m; g.n = n;
+    g.m_pad = fpq_codes_rows_padded(m); g.n_pad = fpq_codes_rows_padded(n);
+    g.slabs = uint32_t(k / GK);
+    g.group_slabs = scale_group == GK ? 1u : g.slabs;
+    g.stages = uint32_t(g_tun.gemm_stages);
+    return FPQ_OK;
+}
+
+}  // namespace
+
+extern "C" int fpq_gemm_codes(const uint8_t* a_codes, const float* a_scales, size_t m, const uint8_t* b_codes, const float* b_scales,
+                              size_t n, size_t k, size_t scale_group, const float* bias, int out_dtype, void* c, size_t ldc, void* stream) {
+    if (m == 0 || n == 0) return FPQ_OK;
+    if (out_dtype != FPQ_F16 && out_dtype != FPQ_F32) return FPQ_ERR_ARG;
+    GemmArgs g;
+    if (int rc = gemm_common(g, a_codes, a_scales, m, b_codes, b_scales, n, k, scale_group, bias, c, ldc)) return rc;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return out_dtype == FPQ_F16 ? launch_gemm_tn<OUT_F16>(g, st) : launch_gemm_tn<OUT_F32>(g, st);
+}
+
+extern "C" int fpq_gemm_codes_sse(const uint8_t* a_codes, const float* a_scales, size_t m, const uint8_t* b_codes, const float* b_scales,
+                                  size_t n, size_t k, size_t scale_group, const float* bias, int ref_dtype, const void* ref, size_t ldr,
+                                  double* sse, void* stream) {
+    if (m == 0 || n == 0) return FPQ_OK;
+    if ((ref_dtype != FPQ_F16 && ref_dtype != FPQ_F32) || !sse) return FPQ_ERR_ARG;
+    GemmArgs g;
+    if (int rc = gemm_common(g, a_codes, a_scales, m, b_codes, b_scales, n, k, scale_group, bias, const_cast<void*>(ref), ldr)) return rc;
+    g.sse = sse;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    return ref_dtype == FPQ_F16 ? launch_gemm_tn<OUT_SSE_F16>(g, st) : launch_gemm_tn<OUT_SSE_F32>(g, st);
 }

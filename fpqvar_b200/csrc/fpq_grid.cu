@@ -161,7 +161,16 @@ extern "C" int fpq_set_tunable(const char* name, long long value) {
         g_tun.gemm_stages = int(value);
         return FPQ_OK;
     }
-    if (strcmp(name, "gemm_desc_swap") == 0) { g_tun.gemm_desc_swap = value != 0; return FPQ_OK; }
+    if (strcmp(name, "gemm_tile_n") == 0) {
+        if (value != 128 && value != 256) return FPQ_ERR_ARG;
+        g_tun.gemm_tile_n = int(value);
+        return FPQ_OK;
+    }
+    if (strcmp(name, "gemm_epi_cols") == 0) {
+        if (value != 32 && value != 64 && value != 128) return FPQ_ERR_ARG;
+        g_tun.gemm_epi_cols = int(value);
+        return FPQ_OK;
+    }
     return FPQ_ERR_ARG;
 }
 

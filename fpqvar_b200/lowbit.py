@@ -30,10 +30,11 @@ class PackedCodes:
     """rows x k values as one e4m3 byte per element (the grid value, exact) and one fp32 scale per (row, 128-group), in the
     tile order of include/fpq_b200.h: codes [k/128][rows_pad/8][8][8][16] bytes, scales [k/128][rows_pad]."""
     codes: torch.Tensor        # uint8 [rows_pad * k]
-    scales: torch.Tensor       # float32 [k / 128, rows_pad]
+    scales: torch.Tensor       # float32 [k / scale_group, rows_pad]
     rows: int
     k: int
     fmt: str
+    scale_group: int = GROUP   # 128 (one scale per row and 128-group) or k (one scale per row: per_token / per_channel)
 
     @property
     def rows_pad(self) -> int:
@@ -44,8 +45,8 @@ class PackedCodes:
         when `dtype` is the input's dtype."""
         out = torch.empty((self.rows, self.k), dtype=dtype, device=self.codes.device)
         with _on_device(self.codes) as dev:
-            L.check(L.lib().fpq_unpack_codes(self.codes.data_ptr(), self.scales.data_ptr(), self.rows, self.k, _DT[dtype],
-                                             out.data_ptr(), _stream(dev)), "fpq_unpack_codes")
+            L.check(L.lib().fpq_unpack_codes(self.codes.data_ptr(), self.scales.data_ptr(), self.rows, self.k, self.scale_group,
+                                             _DT[dtype], out.data_ptr(), _stream(dev)), "fpq_unpack_codes")
         return out
 
     def to_nibbles(self) -> torch.Tensor:
@@ -57,18 +58,19 @@ class PackedCodes:
         return nib
 
     @staticmethod
-    def from_nibbles(nib: torch.Tensor, scales: torch.Tensor, rows: int, k: int, fmt: str) -> "PackedCodes":
+    def from_nibbles(nib: torch.Tensor, scales: torch.Tensor, rows: int, k: int, fmt: str, scale_group: int = GROUP) -> "PackedCodes":
         _require_cuda(nib, "from_nibbles")
         codes = torch.empty(nib.numel() * 2, dtype=torch.uint8, device=nib.device)
         with _on_device(nib) as dev:
             L.check(L.lib().fpq_nibbles_to_codes(nib.data_ptr(), codes.numel(), L.FMT[fmt], codes.data_ptr(), _stream(dev)),
                     f"fpq_nibbles_to_codes({fmt})")
-        return PackedCodes(codes, scales, rows, k, fmt)
+        return PackedCodes(codes, scales, rows, k, fmt, scale_group)
 
 
-def pack_codes(x: torch.Tensor, fmt: str) -> PackedCodes:
+def pack_codes(x: torch.Tensor, fmt: str, per_row: bool = False) -> PackedCodes:
     """fp_quant_*_per_group_cuda (groups of 128 along the last dim, kernel tie rule) with the codes kept instead of multiplied
-    back.  x: [..., k] float16 / float32 CUDA tensor; leading dims are flattened into rows."""
+    back; per_row=True: one scale per row, the per_token / per_channel functions (qu.py:503-534).
+    x: [..., k] float16 / float32 CUDA tensor; leading dims are flattened into rows."""
     _require_cuda(x, "pack_codes")
     if x.dtype not in _DT:
         raise L.FpqError(f"pack_codes: dtype {x.dtype} is not supported (float16 / float32 only)")
@@ -82,12 +84,13 @@ def pack_codes(x: torch.Tensor, fmt: str) -> PackedCodes:
         x2 = x2.contiguous()
     rows = x2.shape[0]
     rp = rows_padded(rows)
+    sg = k if per_row else GROUP
     codes = torch.empty(rp * k, dtype=torch.uint8, device=x.device)
-    scales = torch.empty((k // GROUP, rp), dtype=torch.float32, device=x.device)
+    scales = torch.empty((k // sg, rp), dtype=torch.float32, device=x.device)
     with _on_device(x2) as dev:
-        L.check(L.lib().fpq_pack_codes(x2.data_ptr(), rows, k, _DT[x2.dtype], L.FMT[fmt], codes.data_ptr(), scales.data_ptr(),
+        L.check(L.lib().fpq_pack_codes(x2.data_ptr(), rows, k, sg, _DT[x2.dtype], L.FMT[fmt], codes.data_ptr(), scales.data_ptr(),
                                        _stream(dev)), f"fpq_pack_codes({fmt})")
-    return PackedCodes(codes, scales, rows, k, fmt)
+    return PackedCodes(codes, scales, rows, k, fmt, sg)
 
 
 def linear_codes(a: PackedCodes, w: PackedCodes, bias: Optional[torch.Tensor] = None, out_dtype=torch.float16,
@@ -97,6 +100,8 @@ def linear_codes(a: PackedCodes, w: PackedCodes, bias: Optional[torch.Tensor] = 
         raise L.FpqError(f"linear_codes: inner sizes differ ({a.k} vs {w.k})")
     if a.codes.device != w.codes.device:
         raise L.FpqError("linear_codes: operands on different devices")
+    if (a.scale_group == GROUP) != (w.scale_group == GROUP):
+        raise L.FpqError("linear_codes: both operands must be scaled per 128-group, or both per row")
     if out_dtype not in _DT:
         raise L.FpqError(f"linear_codes: output dtype {out_dtype} is not supported")
     m, n = a.rows, w.rows
@@ -114,9 +119,32 @@ def linear_codes(a: PackedCodes, w: PackedCodes, bias: Optional[torch.Tensor] = 
         b = bias.detach().to(torch.float32).contiguous()
     with _on_device(a.codes) as dev:
         L.check(L.lib().fpq_gemm_codes(a.codes.data_ptr(), a.scales.data_ptr(), m, w.codes.data_ptr(), w.scales.data_ptr(), n, a.k,
-                                       None if b is None else b.data_ptr(), _DT[out_dtype], out.data_ptr(), n, _stream(dev)),
-                "fpq_gemm_codes")
+                                       a.scale_group, None if b is None else b.data_ptr(), _DT[out_dtype], out.data_ptr(), n,
+                                       _stream(dev)), "fpq_gemm_codes")
     return out
+
+
+def linear_codes_sse(a: PackedCodes, w: PackedCodes, ref: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                     sse: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """sum((ref - F.linear(a, w, bias))^2) without materialising the product: the output-level loss of the format search
+    (search/search_fp4_format.py:472-476, :798-816).  ref: [a.rows, w.rows] float16 / float32, contiguous; returns (and
+    accumulates into) a one-element float64 tensor."""
+    _require_cuda(ref, "linear_codes_sse(ref)")
+    m, n = a.rows, w.rows
+    if a.k != w.k or (a.scale_group == GROUP) != (w.scale_group == GROUP):
+        raise L.FpqError("linear_codes_sse: operands do not match")
+    if ref.dtype not in _DT or ref.shape != (m, n) or not ref.is_contiguous() or n % 8 != 0:
+        raise L.FpqError("linear_codes_sse: ref must be a contiguous float16 / float32 [m, n] tensor, n a multiple of 8")
+    if sse is None:
+        sse = torch.zeros(1, dtype=torch.float64, device=ref.device)
+    elif sse.dtype != torch.float64 or not sse.is_cuda or sse.numel() < 1:
+        raise L.FpqError("linear_codes_sse: sse must be a float64 CUDA tensor")
+    b = None if bias is None else bias.detach().to(torch.float32).contiguous()
+    with _on_device(a.codes) as dev:
+        L.check(L.lib().fpq_gemm_codes_sse(a.codes.data_ptr(), a.scales.data_ptr(), m, w.codes.data_ptr(), w.scales.data_ptr(), n, a.k,
+                                           a.scale_group, None if b is None else b.data_ptr(), _DT[ref.dtype], ref.data_ptr(), n,
+                                           sse.data_ptr(), _stream(dev)), "fpq_gemm_codes_sse")
+    return sse
 
 
 class QuantizedLinearLowBit(torch.nn.Module):
@@ -128,23 +156,27 @@ class QuantizedLinearLowBit(torch.nn.Module):
         super().__init__()
         self.in_features, self.out_features = weight.k, weight.rows
         self.weight_fmt, self.act_fmt, self.out_dtype = weight.fmt, act_fmt, out_dtype
+        self.per_row = weight.scale_group != GROUP
         self.register_buffer("weight_codes", weight.codes)
         self.register_buffer("weight_scales", weight.scales)
         self.register_buffer("bias", None if bias is None else bias.detach().to(torch.float32).contiguous())
 
     @classmethod
-    def from_float(cls, module: torch.nn.Linear, weight_fmt: str = "e2m1", act_fmt: str = "e2m1", out_dtype=torch.float16):
+    def from_float(cls, module: torch.nn.Linear, weight_fmt: str = "e2m1", act_fmt: str = "e2m1", out_dtype=torch.float16,
+                   per_row: bool = False):
         """module.weight: [out, in] on a CUDA device; quantized exactly as QuantizedLinear.from_float does for
-        weight_quant='per_group' (qu.py:772-813: fp_quant_*_per_group_cuda on the fp32 weight)."""
+        weight_quant='per_group' (qu.py:772-813: fp_quant_*_per_group_cuda on the fp32 weight), or, with per_row=True, for
+        weight_quant='per_channel' / act_quant='per_token' (the README's W6A6 commands)."""
         w = module.weight.detach()
         _require_cuda(w, "QuantizedLinearLowBit.from_float")
-        return cls(pack_codes(w.to(torch.float32), weight_fmt), module.bias, act_fmt, out_dtype)
+        return cls(pack_codes(w.to(torch.float32), weight_fmt, per_row), module.bias, act_fmt, out_dtype)
 
     def weight_packed(self) -> PackedCodes:
-        return PackedCodes(self.weight_codes, self.weight_scales, self.out_features, self.in_features, self.weight_fmt)
+        return PackedCodes(self.weight_codes, self.weight_scales, self.out_features, self.in_features, self.weight_fmt,
+                           self.in_features if self.per_row else GROUP)
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        a = pack_codes(x, self.act_fmt)
+        a = pack_codes(x, self.act_fmt, self.per_row)
         y = linear_codes(a, self.weight_packed(), self.bias, self.out_dtype)
         return y.reshape(*x.shape[:-1], self.out_features)
 

@@ -94,6 +94,7 @@ FPQ_API uint64_t fpq_launch_count(void);
  *   "rot_small_max_chunks" rotate launches of up to this many 128-chunks take the small-launch kernel (default 40000)
  *   "smem_kb"              0 (default: the driver chooses per kernel) | 1..228: the shared-memory carveout (KB per SM) every
  *                          activation kernel asks for, and the streaming rotate kernel's shared-memory budget
+ *   "gemm_tile_n", "gemm_epi_cols", "gemm_stages"   tile shape, epilogue split and ring depth of fpq_gemm_codes (see there)
  * Results never depend on a tunable (tests/test_gpu_shapes.py).  Returns FPQ_ERR_ARG for an unknown name or value.
  */
 FPQ_API int fpq_set_tunable(const char *name, long long value);
@@ -266,30 +267,48 @@ FPQ_API int fpq_selftest_f16_flow(int format, unsigned long long *result, void *
  * Layout of an operand of `rows` x k (k % 128 == 0), rows_pad = fpq_codes_rows_padded(rows) = rows rounded up to 128:
  *   codes  : rows_pad * k bytes, [k/128 slabs][rows_pad/8][8 chunks of 16 K][8 rows][16 bytes]; byte = e4m3 encoding of the grid
  *            value (every FP4 / FP6 grid of the reference is a subset of e4m3); padding rows hold 0
- *   scales : fp32 [k/128][rows_pad]; 0 for the padding rows
+ *   scales : fp32 [k/128][rows_pad] (one per row and 128-group) or [1][rows_pad] (one per row); 0 for the padding rows
  * so that a 128-row x 128-K tile is 16 KB of contiguous memory in the tensor core's K-major core-matrix order.
  * ------------------------------------------------------------------------------------------------------------------ */
 FPQ_API size_t fpq_codes_rows_padded(size_t rows);
-/* x: [rows, k] contiguous, FPQ_F16 | FPQ_F32, 16-byte aligned; format: FPQ_FMT_*; groups of 128 along k; kernel tie rule. */
-FPQ_API int fpq_pack_codes(const void *x, size_t rows, size_t k, int in_dtype, int format, uint8_t *codes, float *scales,
-                   void *stream);
+/*
+ * x: [rows, k] contiguous, FPQ_F16 | FPQ_F32, 16-byte aligned; format: FPQ_FMT_*; kernel tie rule.
+ * scale_group: 128 = one scale per (row, 128-group), fp_quant_*_per_group_cuda (qu.py:265-378, 537-574); scales [k/128][rows_pad]
+ *              k   = one scale per row, the per_token / per_channel functions (qu.py:503-534);          scales [1][rows_pad]
+ */
+FPQ_API int fpq_pack_codes(const void *x, size_t rows, size_t k, size_t scale_group, int in_dtype, int format, uint8_t *codes,
+                   float *scales, void *stream);
 /* out[r, c] = out_dtype( fl32(q) * scale ): the fake-quantized tensor the codes stand for, [rows, k] contiguous. */
-FPQ_API int fpq_unpack_codes(const uint8_t *codes, const float *scales, size_t rows, size_t k, int out_dtype, void *out,
-                   void *stream);
+FPQ_API int fpq_unpack_codes(const uint8_t *codes, const float *scales, size_t rows, size_t k, size_t scale_group,
+                   int out_dtype, void *out, void *stream);
 /* 4-bit storage of the FP4 formats (FPQ_FMT_E2M1 | E1M2 | E3M0): nibble = sign << 3 | index of |q| in the ascending
  * non-negative half grid; byte i of `nibbles` holds codes 2i (low nibble) and 2i+1.  n_codes % 8 == 0.  Lossless both ways. */
 FPQ_API int fpq_codes_to_nibbles(const uint8_t *codes, size_t n_codes, int format, uint8_t *nibbles, void *stream);
 FPQ_API int fpq_nibbles_to_codes(const uint8_t *nibbles, size_t n_codes, int format, uint8_t *codes, void *stream);
 /*
- * C[i, j] = bias[j] + sum_t fma-chain over the k/128 slabs t (ascending) of  (P_t[i, j] * sa[t, i]) * sw[t, j],
- *           P_t[i, j] = sum over the slab's 128 k of qa[i, k] * qw[j, k]      (exact; fp32 accumulate in tensor memory)
- * i.e. F.linear(A, W, bias) for A = [m, k] and W = [n, k] given as codes.  c: [m, ldc] row-major, FPQ_F16 | FPQ_F32, 16-byte
- * aligned, n % 8 == 0, ldc % 8 == 0; bias: fp32 [n] or NULL.  One 128 x 128 tile per CTA, 203 KB of shared memory.
- * Tunables: "gemm_stages" (2..6, default 6), "gemm_desc_swap" (bring-up aid, default 0).
+ * F.linear(A, W, bias) for A = [m, k] and W = [n, k] given as codes that share `scale_group` (128 or k):
+ *   C[i, j] = bias[j] + fma-chain over the scale groups t (ascending) of  (P_t[i, j] * sa[t, i]) * sw[t, j],
+ *             P_t[i, j] = sum over the group's k of qa[i, k] * qw[j, k]        (fp32 accumulate in tensor memory; exact for the
+ *                                                                              FP4 formats and for 128-groups of the FP6 ones)
+ * c: [m, ldc] row-major, FPQ_F16 | FPQ_F32, 16-byte aligned, n % 8 == 0, ldc % 8 == 0; bias: fp32 [n] or NULL.
+ * Persistent kernel, one CTA per SM, 128 x 256 (or 128 x 128) tiles of C, ~205 KB of shared memory.  With groups of 128 every
+ * accumulator is handed to the epilogue warps once per 128 K (1.1-1.4 PFLOP/s on a B200); with row scales once per tile
+ * (2.0-2.5 PFLOP/s; the fp16 library GEMM on the fake-quantized tensors runs at 1.4-1.5).
+ * Tunables: "gemm_tile_n" (128 | 256, default 256), "gemm_epi_cols" (columns per epilogue warp: 32 | 64 | 128, default 128),
+ * "gemm_stages" (2..6, default 6; at most 4 with 256-column tiles).  Results never depend on them.
  */
 FPQ_API int fpq_gemm_codes(const uint8_t *a_codes, const float *a_scales, size_t m, const uint8_t *b_codes,
-                   const float *b_scales, size_t n, size_t k, const float *bias, int out_dtype, void *c, size_t ldc,
-                   void *stream);
+                   const float *b_scales, size_t n, size_t k, size_t scale_group, const float *bias, int out_dtype,
+                   void *c, size_t ldc, void *stream);
+/*
+ * Output-level loss of the format search without materialising the quantized layer's output (SURVEY.md section 8 f3;
+ * search/search_fp4_format.py:472-476, :798-816: compute_quant_error(y_fp, F.linear(x_q, W_q))):
+ *   *sse += sum_{i<m, j<n} (ref[i, j] - C[i, j])^2,   C as fpq_gemm_codes computes it in fp32 (never stored)
+ * ref: [m, ldr] row-major, FPQ_F16 | FPQ_F32, the full-precision layer output; sse: one float64 accumulator the caller zeroes.
+ */
+FPQ_API int fpq_gemm_codes_sse(const uint8_t *a_codes, const float *a_scales, size_t m, const uint8_t *b_codes,
+                   const float *b_scales, size_t n, size_t k, size_t scale_group, const float *bias, int ref_dtype,
+                   const void *ref, size_t ldr, double *sse, void *stream);
 
 #ifdef __cplusplus
 }

@@ -32,7 +32,7 @@ def _lib():
         lib = ctypes.CDLL(so)
         lib.gemm_codes_ref.restype = None
         lib.gemm_codes_ref.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p,
-                                       ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
+                                       ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_void_p]
         _LIB = lib
     return _LIB
 
@@ -41,25 +41,27 @@ def rows_padded(rows: int) -> int:
     return (rows + TILE_ROWS - 1) // TILE_ROWS * TILE_ROWS
 
 
-def quantize_codes(x: np.ndarray, fmt: str):
-    """(q, s): q fp32 [rows, k] grid values, s fp32 [rows, k/128] scales, as fp_quant_*_per_group_cuda computes them
-    (qu.py:320-326: scale = absmax / max|grid| in the input dtype, x / scale in the input dtype, quant_cuda.quant)."""
+def quantize_codes(x: np.ndarray, fmt: str, scale_group=GROUP):
+    """(q, s): q fp32 [rows, k] grid values, s fp32 [rows, k/scale_group] scales, as fp_quant_*_per_group_cuda computes them
+    (qu.py:320-326: scale = absmax / max|grid| in the input dtype, x / scale in the input dtype, quant_cuda.quant);
+    scale_group=None: one scale per row, the per_token / per_channel functions (qu.py:503-534)."""
     x = np.asarray(x)
     assert x.ndim == 2 and x.shape[1] % GROUP == 0 and x.dtype in (np.float16, np.float32)
     dt = x.dtype
     grid = O.GRIDS[fmt]
-    g = O._as_groups(x, GROUP)
+    scale_group = x.shape[1] if scale_group is None else scale_group
+    g = O._as_groups(x, scale_group)
     a = O._absmax_lastdim(g)
     s = O._div(a, np.full_like(a, O.grid_absmax(fmt), dtype=np.float32), dt)
     v = O._div(g, s, dt)
     q = O.scan_quant(v.astype(np.float32), grid).reshape(x.shape)
-    return q.astype(np.float32), s.astype(np.float32).reshape(x.shape[0], x.shape[1] // GROUP)
+    return q.astype(np.float32), s.astype(np.float32).reshape(x.shape[0], x.shape[1] // scale_group)
 
 
 def dequantize(q: np.ndarray, s: np.ndarray, dtype) -> np.ndarray:
     """qu.py:328-329: quantized * scale in fp32, cast to the output dtype."""
     with np.errstate(invalid="ignore", over="ignore", under="ignore"):
-        out = q.reshape(q.shape[0], -1, GROUP) * s[:, :, None]
+        out = q.reshape(q.shape[0], s.shape[1], -1) * s[:, :, None]
         return out.reshape(q.shape).astype(dtype)
 
 
@@ -114,9 +116,9 @@ def scales_layout(s: np.ndarray) -> np.ndarray:
     return out
 
 
-def pack_codes(x: np.ndarray, fmt: str):
-    """What fpq_pack_codes writes: (flat code bytes, scales [k/128, rows_pad])."""
-    q, s = quantize_codes(x, fmt)
+def pack_codes(x: np.ndarray, fmt: str, scale_group=GROUP):
+    """What fpq_pack_codes writes: (flat code bytes, scales [k/scale_group, rows_pad])."""
+    q, s = quantize_codes(x, fmt, scale_group)
     return to_blocked(e4m3_encode(q)), scales_layout(s)
 
 
@@ -143,8 +145,9 @@ def nibbles_to_codes(nib: np.ndarray, fmt: str) -> np.ndarray:
 
 
 def gemm_codes(qa: np.ndarray, sa: np.ndarray, qw: np.ndarray, sw: np.ndarray, bias=None) -> np.ndarray:
-    """fp32 [m, n] in the fixed operation order of oracle/gemm_codes.c.  qa [m, k], sa [m, k/128], qw [n, k], sw [n, k/128]."""
+    """fp32 [m, n] in the fixed operation order of oracle/gemm_codes.c.  qa [m, k], sa [m, groups], qw [n, k], sw [n, groups]."""
     m, k = qa.shape
+    assert sa.shape[1] == sw.shape[1] and k % sa.shape[1] == 0
     n = qw.shape[0]
     qa = np.ascontiguousarray(qa, dtype=np.float32)
     qw = np.ascontiguousarray(qw, dtype=np.float32)
@@ -152,14 +155,14 @@ def gemm_codes(qa: np.ndarray, sa: np.ndarray, qw: np.ndarray, sw: np.ndarray, b
     swt = np.ascontiguousarray(sw.T, dtype=np.float32)
     b = None if bias is None else np.ascontiguousarray(bias, dtype=np.float32)
     c = np.empty((m, n), dtype=np.float32)
-    _lib().gemm_codes_ref(qa.ctypes.data, sat.ctypes.data, m, qw.ctypes.data, swt.ctypes.data, n, k,
+    _lib().gemm_codes_ref(qa.ctypes.data, sat.ctypes.data, m, qw.ctypes.data, swt.ctypes.data, n, k, k // sa.shape[1],
                           None if b is None else b.ctypes.data, c.ctypes.data)
     return c
 
 
 def linear_f64(qa, sa, qw, sw, bias=None) -> np.ndarray:
     """The reference's expression F.linear(q_x * s_x, W_q * s_w, b) evaluated in float64 on the exact operand values."""
-    a = qa.astype(np.float64).reshape(qa.shape[0], -1, GROUP) * sa.astype(np.float64)[:, :, None]
-    w = qw.astype(np.float64).reshape(qw.shape[0], -1, GROUP) * sw.astype(np.float64)[:, :, None]
+    a = qa.astype(np.float64).reshape(qa.shape[0], sa.shape[1], -1) * sa.astype(np.float64)[:, :, None]
+    w = qw.astype(np.float64).reshape(qw.shape[0], sw.shape[1], -1) * sw.astype(np.float64)[:, :, None]
     c = a.reshape(qa.shape) @ w.reshape(qw.shape).T
     return c if bias is None else c + np.asarray(bias, dtype=np.float64)

@@ -82,22 +82,96 @@ def _operands(rng, m, n, k, fmt_a, fmt_w, dtype_a=np.float16):
     return x, w, LB.quantize_codes(x, fmt_a), LB.quantize_codes(w, fmt_w)
 
 
-@pytest.mark.parametrize("m,n,k", [(128, 128, 128), (128, 128, 256), (1, 8, 128), (100, 136, 384), (300, 384, 1920), (257, 128, 7680)])
-@pytest.mark.parametrize("stages", [6, 2])
-def test_gemm_codes_bit_exact_against_the_fixed_order_oracle(m, n, k, stages):
+@pytest.mark.parametrize("m,n,k", [(128, 128, 128), (128, 128, 256), (1, 8, 128), (100, 136, 384), (300, 384, 1920), (257, 128, 7680),
+                                   (700, 640, 640)])
+@pytest.mark.parametrize("tile_n,epi_cols,stages", [(256, 64, 4), (256, 128, 2), (128, 32, 6), (128, 64, 2), (128, 128, 3)])
+def test_gemm_codes_bit_exact_against_the_fixed_order_oracle(m, n, k, tile_n, epi_cols, stages):
     rng = np.random.default_rng(m + n + k)
     x, w, (qa, sa), (qw, sw) = _operands(rng, m, n, k, "e2m1", "e2m1")
     bias = rng.standard_normal(n).astype(np.float32)
     a = lowbit.pack_codes(torch.from_numpy(x).to(dev()), "e2m1")
     ww = lowbit.pack_codes(torch.from_numpy(w).to(dev()), "e2m1")
     L.set_tunable("gemm_stages", stages)
+    L.set_tunable("gemm_tile_n", tile_n)
+    L.set_tunable("gemm_epi_cols", epi_cols)
     try:
         c32 = lowbit.linear_codes(a, ww, torch.from_numpy(bias).to(dev()), torch.float32).cpu().numpy()
         c16 = lowbit.linear_codes(a, ww, None, torch.float16).cpu().numpy()
     finally:
         L.set_tunable("gemm_stages", 6)
+        L.set_tunable("gemm_tile_n", 256)
+        L.set_tunable("gemm_epi_cols", 128)
     assert np.array_equal(bits(c32), bits(LB.gemm_codes(qa, sa, qw, sw, bias)))
     assert np.array_equal(bits(c16), bits(LB.gemm_codes(qa, sa, qw, sw).astype(np.float16)))
+
+
+def test_gemm_codes_many_tiles_per_cta():
+    """more tiles than SMs: the persistent loop, the scale ring and both accumulators wrap several times"""
+    rng = np.random.default_rng(99)
+    m, n, k = 128 * 21, 256 * 9 + 128, 384
+    x, w, (qa, sa), (qw, sw) = _operands(rng, m, n, k, "e2m1", "e1m2")
+    a = lowbit.pack_codes(torch.from_numpy(x).to(dev()), "e2m1")
+    ww = lowbit.pack_codes(torch.from_numpy(w).to(dev()), "e1m2")
+    want = LB.gemm_codes(qa, sa, qw, sw)
+    for tile_n, epi_cols in ((256, 64), (256, 128), (128, 32), (128, 64), (128, 128)):
+        L.set_tunable("gemm_tile_n", tile_n)
+        L.set_tunable("gemm_epi_cols", epi_cols)
+        try:
+            c = lowbit.linear_codes(a, ww, None, torch.float32).cpu().numpy()
+        finally:
+            L.set_tunable("gemm_tile_n", 256)
+            L.set_tunable("gemm_epi_cols", 128)
+        assert np.array_equal(bits(c), bits(want))
+
+
+@pytest.mark.parametrize("fmt_a,fmt_w,dtype", [("e2m1", "e2m1", np.float16), ("e1m2", "e3m0", np.float32), ("e2m3", "e2m3", np.float16),
+                                               ("e3m2", "e3m2", np.float16)])
+def test_row_scaled_codes_and_gemm(fmt_a, fmt_w, dtype):
+    """per_token activations x per_channel weights (the README's W6A6 commands; fp6_quant_*_per_token_cuda qu.py:503-534):
+    one scale per row, the whole K accumulates in tensor memory.  FP4: bit-exact (the sums are exact in fp32); FP6: the
+    accumulation order inside the tensor core is not specified, tolerance 2^-20 of sum |terms|."""
+    rng = np.random.default_rng(13)
+    m, n, k = 300, 384, 2304
+    x = rng.standard_normal((m, k)).astype(dtype)
+    w = (rng.standard_normal((n, k)) * 0.05).astype(np.float32)
+    a = lowbit.pack_codes(torch.from_numpy(x).to(dev()), fmt_a, per_row=True)
+    ww = lowbit.pack_codes(torch.from_numpy(w).to(dev()), fmt_w, per_row=True)
+    wc, ws = LB.pack_codes(x, fmt_a, None)
+    assert np.array_equal(a.codes.cpu().numpy(), wc) and same_bits(a.scales.cpu().numpy(), ws)
+    out_dt = np.float16 if (dtype == np.float16 or fmt_a in ("e2m3", "e3m2")) else np.float32
+    got = a.dequantize(torch.float16 if out_dt == np.float16 else torch.float32).cpu().numpy()
+    assert same_bits(got, O.fake_quant(x, fmt_a, None, "kernel", out_dtype=out_dt))
+    (qa, sa), (qw, sw) = LB.quantize_codes(x, fmt_a, None), LB.quantize_codes(w, fmt_w, None)
+    c = lowbit.linear_codes(a, ww, None, torch.float32).cpu().numpy()
+    want = LB.gemm_codes(qa, sa, qw, sw)
+    if fmt_a in ("e2m1", "e1m2", "e3m0"):
+        assert np.array_equal(bits(c), bits(want))
+    else:
+        mag = (np.abs(qa) * sa) @ (np.abs(qw) * sw).T
+        assert np.all(np.abs(c.astype(np.float64) - want) <= 2.0 ** -20 * mag)
+
+
+@pytest.mark.parametrize("ref_dtype", [torch.float32, torch.float16])
+@pytest.mark.parametrize("per_row", [False, True])
+def test_fused_output_level_loss(ref_dtype, per_row):
+    """fpq_gemm_codes_sse == sum((ref - linear_codes)^2) in float64, without the product ever being stored
+    (compute_quant_error of search/search_fp4_format.py:472-476 at the layer output)."""
+    torch.manual_seed(3)
+    m, n, k = 1000, 640, 1920
+    x = torch.randn(m, k, device=dev(), dtype=torch.float16)
+    w = torch.randn(n, k, device=dev()) * 0.03
+    bias = torch.randn(n, device=dev())
+    ref = torch.nn.functional.linear(x.float(), w, bias).to(ref_dtype)
+    a, ww = lowbit.pack_codes(x, "e2m1", per_row), lowbit.pack_codes(w, "e2m1", per_row)
+    y = lowbit.linear_codes(a, ww, bias, torch.float32)
+    want = ((ref.double() - y.double()) ** 2).sum().item()
+    for tile_n in (256, 128):
+        L.set_tunable("gemm_tile_n", tile_n)
+        try:
+            got = lowbit.linear_codes_sse(a, ww, ref, bias).item()
+        finally:
+            L.set_tunable("gemm_tile_n", 256)
+        assert abs(got - want) <= 2e-6 * want          # fp32 squares of 8 columns, then float64
 
 
 @pytest.mark.parametrize("fmt_a,fmt_w", [("e1m2", "e3m0"), ("e2m3", "e2m3"), ("e3m2", "e2m1"), ("e3m2", "e3m2")])

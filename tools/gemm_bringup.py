@@ -122,19 +122,27 @@ def bench(dev, shapes):
         wq = ops.fake_quant(wt, "e2m1", 128, "kernel").half()
         flop = 2.0 * m * n * k
         res = {}
-        for st in (6, 4, 3):
+        ar, wr = lowbit.pack_codes(x, "e2m1", True), lowbit.pack_codes(wt, "e2m1", True)
+        for tn, ec, st in ((256, 64, 4), (256, 128, 4), (128, 32, 6), (128, 64, 6), (128, 128, 6)):
             L.set_tunable("gemm_stages", st)
-            res[st] = timeit(lambda: lowbit.linear_codes(a, w, None, torch.float16, out))
+            L.set_tunable("gemm_tile_n", tn)
+            L.set_tunable("gemm_epi_cols", ec)
+            res[f"g128 tn{tn} ec{ec}"] = timeit(lambda: lowbit.linear_codes(a, w, None, torch.float16, out))
+            res[f"row tn{tn} ec{ec}"] = timeit(lambda: lowbit.linear_codes(ar, wr, None, torch.float16, out))
         L.set_tunable("gemm_stages", 6)
+        L.set_tunable("gemm_tile_n", 256)
+        L.set_tunable("gemm_epi_cols", 128)
+        res["sse g128"] = timeit(lambda: lowbit.linear_codes_sse(a, w, out))
+        t_packrow = timeit(lambda: lowbit.pack_codes(x, "e2m1", True))
         t_pack = timeit(lambda: lowbit.pack_codes(x, "e2m1"))
         t_fq = timeit(lambda: ops.fake_quant(x, "e2m1", 128, "kernel"))
         t_ref = timeit(lambda: torch.nn.functional.linear(xq, wq))
         y = lowbit.linear_codes(a, w, None, torch.float16)
         yr = torch.nn.functional.linear(xq, wq)
         rel = ((y.float() - yr.float()).abs().max() / yr.float().abs().max()).item()
-        print(f"{name} m={m} n={n} k={k}: codes GEMM " + " ".join(f"st{st} {t:.3f} ms ({flop / t / 1e9:.0f} TF/s)" for st, t in res.items())
+        print(f"{name} m={m} n={n} k={k}: codes GEMM " + " ".join(f"[{st}] {t:.3f} ms ({flop / t / 1e9:.0f} TF/s)" for st, t in res.items())
               + f" | cuBLAS fp16 on fake-quantized {t_ref:.3f} ms ({flop / t_ref / 1e9:.0f} TF/s) | pack {t_pack:.3f} ms ({(m * k * 3 + m * k / 32) / t_pack / 1e6:.0f} GB/s)"
-              f" fake_quant {t_fq:.3f} ms | max rel diff {rel:.2e}", flush=True)
+              f" pack per-row {t_packrow:.3f} ms fake_quant {t_fq:.3f} ms | max rel diff {rel:.2e}", flush=True)
 
 
 if __name__ == "__main__":
@@ -143,13 +151,15 @@ if __name__ == "__main__":
     t0 = time.time()
     ok = check_pack(dev)
     ok2 = check_gemm(dev)
-    if not ok2:
-        print("retrying with the descriptor strides swapped")
-        L.set_tunable("gemm_desc_swap", 1)
-        ok3 = check_gemm(dev)
-        L.set_tunable("gemm_desc_swap", 0)
-        print("swapped:", ok3)
+    for tn, ec in ((256, 64), (128, 32), (128, 64), (128, 128)):
+        L.set_tunable("gemm_tile_n", tn)
+        L.set_tunable("gemm_epi_cols", ec)
+        print(f"tile_n {tn}, epilogue columns {ec}:")
+        ok2 = check_gemm(dev) and ok2
+    L.set_tunable("gemm_tile_n", 256)
+    L.set_tunable("gemm_epi_cols", 128)
     print(f"parity ladder took {time.time() - t0:.1f} s")
     if ok2 or "--bench" in sys.argv:
-        bench(dev, [("d30 mat_qkv stage 9", 25600, 5760, 1920), ("d30 fc1 stage 9", 25600, 7680, 1920), ("d30 proj stage 9", 25600, 1920, 1920),
-                    ("d30 fc2-shape stage 9", 25600, 1920, 7680), ("d30 mat_qkv all stages", 68000, 5760, 1920), ("d16 fc1 B=64", 32768, 4096, 1024)])
+        shapes = [("d30 mat_qkv stage 9", 25600, 5760, 1920), ("d30 fc1 stage 9", 25600, 7680, 1920), ("d30 proj stage 9", 25600, 1920, 1920),
+                  ("d30 fc2-shape stage 9", 25600, 1920, 7680), ("d30 mat_qkv all stages", 68000, 5760, 1920), ("d16 fc1 B=64", 32768, 4096, 1024)]
+        bench(dev, shapes[:1] + shapes[3:4] if "--short" in sys.argv else shapes)
