@@ -64,6 +64,7 @@ def parse_args():
     ap.add_argument("--gen-iters", type=int, default=3)
     ap.add_argument("--no-search", action="store_true", help="skip the format-search leg (BASELINE configs[4] on a bounded unit list)")
     ap.add_argument("--search-blocks", type=int, default=2, help="transformer blocks whose four layers the search leg scores (the full sweep has 30)")
+    ap.add_argument("--no-lowbit", action="store_true", help="skip the low-bit GEMM leg (SURVEY section 8 f4)")
     ap.add_argument("--no-reference-legs", action="store_true",
                     help="skip reference_gpu_path / generation_reference_model (the unmodified reference from baseline/_ref on this GPU)")
     ap.add_argument("--no-other-configs", action="store_true",
@@ -435,42 +436,110 @@ def search_leg(torch, dist, dev, rank, world, blocks, depth=30, acts=1000):
             x = torch.nn.functional.gelu(x, approximate="tanh")
         return w, list(x.to(dt).split(rows))
 
-    def run():
+    def run(scorer=None):
+        scorer = scorer or search.search_layer_batched
         table.zero_()
         cur, data = None, None
         for li, wi in mine:
             if li != cur:
                 cur, data = li, layer(li)
-            table[li, wi] = search.search_layer_batched(data[0], data[1], [search.FP4_FORMATS[wi]], search.FP4_FORMATS)[0]
+            table[li, wi] = scorer(data[0], data[1], [search.FP4_FORMATS[wi]], search.FP4_FORMATS)[0]
         if world > 1:
             dist.all_reduce(table)
+
+    def timed(scorer):
+        run(scorer)                                 # warm-up (cuBLAS heuristics, allocator)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(scorer)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
     # the reference's search scripts never enable TF32: the fp32 GEMMs of the mat_qkv / fc1 layers run at full precision
     # (the generation harness above switches TF32 on, like evaluate_fp_quant_transform_rotate.py:171-175 -- undo that here)
     tf32_saved = (torch.backends.cuda.matmul.allow_tf32, torch.get_float32_matmul_precision())
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.set_float32_matmul_precision("highest")
-    run()                                           # warm-up (cuBLAS heuristics, allocator)
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    run()
-    e1.record()
-    torch.cuda.synchronize()
-    t = torch.tensor([e0.elapsed_time(e1) / 1e3], device=dev, dtype=torch.float64)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    secs = float(t.item())
+    # the same sweep with the candidates evaluated from codes on the tensor cores and the loss taken in the GEMM's epilogue
+    # (search.search_layer_lowbit); then the fake-quant + library-GEMM path, whose table is the one reported
+    secs_lowbit = timed(search.search_layer_lowbit)
+    table_lowbit = table.clone()
+    secs = timed(None)
     torch.backends.cuda.matmul.allow_tf32 = tf32_saved[0]
     torch.set_float32_matmul_precision(tf32_saved[1])
     best = [search.best_formats(table[li], search.FP4_FORMATS, search.FP4_FORMATS) for li in range(len(names))]
-    return {"seconds": secs, "units": len(units), "units_per_sec": len(units) / secs, "layers": len(names), "scaling": "strong",
+    best_lb = [search.best_formats(table_lowbit[li], search.FP4_FORMATS, search.FP4_FORMATS) for li in range(len(names))]
+    rel = float(((table_lowbit - table).abs() / table.abs().clamp_min(1e-300)).max().item())
+    lowbit = {"seconds": secs_lowbit, "units_per_sec": len(units) / secs_lowbit, "max_rel_diff_of_loss_table": rel,
+              "same_winners": all(a["weight_format"] == b["weight_format"] and a["activation_format"] == b["activation_format"]
+                                  for a, b in zip(best, best_lb)),
+              "what": "search_layer_lowbit: quantizers emit codes, tcgen05 e4m3-container GEMM, loss in the epilogue (nothing written)"}
+    return {"seconds": secs, "lowbit": lowbit, "units": len(units), "units_per_sec": len(units) / secs, "layers": len(names), "scaling": "strong",
             "calibration_rows_per_layer": sum(rows), "activations_per_layer": acts,
             "desc": f"FP4 format search, {blocks} of {depth} VAR-d30 blocks x 4 layers x 3 weight formats = {len(units)} units over {world} rank(s); "
                     "per unit: 3 activation formats, output-level loss over 1000 row-stacked calibration tensors",
             "winners": {f"blocks.{b}.{n}": f"w={best[i]['weight_format']},a={best[i]['activation_format']}" for i, (b, n) in enumerate(names)}}
+
+
+def lowbit_gemm_leg(torch, dev, peaks):
+    """the four linears of one VAR-d30 block at the largest stage (25 600 token rows) as REAL low-bit GEMMs
+    from packed codes (fpqvar_b200.lowbit: tcgen05.mma kind::f8f6f4 on e4m3 containers) beside what the reference runs -- the
+    fp16 library GEMM on the fake-quantized tensors (QuantizedLinear.forward, qu.py:764-769).  `group128` = one scale per (row,
+    128-group) on both operands (the README W4A4 configuration; bit-exact against oracle/gemm_codes.c), `row` = per_token x
+    per_channel (the README W6A6 configuration).  CUDA events, 20 launches after 3 warm-ups, outputs rotate through 4 buffers."""
+    from fpqvar_b200 import lowbit, ops
+    C, rows = 1920, 25600
+    layers = {"mat_qkv": (3 * C, C), "proj": (C, C), "fc1": (4 * C, C), "fc2": (C, 4 * C)}
+
+    def timeit(fn, iters=20, warm=3):
+        for i in range(warm):
+            fn(i)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters / 1e3
+
+    out, tot = {}, {"group128": 0.0, "row": 0.0, "fp16_library": 0.0, "flop": 0.0}
+    g = torch.Generator(device=dev).manual_seed(7)
+    for name, (n, k) in layers.items():
+        x = torch.randn(rows, k, device=dev, dtype=torch.float16, generator=g)
+        w = torch.randn(n, k, device=dev, generator=g) * 0.02
+        outs = [torch.empty(rows, n, device=dev, dtype=torch.float16) for _ in range(4)]
+        a, ww = lowbit.pack_codes(x, "e2m1"), lowbit.pack_codes(w, "e2m1")
+        ar, wr = lowbit.pack_codes(x, "e2m1", True), lowbit.pack_codes(w, "e2m1", True)
+        xq, wq = ops.fake_quant(x, "e2m1", 128, "kernel"), ops.fake_quant(w, "e2m1", 128, "kernel").half()
+        flop = 2.0 * rows * n * k
+        t_g = timeit(lambda i: lowbit.linear_codes(a, ww, None, torch.float16, outs[i % 4]))
+        t_r = timeit(lambda i: lowbit.linear_codes(ar, wr, None, torch.float16, outs[i % 4]))
+        t_l = timeit(lambda i: torch.nn.functional.linear(xq, wq))
+        t_p = timeit(lambda i: lowbit.pack_codes(x, "e2m1"))
+        t_f = timeit(lambda i: ops.fake_quant(x, "e2m1", 128, "kernel"))
+        out[name] = {"m_n_k": [rows, n, k], "group128_TFLOPs": flop / t_g / 1e12, "row_TFLOPs": flop / t_r / 1e12,
+                     "fp16_library_on_fake_quantized_TFLOPs": flop / t_l / 1e12,
+                     "quantize_to_codes_us": t_p * 1e6, "quantize_to_codes_GBps": rows * k * 3.03 / t_p / 1e9, "fake_quant_us": t_f * 1e6}
+        for key, t in (("group128", t_g), ("row", t_r), ("fp16_library", t_l)):
+            tot[key] += t
+        tot["flop"] += flop
+        del x, w, outs, a, ww, ar, wr, xq, wq
+    peak = peaks.get("bf16_tflops") if peaks else None
+    return {"layers": out,
+            "block_TFLOPs": {k: tot["flop"] / tot[k] / 1e12 for k in ("group128", "row", "fp16_library")},
+            "roofline": {"bound": "tensor", "kernel": "gemm_codes_kernel<256, 128> (row scales)", "achieved": tot["flop"] / tot["row"] / 1e12,
+                         "peak": 2 * peak if peak else None, "unit": "TFLOP/s",
+                         "frac": tot["flop"] / tot["row"] / 1e12 / (2 * peak) if peak else None,
+                         "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (the 8-bit tensor rate is twice the 16-bit one; no measured 8-bit figure on this pool)"},
+            "what": "VAR-d30 block at the largest stage, W4A4 e2m1 x e2m1 from codes; see profiles/r2_gemm_codes.txt for the variants"}
 
 
 def main():
@@ -648,6 +717,17 @@ def main():
         except Exception as e:  # noqa: BLE001
             search_res = {"error": f"{type(e).__name__}: {e}"}
 
+    # ---- real low-bit GEMMs from codes beside the fp16 library GEMM on the fake-quantized tensors (rank 0) ----
+    lowbit_res = None
+    if rank == 0 and not args.no_lowbit:
+        try:
+            mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            lowbit_res = lowbit_gemm_leg(torch, dev, json.load(open(mp)) if os.path.exists(mp) else None)
+        except Exception as e:  # noqa: BLE001
+            lowbit_res = {"error": f"{type(e).__name__}: {e}"}
+    if world > 1:
+        dist.barrier()
+
     # ---- the reference's own GPU path and its own model on this box (rank 0, N=1; outside every timed region above) ----
     reference_gpu = generation_ref = other = None
     if world == 1 and not args.no_reference_legs:
@@ -709,6 +789,8 @@ def main():
             line["generation"] = generation
         if search_res is not None:
             line["search"] = search_res
+        if lowbit_res is not None:
+            line["lowbit_gemm"] = lowbit_res
         if reference_gpu is not None:
             line["reference_gpu_path"] = reference_gpu
         if generation_ref is not None:

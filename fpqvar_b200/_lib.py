@@ -58,7 +58,7 @@ SIGNATURES = {
     "fpq_gemm_codes": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t,
                                   _c.c_size_t, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_size_t, _c.c_void_p]),
     "fpq_gemm_codes_sse": (_c.c_int, [_c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p, _c.c_size_t, _c.c_size_t,
-                                      _c.c_size_t, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p]),
+                                      _c.c_size_t, _c.c_void_p, _c.c_int, _c.c_void_p, _c.c_size_t, _c.c_void_p, _c.c_void_p, _c.c_void_p]),
 }
 
 _lib = None

@@ -297,6 +297,7 @@ struct GemmArgs {
     const float* bias;       // fp32 [n] or null
     void* c;                 // output matrix, or the reference matrix of the SSE modes
     double* sse;             // SSE modes: one accumulator
+    const double* row_weight;  // SSE modes: weight of every row's squared error, or null (= 1)
     size_t ldc;              // elements
     size_t m, n;             // valid rows / columns of C
     size_t m_pad, n_pad;     // padded row counts of the two code arrays (multiples of 128)
@@ -478,6 +479,7 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
                 if (lane == 0) mbar_arrive(&bar_sempty[q]);
             }
             const size_t row0 = size_t(tile / g.tiles_n) * TM + quarter * 32 + tr, col0 = size_t(tile % g.tiles_n) * TN + col_off + 2 * tq;
+            float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};          // SSE modes: squared error of this thread's piece of each of its rows
 #pragma unroll
             for (int bl = 0; bl < NB; ++bl) {
                 const size_t col = col0 + 8 * bl;
@@ -494,7 +496,7 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
                     } else if constexpr (OUT == OUT_F32) {
                         *reinterpret_cast<float2*>(static_cast<float*>(g.c) + row * g.ldc + col) = make_float2(o.lo, o.hi);
                     } else {
-                        // squared distance to the reference matrix: fp32 differences, rows of the tile in fp64
+                        // squared distance to the reference matrix: fp32 differences and row pieces, float64 across rows
                         float r0, r1;
                         if constexpr (OUT == OUT_SSE_F16) {
                             const uint32_t u = *reinterpret_cast<const uint32_t*>(static_cast<const __half*>(g.c) + row * g.ldc + col);
@@ -506,8 +508,15 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
                             r1 = u.y;
                         }
                         const float d0 = r0 - o.lo, d1 = r1 - o.hi;
-                        sse_thread += double(__fmaf_rn(d1, d1, __fmul_rn(d0, d0)));
+                        part[rr] = __fmaf_rn(d1, d1, __fmaf_rn(d0, d0, part[rr]));
                     }
+                }
+            }
+            if constexpr (OUT == OUT_SSE_F16 || OUT == OUT_SSE_F32) {
+#pragma unroll
+                for (int rr = 0; rr < 4; ++rr) {
+                    const size_t row = row0 + 8 * rr;
+                    if (row < g.m) sse_thread += double(part[rr]) * (g.row_weight ? g.row_weight[row] : 1.0);
                 }
             }
         }
@@ -674,7 +683,7 @@ int gemm_common(GemmArgs& g, const uint8_t* a_codes, const float* a_scales, size
     if (!aligned16(a_codes) || !aligned16(a_scales) || !aligned16(b_codes) || !aligned16(b_scales) || !aligned16(c)) return FPQ_ERR_ARG;
     if (n % 8 != 0 || ldc % 8 != 0 || ldc < n || (reinterpret_cast<uintptr_t>(bias) & 7u)) return FPQ_ERR_ARG;
     g.a_codes = a_codes; g.a_scales = a_scales; g.b_codes = b_codes; g.b_scales = b_scales; g.bias = bias;
-    g.c = c; g.sse = nullptr; g.ldc = ldc; g.m = m; g.n = n;
+    g.c = c; g.sse = nullptr; g.row_weight = nullptr; g.ldc = ldc; g.m = m; g.n = n;
     g.m_pad = fpq_codes_rows_padded(m); g.n_pad = fpq_codes_rows_padded(n);
     g.slabs = uint32_t(k / GK);
     g.group_slabs = scale_group == GK ? 1u : g.slabs;
@@ -696,12 +705,13 @@ extern "C" int fpq_gemm_codes(const uint8_t* a_codes, const float* a_scales, siz
 
 extern "C" int fpq_gemm_codes_sse(const uint8_t* a_codes, const float* a_scales, size_t m, const uint8_t* b_codes, const float* b_scales,
                                   size_t n, size_t k, size_t scale_group, const float* bias, int ref_dtype, const void* ref, size_t ldr,
-                                  double* sse, void* stream) {
+                                  const double* row_weight, double* sse, void* stream) {
     if (m == 0 || n == 0) return FPQ_OK;
     if ((ref_dtype != FPQ_F16 && ref_dtype != FPQ_F32) || !sse) return FPQ_ERR_ARG;
     GemmArgs g;
     if (int rc = gemm_common(g, a_codes, a_scales, m, b_codes, b_scales, n, k, scale_group, bias, const_cast<void*>(ref), ldr)) return rc;
     g.sse = sse;
+    g.row_weight = row_weight;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     return ref_dtype == FPQ_F16 ? launch_gemm_tn<OUT_SSE_F16>(g, st) : launch_gemm_tn<OUT_SSE_F32>(g, st);
 }

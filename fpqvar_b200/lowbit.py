@@ -125,10 +125,10 @@ def linear_codes(a: PackedCodes, w: PackedCodes, bias: Optional[torch.Tensor] = 
 
 
 def linear_codes_sse(a: PackedCodes, w: PackedCodes, ref: torch.Tensor, bias: Optional[torch.Tensor] = None,
-                     sse: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """sum((ref - F.linear(a, w, bias))^2) without materialising the product: the output-level loss of the format search
-    (search/search_fp4_format.py:472-476, :798-816).  ref: [a.rows, w.rows] float16 / float32, contiguous; returns (and
-    accumulates into) a one-element float64 tensor."""
+                     sse: Optional[torch.Tensor] = None, row_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """sum_i row_weight[i] * sum_j (ref - F.linear(a, w, bias))[i, j]^2 without materialising the product: the output-level loss
+    of the format search (search/search_fp4_format.py:472-476, :798-816).  ref: [a.rows, w.rows] float16 / float32, contiguous;
+    row_weight: float64 [a.rows] or None (= 1); returns (and accumulates into) a one-element float64 tensor."""
     _require_cuda(ref, "linear_codes_sse(ref)")
     m, n = a.rows, w.rows
     if a.k != w.k or (a.scale_group == GROUP) != (w.scale_group == GROUP):
@@ -140,10 +140,14 @@ def linear_codes_sse(a: PackedCodes, w: PackedCodes, ref: torch.Tensor, bias: Op
     elif sse.dtype != torch.float64 or not sse.is_cuda or sse.numel() < 1:
         raise L.FpqError("linear_codes_sse: sse must be a float64 CUDA tensor")
     b = None if bias is None else bias.detach().to(torch.float32).contiguous()
+    if row_weight is not None and (row_weight.dtype != torch.float64 or not row_weight.is_cuda or row_weight.numel() != m
+                                   or not row_weight.is_contiguous()):
+        raise L.FpqError("linear_codes_sse: row_weight must be a contiguous float64 CUDA tensor with one entry per row")
     with _on_device(a.codes) as dev:
         L.check(L.lib().fpq_gemm_codes_sse(a.codes.data_ptr(), a.scales.data_ptr(), m, w.codes.data_ptr(), w.scales.data_ptr(), n, a.k,
                                            a.scale_group, None if b is None else b.data_ptr(), _DT[ref.dtype], ref.data_ptr(), n,
-                                           sse.data_ptr(), _stream(dev)), "fpq_gemm_codes_sse")
+                                           None if row_weight is None else row_weight.data_ptr(), sse.data_ptr(), _stream(dev)),
+                "fpq_gemm_codes_sse")
     return sse
 
 

@@ -137,6 +137,37 @@ def search_layer_batched(weight: torch.Tensor, activations: Sequence[torch.Tenso
     return loss
 
 
+def search_layer_lowbit(weight: torch.Tensor, activations: Sequence[torch.Tensor], weight_formats: Sequence[str] = FP4_FORMATS,
+                        act_formats: Sequence[str] = FP4_FORMATS, per: str = "group", max_rows: int = 65536) -> torch.Tensor:
+    """The loss table of `search_layer_batched` with the quantized layer evaluated from codes on the tensor cores and compared
+    with y_fp inside the GEMM's epilogue (lowbit.linear_codes_sse: SURVEY.md section 8 f3): every candidate pair costs one
+    low-bit GEMM that writes nothing, every activation format one quantizer pass, every weight format one; the only library
+    GEMM left is y_fp.  Symmetric formats only.  Rounding is the kernel tie rule of the evaluation path
+    (fp_quant_*_per_group_cuda) where the search scripts' FPQuant uses torch.argmin (search_fp4_format.py:340-363): the two
+    differ on exact midpoints only.  The products are exact where the reference's fp16 / fp32 GEMMs round; measured agreement
+    of the loss tables: tests/test_gpu_gemm_codes.py."""
+    from . import lowbit
+    if not activations:
+        return torch.zeros(len(weight_formats), len(act_formats), dtype=torch.float64, device=weight.device)
+    per_row = per != "group"
+    c_in = weight.shape[1]
+    flat = [x.reshape(-1, c_in) for x in activations]
+    rows = torch.tensor([f.shape[0] for f in flat], device=weight.device)
+    X = torch.cat(flat)
+    row_w = torch.repeat_interleave(1.0 / (rows.double() * weight.shape[0] * len(flat)), rows)
+    wq = [lowbit.pack_codes(weight, wf, per_row) for wf in weight_formats]
+    loss = torch.zeros(len(weight_formats), len(act_formats), dtype=torch.float64, device=weight.device)
+    for r0 in range(0, X.shape[0], max_rows):
+        xs = X[r0:r0 + max_rows].contiguous()
+        ws = row_w[r0:r0 + max_rows].contiguous()
+        y_fp = torch.matmul(xs, weight.T.to(xs.dtype)).contiguous()
+        for ai, af in enumerate(act_formats):
+            a = lowbit.pack_codes(xs, af, per_row)
+            for wi in range(len(weight_formats)):
+                lowbit.linear_codes_sse(a, wq[wi], y_fp, None, loss[wi, ai:ai + 1], ws)
+    return loss
+
+
 def best_formats(loss: torch.Tensor, weight_formats: Sequence[str], act_formats: Sequence[str]) -> Dict[str, object]:
     """argmin in the reference's iteration order (weight format outer, activation format inner; the first
     strictly smaller loss wins, search_fp4_format.py:818-821)."""

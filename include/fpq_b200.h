@@ -303,12 +303,14 @@ FPQ_API int fpq_gemm_codes(const uint8_t *a_codes, const float *a_scales, size_t
 /*
  * Output-level loss of the format search without materialising the quantized layer's output (SURVEY.md section 8 f3;
  * search/search_fp4_format.py:472-476, :798-816: compute_quant_error(y_fp, F.linear(x_q, W_q))):
- *   *sse += sum_{i<m, j<n} (ref[i, j] - C[i, j])^2,   C as fpq_gemm_codes computes it in fp32 (never stored)
- * ref: [m, ldr] row-major, FPQ_F16 | FPQ_F32, the full-precision layer output; sse: one float64 accumulator the caller zeroes.
+ *   *sse += sum_{i<m} row_weight[i] * sum_{j<n} (ref[i, j] - C[i, j])^2,   C as fpq_gemm_codes computes it in fp32 (never stored)
+ * ref: [m, ldr] row-major, FPQ_F16 | FPQ_F32, the full-precision layer output; row_weight: float64 [m] or NULL (= 1): with the
+ * calibration tensors stacked into one matrix, 1 / (rows_of_its_tensor * n * tensors) turns the sum into the reference's mean of
+ * per-tensor means; sse: one float64 accumulator the caller zeroes.
  */
 FPQ_API int fpq_gemm_codes_sse(const uint8_t *a_codes, const float *a_scales, size_t m, const uint8_t *b_codes,
                    const float *b_scales, size_t n, size_t k, size_t scale_group, const float *bias, int ref_dtype,
-                   const void *ref, size_t ldr, double *sse, void *stream);
+                   const void *ref, size_t ldr, const double *row_weight, double *sse, void *stream);
 
 #ifdef __cplusplus
 }

@@ -169,9 +169,13 @@ def test_fused_output_level_loss(ref_dtype, per_row):
         L.set_tunable("gemm_tile_n", tile_n)
         try:
             got = lowbit.linear_codes_sse(a, ww, ref, bias).item()
+            rw = torch.rand(m, device=dev(), dtype=torch.float64)
+            got_w = lowbit.linear_codes_sse(a, ww, ref, bias, None, rw).item()
         finally:
             L.set_tunable("gemm_tile_n", 256)
-        assert abs(got - want) <= 2e-6 * want          # fp32 squares of 8 columns, then float64
+        assert abs(got - want) <= 2e-6 * want          # fp32 squares along a row piece, then float64
+        want_w = (((ref.double() - y.double()) ** 2).sum(1) * rw).sum().item()
+        assert abs(got_w - want_w) <= 2e-6 * want_w
 
 
 @pytest.mark.parametrize("fmt_a,fmt_w", [("e1m2", "e3m0"), ("e2m3", "e2m3"), ("e3m2", "e2m1"), ("e3m2", "e3m2")])
@@ -223,6 +227,27 @@ def test_gemm_codes_full_size_properties():
     ref = torch.nn.functional.linear(ops.fake_quant(x, "e2m1", 128, "kernel"), ops.fake_quant(w, "e2m1", 128, "kernel").half())
     err = (y - ref.float()).abs().max().item()
     assert err <= 2.0 ** -8 * ref.float().abs().max().item()
+
+
+@pytest.mark.parametrize("per", ["group", "row"])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float16])
+def test_search_loss_table_from_codes(per, dtype):
+    """search.search_layer_lowbit (low-bit GEMM + fused loss) against search.search_layer_batched (fake-quant + library GEMMs +
+    fpq_sse_rows), the path pinned to the reference's loop by tests/test_reference_search.py.  Calibration tensors of unequal
+    row counts, as the reference's [2, pn^2, C] stages.  Stated tolerance: 2e-3 relative per entry (fp16 library GEMM output
+    rounding on one side, none on the other), same winner."""
+    from fpqvar_b200 import search
+    torch.manual_seed(5)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    c_in, c_out = 640, 384
+    w = (torch.randn(c_out, c_in, device=dev()) * 0.04).to(dtype)
+    acts = [torch.randn(2, pn * pn, c_in, device=dev()).to(dtype) for pn in (1, 2, 3, 4, 5, 6, 8, 10, 13)]
+    fmts = ["e2m1", "e1m2", "e3m0"]
+    want = search.search_layer_batched(w, acts, fmts, fmts, per if per == "group" else "token")
+    got = search.search_layer_lowbit(w, acts, fmts, fmts, per if per == "group" else "token")
+    assert torch.allclose(got, want, rtol=2e-3, atol=0)
+    assert search.best_formats(got, fmts, fmts)["weight_format"] == search.best_formats(want, fmts, fmts)["weight_format"]
+    assert search.best_formats(got, fmts, fmts)["activation_format"] == search.best_formats(want, fmts, fmts)["activation_format"]
 
 
 def test_gemm_codes_argument_errors():
