@@ -28,6 +28,7 @@
 #include "fpq_common.cuh"
 #include "fpq_stream.cuh"
 #include <cuda_fp8.h>
+#include <type_traits>
 
 namespace fpq {
 
@@ -41,7 +42,7 @@ constexpr uint32_t A_BYTES = TM * GK, SA_BYTES = TM * 4;
 // ---------------------------------------------------------------------------------------------------------------------
 // quantizer -> codes.  One warp per (8 rows x 128 K) block: lane = (row & 7) + 8 * (chunk & 3), two chunks of 16 elements per
 // lane, so that a warp reads 8 x 128 contiguous bytes (fp16) per instruction pair and writes 512 contiguous bytes per store.
-// Arithmetic: the reference's own sequence (qu.py:313-330 and Appendix A of SURVEY.md), with true divisions.
+// Arithmetic: the reference's own sequence (qu.py:313-330 and Appendix A of SURVEY.md); see grid_values16.
 // ---------------------------------------------------------------------------------------------------------------------
 template <typename T> struct Chunk16;
 template <> struct Chunk16<__half> {
@@ -74,6 +75,30 @@ __device__ __forceinline__ uint32_t e4m3x4(float a, float b, float c, float d) {
     const uint32_t lo = __nv_cvt_float2_to_fp8x2(make_float2(a, b), __NV_SATFINITE, __NV_E4M3);
     const uint32_t hi = __nv_cvt_float2_to_fp8x2(make_float2(c, d), __NV_SATFINITE, __NV_E4M3);
     return lo | (hi << 16);
+}
+
+// Grid values of 16 elements that share the scale s.  fp16 tensors with a regular scale (normal, finite: everything but zero,
+// tiny, inf and NaN groups) take the division-free element function of the packed fp16 quantizers (fpq_h16.cuh: half(x * RN(1/s))
+// == half(x / s), tie shift 2^-17, magic-number rounding; checked against the literal sequence for every (x, scale) pair by
+// fpq_selftest_f16_flow) -- the grid value is that function's intermediate; everything else takes the literal sequence.
+template <typename T, class HG>
+__device__ __forceinline__ void grid_values16(const float (&v)[16], float s, float delta, float (&q)[16]) {
+    if constexpr (std::is_same<T, __half>::value) {
+        if (scale_bits_regular(uint32_t(__half_as_ushort(__float2half_rn(s))))) {
+            const float r = rcp_rn_normal(s);
+            const uint64_t r2 = pk(r, r);
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+                const uint32_t v2 = pack_h2_u64(fmul2(pk(v[i], v[i + 1]), r2));                      // half(x/s)
+                const F2 f = unpk(round_pair_magic(fhadd(uint16_t(v2 & 0xffffu), delta), fhadd(uint16_t(v2 >> 16), delta), Magic<HG>::EM, Magic<HG>::SC));
+                q[i] = f.lo;
+                q[i + 1] = f.hi;
+            }
+            return;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) q[i] = round_any_sym<HG, TIE_KERNEL>(Chunk16<T>::norm(v[i], s));
 }
 
 template <typename T, class HG>
@@ -113,11 +138,11 @@ __global__ void __launch_bounds__(256) pack_codes_kernel(const T* __restrict__ x
         if ((nanmask >> r) & 1u) amax = __int_as_float(0x7fc00000);          // torch's max propagates NaN
         const float s = Chunk16<T>::scale(amax, HG::VMAX);
         uint8_t* blk = codes + (slab * row_blocks + rb) * BLK_BYTES;
+        const float delta = tie_delta_kernel(uint32_t(uint64_t(task) >> 40));
 #pragma unroll
         for (int j = 0; j < 2; ++j) {
             float q[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) q[i] = round_any_sym<HG, TIE_KERNEL>(Chunk16<T>::norm(v[j][i], s));
+            grid_values16<T, HG>(v[j], s, delta, q);
             uint4 o;
             o.x = e4m3x4(q[0], q[1], q[2], q[3]);
             o.y = e4m3x4(q[4], q[5], q[6], q[7]);
@@ -162,6 +187,7 @@ __global__ void __launch_bounds__(256) pack_codes_row_kernel(const T* __restrict
         nanmask |= nanmask >> 8;
         if ((nanmask >> r) & 1u) amax = __int_as_float(0x7fc00000);
         const float s = Chunk16<T>::scale(amax, HG::VMAX);
+        const float delta = tie_delta_kernel(uint32_t(uint64_t(rb) >> 40));
         for (size_t c = kq; c < slabs * 8; c += 4) {
             float v[16], q[16];
             if (live) Chunk16<T>::load(x + row * k + c * 16, v);
@@ -169,8 +195,7 @@ __global__ void __launch_bounds__(256) pack_codes_row_kernel(const T* __restrict
 #pragma unroll
                 for (int i = 0; i < 16; ++i) v[i] = 0.0f;
             }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) q[i] = round_any_sym<HG, TIE_KERNEL>(Chunk16<T>::norm(v[i], s));
+            grid_values16<T, HG>(v, s, delta, q);
             uint4 o;
             o.x = e4m3x4(q[0], q[1], q[2], q[3]);
             o.y = e4m3x4(q[4], q[5], q[6], q[7]);
