@@ -342,13 +342,20 @@ struct GemmCfg {
     // launch bound and spills more; removed)
     static constexpr uint32_t B_BYTES = TN * GK;
     static constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;    // 32 KB | 48 KB
-    static constexpr int MAX_STAGES = TN == 128 ? 6 : 4;
+    // fp16 output: the C tile leaves through a per-warp shared-memory staging buffer (32 rows x 64 columns, rows padded to 144 bytes)
+    // so that a warp store covers whole 128-byte lines; from the fragment layout a store instruction touches 8 lines for 128 bytes
+    // and the tile's stores alone occupy the load/store pipe for ~4000 clk (profiles/r2_gemm_codes.txt)
+    static constexpr bool STAGED_STORE = EPI_WARPS <= 8 && EC >= 64;
+    static constexpr uint32_t ST_ROW = 144, ST_WARP = 32 * ST_ROW;
+    static constexpr uint32_t ST_BYTES = STAGED_STORE ? EPI_WARPS * ST_WARP : 0;
+    static constexpr int MAX_STAGES_FIT = int((227u * 1024u - 2048u - 8u * (SA_BYTES + TN * 4) - ST_BYTES) / (A_BYTES + TN * GK));
+    static constexpr int MAX_STAGES = MAX_STAGES_FIT < 6 ? MAX_STAGES_FIT : 6;
     static constexpr uint32_t SC_BYTES = SA_BYTES + TN * 4;       // one scale pair set: sa[128], sw[TN]
     static constexpr int SC_DEPTH = 8;                            // >= stages + 2: the producer never waits on the scale ring first
     static constexpr int ACC = 512 / TN;                          // accumulators in tensor memory: 4 x 128 or 2 x 256 columns
     static constexpr uint32_t TMEM_COLS = 512;
     static constexpr uint32_t IDESC = (1u << 4) | (uint32_t(TN >> 3) << 17) | (uint32_t(TM >> 4) << 24);
-    static constexpr size_t smem_bytes(int stages) { return size_t(stages) * STAGE_BYTES + SC_DEPTH * SC_BYTES + 1024; }
+    static constexpr size_t smem_bytes(int stages) { return size_t(stages) * STAGE_BYTES + SC_DEPTH * SC_BYTES + ST_BYTES + 1024; }
 };
 
 // Persistent: CTA b works on tiles b, b + gridDim.x, ...; tile t = (t / tiles_n, t % tiles_n), so that the CTAs running at the same
@@ -358,7 +365,7 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
     using Cfg = GemmCfg<TN_, EC_>;
     constexpr int TN = Cfg::TN, EC = Cfg::EC;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_full[Cfg::MAX_STAGES], bar_empty[Cfg::MAX_STAGES], bar_tfull[Cfg::ACC], bar_tempty[Cfg::ACC];
+    __shared__ uint64_t bar_full[6], bar_empty[6], bar_tfull[Cfg::ACC], bar_tempty[Cfg::ACC];
     __shared__ uint64_t bar_sfull[Cfg::SC_DEPTH], bar_sempty[Cfg::SC_DEPTH];
     __shared__ uint32_t tmem_base_slot;
 
@@ -505,6 +512,34 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
             }
             const size_t row0 = size_t(tile / g.tiles_n) * TM + quarter * 32 + tr, col0 = size_t(tile % g.tiles_n) * TN + col_off + 2 * tq;
             float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};          // SSE modes: squared error of this thread's piece of each of its rows
+            if constexpr (OUT == OUT_F16 && Cfg::STAGED_STORE) {
+                uint8_t* stg = sc0 + Cfg::SC_DEPTH * Cfg::SC_BYTES + size_t(warp - 4) * Cfg::ST_WARP;
+                const size_t trow0 = size_t(tile / g.tiles_n) * TM + quarter * 32, tcol0 = size_t(tile % g.tiles_n) * TN + col_off;
+#pragma unroll
+                for (int ch = 0; ch < EC / 64; ++ch) {
+#pragma unroll
+                    for (int bi = 0; bi < 8; ++bi) {
+                        const int bl = ch * 8 + bi;
+                        uint64_t bias2 = 0ull;
+                        if (g.bias && tcol0 + 8 * bl < g.n) { const float2 bb = __ldg(reinterpret_cast<const float2*>(g.bias + tcol0 + 8 * bl + 2 * tq)); bias2 = pk(bb.x, bb.y); }
+#pragma unroll
+                        for (int rr = 0; rr < 4; ++rr) {
+                            const F2 o = unpk(g.bias ? fadd2(acc[rr * NB + bl], bias2) : acc[rr * NB + bl]);
+                            *reinterpret_cast<uint32_t*>(stg + (tr + 8 * rr) * Cfg::ST_ROW + bi * 16 + tq * 4) = pack_h2(o.lo, o.hi);
+                        }
+                    }
+                    __syncwarp();
+                    const size_t col = tcol0 + ch * 64 + (lane & 7) * 8;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int rl = it * 4 + (lane >> 3);
+                        const uint4 u = *reinterpret_cast<const uint4*>(stg + rl * Cfg::ST_ROW + (lane & 7) * 16);
+                        if (trow0 + rl < g.m && col < g.n) *reinterpret_cast<uint4*>(static_cast<__half*>(g.c) + (trow0 + rl) * g.ldc + col) = u;
+                    }
+                    __syncwarp();
+                }
+                continue;
+            }
 #pragma unroll
             for (int bl = 0; bl < NB; ++bl) {
                 const size_t col = col0 + 8 * bl;
