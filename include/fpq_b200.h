@@ -292,10 +292,10 @@ FPQ_API int fpq_nibbles_to_codes(const uint8_t *nibbles, size_t n_codes, int for
  *                                                                              FP4 formats and for 128-groups of the FP6 ones)
  * c: [m, ldc] row-major, FPQ_F16 | FPQ_F32, 16-byte aligned, n % 8 == 0, ldc % 8 == 0; bias: fp32 [n] or NULL.
  * Persistent kernel, one CTA per SM, 128 x 256 (or 128 x 128) tiles of C, ~205 KB of shared memory.  With groups of 128 every
- * accumulator is handed to the epilogue warps once per 128 K (1.1-1.4 PFLOP/s on a B200); with row scales once per tile
+ * accumulator is handed to the epilogue warps once per 128 K (1.0-1.45 PFLOP/s on a B200); with row scales once per tile
  * (2.0-2.5 PFLOP/s; the fp16 library GEMM on the fake-quantized tensors runs at 1.4-1.5).
  * Tunables: "gemm_tile_n" (128 | 256, default 256), "gemm_epi_cols" (columns per epilogue warp: 32 | 64 | 128, default 128),
- * "gemm_stages" (2..6, default 6; at most 4 with 256-column tiles).  Results never depend on them.
+ * "gemm_stages" (2..6, default 6; as many as fit: 3 with 256-column tiles and the fp16 staging buffer).  Results never depend on them.
  */
 FPQ_API int fpq_gemm_codes(const uint8_t *a_codes, const float *a_scales, size_t m, const uint8_t *b_codes,
                    const float *b_scales, size_t n, size_t k, size_t scale_group, const float *bias, int out_dtype,
