@@ -300,16 +300,13 @@ __device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr, uint32_t lbo, 
 }
 // instruction descriptor (GemmCfg::IDESC): D fp32 (bits 4-5 = 1), A / B e4m3 (format 0), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
 
-// 16 lanes x 32 consecutive fp32 columns in the layout of the classic 16 x 8 accumulator fragment, four 8-column blocks i:
+// 16 lanes x 16 consecutive fp32 columns in the layout of the classic 16 x 8 accumulator fragment, two 8-column blocks i:
 // thread t gets v[4i], v[4i+1] = (lane t/4, columns 8i + 2(t%4), +1) and v[4i+2], v[4i+3] = (lane t/4 + 8, same columns)
 // (profiles/r2_tmem_layout.txt: the mapping as measured)
-__device__ __forceinline__ void tc_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-          "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-        : "r"(taddr));
+__device__ __forceinline__ void tc_ld_16x256b_x2(uint32_t taddr, uint32_t (&v)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];\n"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+                 : "r"(taddr));
 }
 
 enum : int { OUT_F16 = 0, OUT_F32 = 1, OUT_SSE_F16 = 2, OUT_SSE_F32 = 3 };
@@ -484,28 +481,35 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
                 mbar_wait(&bar_tfull[a], (gi / Cfg::ACC) & 1);
                 tc_fence_after();
                 const uint32_t t0 = tmem_base + (uint32_t(quarter * 32) << 16) + a * TN + col_off;
+                // 16 columns (two blocks, both 16-lane halves) at a time, the next piece's loads in flight under this piece's arithmetic
+                uint32_t v[2][2][8];
+                tc_ld_16x256b_x2(t0, v[0][0]);
+                tc_ld_16x256b_x2(t0 + (16u << 16), v[0][1]);
+                tc_wait_ld();
 #pragma unroll
-                for (int cb = 0; cb < EC / 32; ++cb) {         // 32 columns: four blocks, both 16-lane halves
-                    uint32_t v[2][16];
-                    tc_ld_16x256b_x4(t0 + cb * 32, v[0]);
-                    tc_ld_16x256b_x4(t0 + (16u << 16) + cb * 32, v[1]);
-                    tc_wait_ld();
-                    if (cb == EC / 32 - 1) {
-                        // every column of this accumulator has been read: hand it back before the arithmetic
+                for (int c = 0; c < EC / 16; ++c) {
+                    constexpr int LAST = EC / 16 - 1;
+                    if (c < LAST) {
+                        tc_ld_16x256b_x2(t0 + (c + 1) * 16, v[(c + 1) & 1][0]);
+                        tc_ld_16x256b_x2(t0 + (16u << 16) + (c + 1) * 16, v[(c + 1) & 1][1]);
+                    } else {
+                        // every column of this accumulator is in registers: hand it back before the arithmetic
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive(&bar_tempty[a]);
                     }
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const int bl = cb * 4 + i;
+                    for (int i = 0; i < 2; ++i) {
+                        const int bl = c * 2 + i;
                         const uint64_t w = swp[4 * bl];
 #pragma unroll
                         for (int h = 0; h < 2; ++h) {
-                            acc[(2 * h) * NB + bl] = ffma2(fmul2(pk(__uint_as_float(v[h][4 * i]), __uint_as_float(v[h][4 * i + 1])), sa2[2 * h]), w, acc[(2 * h) * NB + bl]);
-                            acc[(2 * h + 1) * NB + bl] = ffma2(fmul2(pk(__uint_as_float(v[h][4 * i + 2]), __uint_as_float(v[h][4 * i + 3])), sa2[2 * h + 1]), w, acc[(2 * h + 1) * NB + bl]);
+                            const uint32_t* vv = v[c & 1][h];
+                            acc[(2 * h) * NB + bl] = ffma2(fmul2(pk(__uint_as_float(vv[4 * i]), __uint_as_float(vv[4 * i + 1])), sa2[2 * h]), w, acc[(2 * h) * NB + bl]);
+                            acc[(2 * h + 1) * NB + bl] = ffma2(fmul2(pk(__uint_as_float(vv[4 * i + 2]), __uint_as_float(vv[4 * i + 3])), sa2[2 * h + 1]), w, acc[(2 * h + 1) * NB + bl]);
                         }
                     }
+                    if (c < LAST) tc_wait_ld();
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_sempty[q]);
