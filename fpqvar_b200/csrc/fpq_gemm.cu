@@ -13,18 +13,20 @@
 // GEMM: C[m, n] = sum over slabs t of  sa[t, m] * sw[t, n] * P_t[m, n],   P_t = sum over the slab's 128 k of qa * qw,
 // P_t by tcgen05.mma kind::f8f6f4 (e4m3 x e4m3, fp32 accumulate in tensor memory; exact: every product is a multiple of 2^-8
 // and the sums stay far below 2^24 of them), the scale product by the epilogue warps on the CUDA cores while the tensor core
-// works on the next slabs (512 columns of tensor memory: four 128-column or two 256-column accumulators).  The fp32 operation order is fixed -- acc = fma(P*sa, sw, acc),
-// slabs ascending -- so that oracle/gemm_codes.c reproduces C bit for bit.
+// works on the next slabs (512 columns of tensor memory: four 128-column or two 256-column accumulators).  The fp32 operation
+// order is fixed -- acc = fma(P*sa, sw, acc), slabs ascending -- so that oracle/gemm_codes.c reproduces C bit for bit.
 //
 // Persistent kernel, one CTA per SM, 128 x 256 (or 128 x 128) tiles of C: warp 0 = bulk-copy producer, warp 1 = MMA issuer (one
-// lane), warps 2.. = epilogue (each owns 32 tensor-memory lanes -- its warp-id quarter -- and 128 columns).  Ring of shared-memory
-// stages {A tile, B tile} and a ring of scale sets {sa, sw}, full / empty mbarriers; tcgen05.commit hands a stage back and
-// publishes an accumulator; the epilogue hands the accumulator back as soon as it is in registers.  With one scale per row
-// (per_token x per_channel) the whole K accumulates in tensor memory and the epilogue runs once per tile.
-// Measured (B200, profiles/r2_gemm_codes.txt): row scales 2.0-2.5 PFLOP/s, at the ~6.3 KB/clk L2 -> SM cap with 128 x 256 tiles; groups of
-// 128: 1.1-1.4 PFLOP/s.  What the per-slab hand-over costs is NOT the epilogue's work: with its tensor-memory loads, scale loads
-// and arithmetic all compiled out the kernel still runs at 1.2-1.7 PFLOP/s (tensor-memory loads alone reach ~1 KB/clk per SM,
-// tools/tmem_ldbench.cu).  Switching the accumulator every four MMAs and committing it every slab is what the tensor pipe pays for.
+// lane), warps 4.. = epilogue (each owns 32 tensor-memory lanes -- its warp-id quarter -- and EC columns, read as 16 x 8
+// fragments).  Ring of shared-memory stages {A tile, B tile} and a ring of scale sets {sa, sw}, full / empty mbarriers;
+// tcgen05.commit hands a stage back and publishes an accumulator; the epilogue hands the accumulator back as soon as it is in
+// registers.  With one scale per row (per_token x per_channel) the whole K accumulates in tensor memory and the epilogue runs
+// once per tile.  fp16 C tiles leave through a per-warp staging buffer in shared memory (whole-line stores).
+// Measured (B200, profiles/r2_gemm_codes.txt; the fp16 library GEMM on the fake-quantized tensors: 1.44-1.48 PFLOP/s):
+//   row scales 2.1-2.55 PFLOP/s, at the ~6.3 KB/clk L2 -> SM cap with 128 x 256 tiles (next: CTA pairs / multicast);
+//   groups of 128 1.04-1.49 PFLOP/s: the epilogue's 2 flops per element (512 clk of the fp32 pipe per 128 x 256 slab, as long as
+//   the slab's MMAs) and its tensor-memory loads do not fully overlap with a memory-bound main loop; DESIGN.md 3.6 has the
+//   experiments (tcgen05.ld alone: ~1 KB/clk per SM, tools/tmem_ldbench.cu; epilogue compiled out; per-tile overhead).
 #include "fpq_common.cuh"
 #include "fpq_stream.cuh"
 #include <cuda_fp8.h>
