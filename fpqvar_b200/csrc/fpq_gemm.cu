@@ -23,7 +23,8 @@
 // registers.  With one scale per row (per_token x per_channel) the whole K accumulates in tensor memory and the epilogue runs
 // once per tile.  fp16 C tiles leave through a per-warp staging buffer in shared memory (whole-line stores).
 // Measured (B200, profiles/r2_gemm_codes.txt; the fp16 library GEMM on the fake-quantized tensors: 1.44-1.48 PFLOP/s):
-//   row scales 2.1-2.55 PFLOP/s, at the ~6.3 KB/clk L2 -> SM cap with 128 x 256 tiles (next: CTA pairs / multicast);
+//   row scales 2.1-2.55 PFLOP/s: the SM's shared-memory pipe (48 KB in + 48 KB out per 128 x 256 slab at 128 B/clk = 768 clk; CTA
+//   pairs sharing B by multicast -- PAIR below -- are no faster; next: cta_group::2 MMAs);
 //   groups of 128 1.04-1.49 PFLOP/s: the epilogue's 2 flops per element (512 clk of the fp32 pipe per 128 x 256 slab, as long as
 //   the slab's MMAs) and its tensor-memory loads do not fully overlap with a memory-bound main loop; DESIGN.md 3.6 has the
 //   experiments (tcgen05.ld alone: ~1 KB/clk per SM, tools/tmem_ldbench.cu; epilogue compiled out; per-tile overhead).
@@ -282,6 +283,26 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// the same, arriving on the barrier at this offset in every CTA of `mask` (CTA pairs: a stage is free when BOTH CTAs have read it)
+__device__ __forceinline__ void tc_commit_multicast(uint64_t* bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+// 1-D bulk copy global -> the same shared-memory offset in every CTA of `mask`, byte count on each CTA's barrier at this offset
+__device__ __forceinline__ void bulk_load_multicast(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_cta_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
 // D[tmem] (+)= A[smem] * B[smem]^T, 128 x 128 x 32, e4m3 operands, fp32 accumulate
 __device__ __forceinline__ void tc_mma_f8(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -359,10 +380,19 @@ struct GemmCfg {
 
 // Persistent: CTA b works on tiles b, b + gridDim.x, ...; tile t = (t / tiles_n, t % tiles_n), so that the CTAs running at the same
 // time share A panels and the whole of B through L2.  Warp 0 = producer, warp 1 = MMA issuer, warps 4.. = epilogue.
-template <int TN_, int EC_, int OUT>
+// PAIR: launched as clusters of two CTAs that work on two row tiles of the same tile column (tm = 2 p + rank): each CTA copies its own
+// A tile and HALF of the shared B tile, multicast into both CTAs' stage -- a third less L2 -> SM traffic per slab.  Measured: no
+// faster (the shared-memory pipe of each SM still takes the whole tile in and out); off by default.  A stage is refilled once both CTAs' MMAs have released it (multicast commit, barrier count 2).
+template <int TN_, int EC_, int OUT, bool PAIR = false>
 __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kernel(const GemmArgs g) {
     using Cfg = GemmCfg<TN_, EC_>;
     constexpr int TN = Cfg::TN, EC = Cfg::EC;
+    const uint32_t pair_rank = PAIR ? cluster_cta_rank() : 0u;
+    // work items of this CTA: tiles (or tile pairs) first, first + step, ...; item w -> tile column w % tiles_n, tile row w / tiles_n
+    // (x 2 + rank for pairs; a pair's second row tile may lie past the end: its loads are clamped, its stores masked by row < m)
+    const uint32_t w_first = PAIR ? blockIdx.x / 2 : blockIdx.x, w_step = PAIR ? gridDim.x / 2 : gridDim.x;
+    const uint32_t tiles_m = uint32_t(g.m_pad / TM);
+    const uint32_t w_count = PAIR ? ((tiles_m + 1) / 2) * g.tiles_n : g.n_tiles;
     extern __shared__ uint8_t smem_raw[];
     __shared__ uint64_t bar_full[6], bar_empty[6], bar_tfull[Cfg::ACC], bar_tempty[Cfg::ACC];
     __shared__ uint64_t bar_sfull[Cfg::SC_DEPTH], bar_sempty[Cfg::SC_DEPTH];
@@ -377,7 +407,7 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < stages; ++s) {
             mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_empty[s], 1);               // the MMA's commit
+            mbar_init(&bar_empty[s], PAIR ? 2 : 1);    // the MMA's commit (of both CTAs of a pair)
         }
         for (int a = 0; a < Cfg::ACC; ++a) {
             mbar_init(&bar_tfull[a], 1);
@@ -396,6 +426,7 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();            // the peer's barriers are initialised before anything is sent to them
     tc_fence_after();
     const uint32_t tmem_base = tmem_base_slot;
 
@@ -404,8 +435,9 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
         if (lane == 0) {
             const size_t a_blocks = g.m_pad / 8, b_blocks = g.n_pad / 8;
             uint32_t it = 0, gi = 0;
-            for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
-                const size_t tm = tile / g.tiles_n, tn = tile % g.tiles_n;
+            for (uint32_t w = w_first; w < w_count; w += w_step) {
+                const uint32_t tm_raw = PAIR ? 2 * (w / g.tiles_n) + pair_rank : w / g.tiles_n;
+                const size_t tm = tm_raw < tiles_m ? tm_raw : tiles_m - 1, tn = w % g.tiles_n;
                 const size_t b_left = g.n_pad - tn * TN;
                 const uint32_t b_rows = b_left < size_t(TN) ? uint32_t(b_left) : uint32_t(TN);        // last tile column may be half
                 for (uint32_t i = 0; i < slabs; ++i, ++it) {
@@ -423,7 +455,13 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
                     uint8_t* st = stage0 + size_t(s) * Cfg::STAGE_BYTES;
                     mbar_arrive_expect_tx(&bar_full[s], A_BYTES + b_rows * GK);
                     bulk_load(st, g.a_codes + (size_t(i) * a_blocks + tm * (TM / 8)) * BLK_BYTES, A_BYTES, &bar_full[s]);
-                    bulk_load(st + A_BYTES, g.b_codes + (size_t(i) * b_blocks + tn * (TN / 8)) * BLK_BYTES, b_rows * GK, &bar_full[s]);
+                    if constexpr (PAIR) {
+                        const uint32_t half = b_rows / 2 * GK;             // b_rows is 128 or 256: halves of whole 8-row blocks
+                        bulk_load_multicast(st + A_BYTES + pair_rank * half,
+                                            g.b_codes + (size_t(i) * b_blocks + tn * (TN / 8)) * BLK_BYTES + pair_rank * half, half, &bar_full[s], uint16_t(3));
+                    } else {
+                        bulk_load(st + A_BYTES, g.b_codes + (size_t(i) * b_blocks + tn * (TN / 8)) * BLK_BYTES, b_rows * GK, &bar_full[s]);
+                    }
                 }
             }
         }
@@ -431,7 +469,7 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
     } else if (warp == 1) {
         // ===== MMA issuer: four 128 x TN x 32 MMAs per slab; a scale group accumulates in tensor memory =====
         uint32_t it = 0, gi = 0;
-        for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+        for (uint32_t w = w_first; w < w_count; w += w_step) {
             for (uint32_t i = 0; i < slabs; ++i, ++it) {
                 const uint32_t s = it % stages, n = it / stages, a = gi % Cfg::ACC, u = gi / Cfg::ACC;
                 const bool first = i % gs == 0, last = i % gs == gs - 1;
@@ -444,7 +482,8 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
 #pragma unroll
                     for (uint32_t kk = 0; kk < GK / 32; ++kk)      // 32 K = two core matrices = 256 bytes further on
                         tc_mma_f8(tmem_base + a * TN, da + kk * (256u >> 4), db + kk * (256u >> 4), Cfg::IDESC, (first && kk == 0) ? 0u : 1u);
-                    tc_commit(&bar_empty[s]);
+                    if constexpr (PAIR) tc_commit_multicast(&bar_empty[s], uint16_t(3));
+                    else tc_commit(&bar_empty[s]);
                     if (last) tc_commit(&bar_tfull[a]);
                 }
                 __syncwarp();
@@ -465,7 +504,8 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
         const uint32_t n_groups = slabs / gs;
         uint32_t gi = 0;
         double sse_thread = 0.0;
-        for (uint32_t tile = blockIdx.x; tile < g.n_tiles; tile += gridDim.x) {
+        for (uint32_t w = w_first; w < w_count; w += w_step) {
+            const uint32_t tile_m = PAIR ? 2 * (w / g.tiles_n) + pair_rank : w / g.tiles_n, tile_n = w % g.tiles_n;
             uint64_t acc[4 * NB];                              // [row slot rr][block b]: columns (8 b + 2 tq, + 1) of row tr + 8 rr
 #pragma unroll
             for (int j = 0; j < 4 * NB; ++j) acc[j] = 0ull;
@@ -516,11 +556,11 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&bar_sempty[q]);
             }
-            const size_t row0 = size_t(tile / g.tiles_n) * TM + quarter * 32 + tr, col0 = size_t(tile % g.tiles_n) * TN + col_off + 2 * tq;
+            const size_t row0 = size_t(tile_m) * TM + quarter * 32 + tr, col0 = size_t(tile_n) * TN + col_off + 2 * tq;
             float part[4] = {0.0f, 0.0f, 0.0f, 0.0f};          // SSE modes: squared error of this thread's piece of each of its rows
             if constexpr (OUT == OUT_F16 && Cfg::STAGED_STORE) {
                 uint8_t* stg = sc0 + Cfg::SC_DEPTH * Cfg::SC_BYTES + size_t(warp - 4) * Cfg::ST_WARP;
-                const size_t trow0 = size_t(tile / g.tiles_n) * TM + quarter * 32, tcol0 = size_t(tile % g.tiles_n) * TN + col_off;
+                const size_t trow0 = size_t(tile_m) * TM + quarter * 32, tcol0 = size_t(tile_n) * TN + col_off;
 #pragma unroll
                 for (int ch = 0; ch < EC / 64; ++ch) {
 #pragma unroll
@@ -595,6 +635,7 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
 
     tc_fence_before();
     __syncthreads();
+    if constexpr (PAIR) cluster_sync_all();            // nothing of the peer is in flight towards this CTA's shared memory any more
     if (warp == 0) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
@@ -730,6 +771,46 @@ int launch_gemm(GemmArgs& g, cudaStream_t st) {
     return finish_launch();
 }
 
+// CTA pairs (clusters of two): instantiated for the default tile shape only
+template <int TN_, int EC_, int OUT>
+int launch_gemm_pair(GemmArgs& g, cudaStream_t st) {
+    using Cfg = GemmCfg<TN_, EC_>;
+    if (int(g.stages) > Cfg::MAX_STAGES) g.stages = Cfg::MAX_STAGES;
+    const size_t tiles_n = (g.n_pad + TN_ - 1) / TN_, tiles_m = g.m_pad / TM;
+    const size_t pairs = (tiles_m + 1) / 2 * tiles_n;
+    if (tiles_m * tiles_n > 0x7fffffffull) return FPQ_ERR_UNSUPPORTED;
+    g.n_tiles = uint32_t(tiles_m * tiles_n);
+    g.tiles_n = uint32_t(tiles_n);
+    auto kernel = gemm_codes_kernel<TN_, EC_, OUT, true>;
+    static bool attr_set[64] = {};
+    static int max_clusters[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::smem_bytes(int(g.stages));
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (!attr_set[dev & 63]) {
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::smem_bytes(Cfg::MAX_STAGES))) != cudaSuccess) return finish_launch();
+        cfg.gridDim = dim3(unsigned(sm_count()) / 2 * 2);
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = sm_count() / 2 - 4; }
+        max_clusters[dev & 63] = n;
+        attr_set[dev & 63] = true;
+    }
+    const size_t clusters = pairs < size_t(max_clusters[dev & 63]) ? pairs : size_t(max_clusters[dev & 63]);
+    cfg.gridDim = dim3(unsigned(2 * clusters));
+    cudaLaunchKernelEx(&cfg, kernel, g);
+    return finish_launch();
+}
+
 template <int OUT>
 int launch_gemm_tn(GemmArgs& g, cudaStream_t st) {
     const int ec = g_tun.gemm_epi_cols;
@@ -739,7 +820,8 @@ int launch_gemm_tn(GemmArgs& g, cudaStream_t st) {
         return launch_gemm<128, 128, OUT>(g, st);
     }
     if (ec == 64) return launch_gemm<256, 64, OUT>(g, st);
-    return launch_gemm<256, 128, OUT>(g, st);
+    const bool pair = g_tun.gemm_pair == 1 || (g_tun.gemm_pair < 0 && g.m_pad / TM >= 4);
+    return pair ? launch_gemm_pair<256, 128, OUT>(g, st) : launch_gemm<256, 128, OUT>(g, st);
 }
 
 int gemm_common(GemmArgs& g, const uint8_t* a_codes, const float* a_scales, size_t m, const uint8_t* b_codes, const float* b_scales, size_t n,

@@ -166,6 +166,11 @@ extern "C" int fpq_set_tunable(const char* name, long long value) {
         g_tun.gemm_tile_n = int(value);
         return FPQ_OK;
     }
+    if (strcmp(name, "gemm_pair") == 0) {
+        if (value < -1 || value > 1) return FPQ_ERR_ARG;
+        g_tun.gemm_pair = int(value);
+        return FPQ_OK;
+    }
     if (strcmp(name, "gemm_epi_cols") == 0) {
         if (value != 32 && value != 64 && value != 128) return FPQ_ERR_ARG;
         g_tun.gemm_epi_cols = int(value);

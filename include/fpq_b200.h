@@ -94,7 +94,8 @@ FPQ_API uint64_t fpq_launch_count(void);
  *   "rot_small_max_chunks" rotate launches of up to this many 128-chunks take the small-launch kernel (default 40000)
  *   "smem_kb"              0 (default: the driver chooses per kernel) | 1..228: the shared-memory carveout (KB per SM) every
  *                          activation kernel asks for, and the streaming rotate kernel's shared-memory budget
- *   "gemm_tile_n", "gemm_epi_cols", "gemm_stages"   tile shape, epilogue split and ring depth of fpq_gemm_codes (see there)
+ *   "gemm_tile_n", "gemm_epi_cols", "gemm_stages", "gemm_pair"   tile shape, epilogue split, ring depth and CTA pairing of
+ *                          fpq_gemm_codes (see there)
  * Results never depend on a tunable (tests/test_gpu_shapes.py).  Returns FPQ_ERR_ARG for an unknown name or value.
  */
 FPQ_API int fpq_set_tunable(const char *name, long long value);
@@ -295,7 +296,8 @@ FPQ_API int fpq_nibbles_to_codes(const uint8_t *nibbles, size_t n_codes, int for
  * accumulator is handed to the epilogue warps once per 128 K (1.0-1.45 PFLOP/s on a B200); with row scales once per tile
  * (2.0-2.5 PFLOP/s; the fp16 library GEMM on the fake-quantized tensors runs at 1.4-1.5).
  * Tunables: "gemm_tile_n" (128 | 256, default 256), "gemm_epi_cols" (columns per epilogue warp: 32 | 64 | 128, default 128),
- * "gemm_stages" (2..6, default 6; as many as fit: 3 with 256-column tiles and the fp16 staging buffer).  Results never depend on them.
+ * "gemm_stages" (2..6, default 6; as many as fit: 3 with 256-column tiles and the fp16 staging buffer), "gemm_pair" (1: clusters
+ * of two CTAs share the B tile by multicast; 0 = default, measured no faster; -1: on for >= 4 row tiles).  Results never depend on them.
  */
 FPQ_API int fpq_gemm_codes(const uint8_t *a_codes, const float *a_scales, size_t m, const uint8_t *b_codes,
                    const float *b_scales, size_t n, size_t k, size_t scale_group, const float *bias, int out_dtype,

@@ -84,8 +84,9 @@ def _operands(rng, m, n, k, fmt_a, fmt_w, dtype_a=np.float16):
 
 @pytest.mark.parametrize("m,n,k", [(128, 128, 128), (128, 128, 256), (1, 8, 128), (100, 136, 384), (300, 384, 1920), (257, 128, 7680),
                                    (700, 640, 640)])
-@pytest.mark.parametrize("tile_n,epi_cols,stages", [(256, 64, 4), (256, 128, 2), (128, 32, 6), (128, 64, 2), (128, 128, 3)])
-def test_gemm_codes_bit_exact_against_the_fixed_order_oracle(m, n, k, tile_n, epi_cols, stages):
+@pytest.mark.parametrize("tile_n,epi_cols,stages,pair", [(256, 128, 3, 1), (256, 64, 4, 0), (256, 128, 2, 0), (256, 128, 2, 1), (128, 32, 6, 0),
+                                                         (128, 64, 2, 0), (128, 128, 3, 0)])
+def test_gemm_codes_bit_exact_against_the_fixed_order_oracle(m, n, k, tile_n, epi_cols, stages, pair):
     rng = np.random.default_rng(m + n + k)
     x, w, (qa, sa), (qw, sw) = _operands(rng, m, n, k, "e2m1", "e2m1")
     bias = rng.standard_normal(n).astype(np.float32)
@@ -94,6 +95,7 @@ def test_gemm_codes_bit_exact_against_the_fixed_order_oracle(m, n, k, tile_n, ep
     L.set_tunable("gemm_stages", stages)
     L.set_tunable("gemm_tile_n", tile_n)
     L.set_tunable("gemm_epi_cols", epi_cols)
+    L.set_tunable("gemm_pair", pair)
     try:
         c32 = lowbit.linear_codes(a, ww, torch.from_numpy(bias).to(dev()), torch.float32).cpu().numpy()
         c16 = lowbit.linear_codes(a, ww, None, torch.float16).cpu().numpy()
@@ -101,6 +103,7 @@ def test_gemm_codes_bit_exact_against_the_fixed_order_oracle(m, n, k, tile_n, ep
         L.set_tunable("gemm_stages", 6)
         L.set_tunable("gemm_tile_n", 256)
         L.set_tunable("gemm_epi_cols", 128)
+        L.set_tunable("gemm_pair", 0)
     assert np.array_equal(bits(c32), bits(LB.gemm_codes(qa, sa, qw, sw, bias)))
     assert np.array_equal(bits(c16), bits(LB.gemm_codes(qa, sa, qw, sw).astype(np.float16)))
 
@@ -108,20 +111,24 @@ def test_gemm_codes_bit_exact_against_the_fixed_order_oracle(m, n, k, tile_n, ep
 def test_gemm_codes_many_tiles_per_cta():
     """more tiles than SMs: the persistent loop, the scale ring and both accumulators wrap several times"""
     rng = np.random.default_rng(99)
-    m, n, k = 128 * 21, 256 * 9 + 128, 384
+    m, n, k = 128 * 21 - 5, 256 * 9 + 128, 384          # 21 row tiles: the last CTA pair has a phantom second tile
     x, w, (qa, sa), (qw, sw) = _operands(rng, m, n, k, "e2m1", "e1m2")
     a = lowbit.pack_codes(torch.from_numpy(x).to(dev()), "e2m1")
     ww = lowbit.pack_codes(torch.from_numpy(w).to(dev()), "e1m2")
     want = LB.gemm_codes(qa, sa, qw, sw)
-    for tile_n, epi_cols in ((256, 64), (256, 128), (128, 32), (128, 64), (128, 128)):
+    for tile_n, epi_cols, pair in ((256, 128, 1), (256, 64, 0), (256, 128, 0), (128, 32, 0), (128, 64, 0), (128, 128, 0)):
         L.set_tunable("gemm_tile_n", tile_n)
         L.set_tunable("gemm_epi_cols", epi_cols)
+        L.set_tunable("gemm_pair", pair)
         try:
             c = lowbit.linear_codes(a, ww, None, torch.float32).cpu().numpy()
+            c16 = lowbit.linear_codes(a, ww, None, torch.float16).cpu().numpy()
         finally:
             L.set_tunable("gemm_tile_n", 256)
             L.set_tunable("gemm_epi_cols", 128)
+            L.set_tunable("gemm_pair", 0)
         assert np.array_equal(bits(c), bits(want))
+        assert np.array_equal(bits(c16), bits(want.astype(np.float16)))
 
 
 @pytest.mark.parametrize("fmt_a,fmt_w,dtype", [("e2m1", "e2m1", np.float16), ("e1m2", "e3m0", np.float32), ("e2m3", "e2m3", np.float16),
@@ -165,14 +172,16 @@ def test_fused_output_level_loss(ref_dtype, per_row):
     a, ww = lowbit.pack_codes(x, "e2m1", per_row), lowbit.pack_codes(w, "e2m1", per_row)
     y = lowbit.linear_codes(a, ww, bias, torch.float32)
     want = ((ref.double() - y.double()) ** 2).sum().item()
-    for tile_n in (256, 128):
+    for tile_n, pair in ((256, 1), (256, 0), (128, 0)):
         L.set_tunable("gemm_tile_n", tile_n)
+        L.set_tunable("gemm_pair", pair)
         try:
             got = lowbit.linear_codes_sse(a, ww, ref, bias).item()
             rw = torch.rand(m, device=dev(), dtype=torch.float64)
             got_w = lowbit.linear_codes_sse(a, ww, ref, bias, None, rw).item()
         finally:
             L.set_tunable("gemm_tile_n", 256)
+            L.set_tunable("gemm_pair", 0)
         assert abs(got - want) <= 2e-6 * want          # fp32 squares along a row piece, then float64
         want_w = (((ref.double() - y.double()) ** 2).sum(1) * rw).sum().item()
         assert abs(got_w - want_w) <= 2e-6 * want_w

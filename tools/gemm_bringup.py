@@ -123,15 +123,18 @@ def bench(dev, shapes):
         flop = 2.0 * m * n * k
         res = {}
         ar, wr = lowbit.pack_codes(x, "e2m1", True), lowbit.pack_codes(wt, "e2m1", True)
-        for tn, ec, st in ((256, 64, 4), (256, 128, 4), (128, 32, 6), (128, 64, 6), (128, 128, 6)):
+        for tn, ec, st, pair in ((256, 128, 4, 1), (256, 128, 4, 0), (256, 64, 4, 0), (128, 32, 6, 0), (128, 64, 6, 0), (128, 128, 6, 0)):
             L.set_tunable("gemm_stages", st)
             L.set_tunable("gemm_tile_n", tn)
             L.set_tunable("gemm_epi_cols", ec)
-            res[f"g128 tn{tn} ec{ec}"] = timeit(lambda: lowbit.linear_codes(a, w, None, torch.float16, out))
-            res[f"row tn{tn} ec{ec}"] = timeit(lambda: lowbit.linear_codes(ar, wr, None, torch.float16, out))
+            L.set_tunable("gemm_pair", pair)
+            tag = f"tn{tn} ec{ec}" + (" pair" if pair else "")
+            res[f"g128 {tag}"] = timeit(lambda: lowbit.linear_codes(a, w, None, torch.float16, out))
+            res[f"row {tag}"] = timeit(lambda: lowbit.linear_codes(ar, wr, None, torch.float16, out))
         L.set_tunable("gemm_stages", 6)
         L.set_tunable("gemm_tile_n", 256)
         L.set_tunable("gemm_epi_cols", 128)
+        L.set_tunable("gemm_pair", 0)
         res["sse g128"] = timeit(lambda: lowbit.linear_codes_sse(a, w, out))
         t_packrow = timeit(lambda: lowbit.pack_codes(x, "e2m1", True))
         t_pack = timeit(lambda: lowbit.pack_codes(x, "e2m1"))
@@ -150,7 +153,12 @@ if __name__ == "__main__":
     print(torch.cuda.get_device_name(0))
     t0 = time.time()
     ok = check_pack(dev)
+    L.set_tunable("gemm_pair", 1)
+    print("CTA pairs:")
     ok2 = check_gemm(dev)
+    L.set_tunable("gemm_pair", 0)
+    print("single CTAs:")
+    ok2 = check_gemm(dev) and ok2
     for tn, ec in ((256, 64), (128, 32), (128, 64), (128, 128)):
         L.set_tunable("gemm_tile_n", tn)
         L.set_tunable("gemm_epi_cols", ec)
@@ -158,6 +166,7 @@ if __name__ == "__main__":
         ok2 = check_gemm(dev) and ok2
     L.set_tunable("gemm_tile_n", 256)
     L.set_tunable("gemm_epi_cols", 128)
+    L.set_tunable("gemm_pair", 0)
     print(f"parity ladder took {time.time() - t0:.1f} s")
     if ok2 or "--bench" in sys.argv:
         shapes = [("d30 mat_qkv stage 9", 25600, 5760, 1920), ("d30 fc1 stage 9", 25600, 7680, 1920), ("d30 proj stage 9", 25600, 1920, 1920),
