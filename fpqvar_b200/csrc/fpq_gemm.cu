@@ -24,7 +24,7 @@
 // once per tile.  fp16 C tiles leave through a per-warp staging buffer in shared memory (whole-line stores).
 // Measured (B200, profiles/r2_gemm_codes.txt; the fp16 library GEMM on the fake-quantized tensors: 1.44-1.48 PFLOP/s):
 //   row scales 2.1-2.55 PFLOP/s: the SM's shared-memory pipe (48 KB in + 48 KB out per 128 x 256 slab at 128 B/clk = 768 clk; CTA
-//   pairs sharing B by multicast -- PAIR below -- are no faster; next: cta_group::2 MMAs);
+//   pairs sharing B by multicast were no faster, cta_group::2 MMAs -- PAIR below -- are bit-exact but slower so far);
 //   groups of 128 1.04-1.49 PFLOP/s: the epilogue's 2 flops per element (512 clk of the fp32 pipe per 128 x 256 slab, as long as
 //   the slab's MMAs) and its tensor-memory loads do not fully overlap with a memory-bound main loop; DESIGN.md 3.6 has the
 //   experiments (tcgen05.ld alone: ~1 KB/clk per SM, tools/tmem_ldbench.cu; epilogue compiled out; per-tile overhead).
@@ -283,16 +283,42 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// the same, arriving on the barrier at this offset in every CTA of `mask` (CTA pairs: a stage is free when BOTH CTAs have read it)
-__device__ __forceinline__ void tc_commit_multicast(uint64_t* bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+// cta_group::2: one MMA over a CTA pair, 256 x N x 32: each CTA supplies its 128 rows of A and its half (N/2 rows) of B from its own
+// shared memory (same offsets in both), each CTA's tensor memory receives its 128 rows of D.  Issued by the pair's leader only.
+__device__ __forceinline__ void tc_mma_f8_duo(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_duo(uint64_t* bar) {          // arrives on the barrier at this offset in BOTH CTAs
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(uint16_t(3))
                  : "memory");
 }
-// 1-D bulk copy global -> the same shared-memory offset in every CTA of `mask`, byte count on each CTA's barrier at this offset
-__device__ __forceinline__ void bulk_load_multicast(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint16_t mask) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(smem_u32(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)), "h"(mask)
-                 : "memory");
+// arrive on the barrier at this offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 ra;\n"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(rank)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {      // acquire at cluster scope
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FPQ_WAITC:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra FPQ_DONEC;\n"
+        "bra FPQ_WAITC;\n"
+        "FPQ_DONEC:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -376,13 +402,21 @@ struct GemmCfg {
     static constexpr uint32_t TMEM_COLS = 512;
     static constexpr uint32_t IDESC = (1u << 4) | (uint32_t(TN >> 3) << 17) | (uint32_t(TM >> 4) << 24);
     static constexpr size_t smem_bytes(int stages) { return size_t(stages) * STAGE_BYTES + SC_DEPTH * SC_BYTES + ST_BYTES + 1024; }
+    // CTA pairs: a stage holds the A tile and HALF of the B tile
+    static constexpr uint32_t STAGE_BYTES_PAIR = A_BYTES + B_BYTES / 2;
+    static constexpr int MAX_STAGES_PAIR_FIT = int((227u * 1024u - 2048u - 8u * (SA_BYTES + TN * 4) - ST_BYTES) / STAGE_BYTES_PAIR);
+    static constexpr int MAX_STAGES_PAIR = MAX_STAGES_PAIR_FIT < 6 ? MAX_STAGES_PAIR_FIT : 6;
+    static constexpr size_t smem_bytes_pair(int stages) { return size_t(stages) * STAGE_BYTES_PAIR + SC_DEPTH * SC_BYTES + ST_BYTES + 1024; }
 };
 
 // Persistent: CTA b works on tiles b, b + gridDim.x, ...; tile t = (t / tiles_n, t % tiles_n), so that the CTAs running at the same
 // time share A panels and the whole of B through L2.  Warp 0 = producer, warp 1 = MMA issuer, warps 4.. = epilogue.
-// PAIR: launched as clusters of two CTAs that work on two row tiles of the same tile column (tm = 2 p + rank): each CTA copies its own
-// A tile and HALF of the shared B tile, multicast into both CTAs' stage -- a third less L2 -> SM traffic per slab.  Measured: no
-// faster (the shared-memory pipe of each SM still takes the whole tile in and out); off by default.  A stage is refilled once both CTAs' MMAs have released it (multicast commit, barrier count 2).
+// PAIR: launched as clusters of two CTAs that work on two row tiles of the same tile column (tm = 2 p + rank) with cta_group::2 MMAs:
+// each CTA copies its own A tile and only ITS HALF of the B tile into its own shared memory, the pair's leader issues one
+// 256 x TN x 32 MMA per K step that reads both CTAs' shared memory, each CTA's tensor memory receives its 128 rows.  Per slab an SM
+// takes 32 KB in and 32 KB out of shared memory instead of 48 + 48: the pipe that bounds the single-CTA kernel.  The peer's MMA warp
+// forwards "my stage is full" to the leader; the epilogue warps of both CTAs hand accumulators back to the leader.
+// Measured: bit-exact, 0.65x of the single-CTA kernel whatever the ring depth (profiles/r2_gemm_codes.txt); off by default.
 template <int TN_, int EC_, int OUT, bool PAIR = false>
 __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kernel(const GemmArgs g) {
     using Cfg = GemmCfg<TN_, EC_>;
@@ -394,7 +428,7 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
     const uint32_t tiles_m = uint32_t(g.m_pad / TM);
     const uint32_t w_count = PAIR ? ((tiles_m + 1) / 2) * g.tiles_n : g.n_tiles;
     extern __shared__ uint8_t smem_raw[];
-    __shared__ uint64_t bar_full[6], bar_empty[6], bar_tfull[Cfg::ACC], bar_tempty[Cfg::ACC];
+    __shared__ uint64_t bar_full[6], bar_empty[6], bar_pfull[6], bar_tfull[Cfg::ACC], bar_tempty[Cfg::ACC];
     __shared__ uint64_t bar_sfull[Cfg::SC_DEPTH], bar_sempty[Cfg::SC_DEPTH];
     __shared__ uint32_t tmem_base_slot;
 
@@ -402,16 +436,18 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
     const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;                 // stage bases on 1 KB
     uint8_t* const stage0 = smem_raw + (smem0 - smem_u32(smem_raw));
     const uint32_t stages = g.stages, slabs = g.slabs, gs = g.group_slabs;
-    uint8_t* const sc0 = stage0 + size_t(stages) * Cfg::STAGE_BYTES;
+    constexpr uint32_t STAGE = PAIR ? Cfg::STAGE_BYTES_PAIR : Cfg::STAGE_BYTES;
+    uint8_t* const sc0 = stage0 + size_t(stages) * STAGE;
 
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < stages; ++s) {
             mbar_init(&bar_full[s], 1);
-            mbar_init(&bar_empty[s], PAIR ? 2 : 1);    // the MMA's commit (of both CTAs of a pair)
+            mbar_init(&bar_empty[s], 1);               // the MMA's commit (pairs: the leader's, multicast)
+            mbar_init(&bar_pfull[s], 1);               // pairs, leader: the peer's stage is full
         }
         for (int a = 0; a < Cfg::ACC; ++a) {
             mbar_init(&bar_tfull[a], 1);
-            mbar_init(&bar_tempty[a], Cfg::EPI_WARPS);
+            mbar_init(&bar_tempty[a], PAIR ? 2 * Cfg::EPI_WARPS : Cfg::EPI_WARPS);    // pairs: both CTAs' epilogue warps, on the leader
         }
         for (int q = 0; q < Cfg::SC_DEPTH; ++q) {
             mbar_init(&bar_sfull[q], 1);
@@ -420,9 +456,15 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
         mbar_fence_init();
     }
     if (warp == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(Cfg::TMEM_COLS)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if constexpr (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(Cfg::TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(Cfg::TMEM_COLS)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -452,14 +494,15 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
                     }
                     const uint32_t s = it % stages, n = it / stages;
                     if (n > 0) mbar_wait(&bar_empty[s], (n - 1) & 1);
-                    uint8_t* st = stage0 + size_t(s) * Cfg::STAGE_BYTES;
-                    mbar_arrive_expect_tx(&bar_full[s], A_BYTES + b_rows * GK);
-                    bulk_load(st, g.a_codes + (size_t(i) * a_blocks + tm * (TM / 8)) * BLK_BYTES, A_BYTES, &bar_full[s]);
+                    uint8_t* st = stage0 + size_t(s) * STAGE;
                     if constexpr (PAIR) {
                         const uint32_t half = b_rows / 2 * GK;             // b_rows is 128 or 256: halves of whole 8-row blocks
-                        bulk_load_multicast(st + A_BYTES + pair_rank * half,
-                                            g.b_codes + (size_t(i) * b_blocks + tn * (TN / 8)) * BLK_BYTES + pair_rank * half, half, &bar_full[s], uint16_t(3));
+                        mbar_arrive_expect_tx(&bar_full[s], A_BYTES + half);
+                        bulk_load(st, g.a_codes + (size_t(i) * a_blocks + tm * (TM / 8)) * BLK_BYTES, A_BYTES, &bar_full[s]);
+                        bulk_load(st + A_BYTES, g.b_codes + (size_t(i) * b_blocks + tn * (TN / 8)) * BLK_BYTES + pair_rank * half, half, &bar_full[s]);
                     } else {
+                        mbar_arrive_expect_tx(&bar_full[s], A_BYTES + b_rows * GK);
+                        bulk_load(st, g.a_codes + (size_t(i) * a_blocks + tm * (TM / 8)) * BLK_BYTES, A_BYTES, &bar_full[s]);
                         bulk_load(st + A_BYTES, g.b_codes + (size_t(i) * b_blocks + tn * (TN / 8)) * BLK_BYTES, b_rows * GK, &bar_full[s]);
                     }
                 }
@@ -469,25 +512,49 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
     } else if (warp == 1) {
         // ===== MMA issuer: four 128 x TN x 32 MMAs per slab; a scale group accumulates in tensor memory =====
         uint32_t it = 0, gi = 0;
-        for (uint32_t w = w_first; w < w_count; w += w_step) {
-            for (uint32_t i = 0; i < slabs; ++i, ++it) {
-                const uint32_t s = it % stages, n = it / stages, a = gi % Cfg::ACC, u = gi / Cfg::ACC;
-                const bool first = i % gs == 0, last = i % gs == gs - 1;
-                if (first && u > 0) mbar_wait(&bar_tempty[a], (u - 1) & 1);
-                mbar_wait(&bar_full[s], n & 1);
-                tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t st_addr = smem0 + s * Cfg::STAGE_BYTES;
-                    const uint64_t da = umma_desc(st_addr, 128u, 1024u), db = umma_desc(st_addr + A_BYTES, 128u, 1024u);
-#pragma unroll
-                    for (uint32_t kk = 0; kk < GK / 32; ++kk)      // 32 K = two core matrices = 256 bytes further on
-                        tc_mma_f8(tmem_base + a * TN, da + kk * (256u >> 4), db + kk * (256u >> 4), Cfg::IDESC, (first && kk == 0) ? 0u : 1u);
-                    if constexpr (PAIR) tc_commit_multicast(&bar_empty[s], uint16_t(3));
-                    else tc_commit(&bar_empty[s]);
-                    if (last) tc_commit(&bar_tfull[a]);
+        if (PAIR && pair_rank != 0) {
+            // the pair's second CTA issues no MMA: tell the leader when this CTA's stage is full
+            for (uint32_t w = w_first; w < w_count; w += w_step)
+                for (uint32_t i = 0; i < slabs; ++i, ++it) {
+                    mbar_wait(&bar_full[it % stages], (it / stages) & 1);
+                    if (lane == 0) mbar_arrive_remote(&bar_pfull[it % stages], 0u);
+                    __syncwarp();
                 }
-                __syncwarp();
-                if (last) ++gi;
+        } else {
+            for (uint32_t w = w_first; w < w_count; w += w_step) {
+                const size_t b_left = g.n_pad - size_t(w % g.tiles_n) * TN;
+                const uint32_t b_rows = b_left < size_t(TN) ? uint32_t(b_left) : uint32_t(TN);
+                // pairs: M = 256 over both CTAs, N = the tile's columns (each CTA holds half of the B rows)
+                const uint32_t idesc = PAIR ? ((1u << 4) | ((b_rows >> 3) << 17) | (uint32_t(256 >> 4) << 24)) : Cfg::IDESC;
+                for (uint32_t i = 0; i < slabs; ++i, ++it) {
+                    const uint32_t s = it % stages, n = it / stages, a = gi % Cfg::ACC, u = gi / Cfg::ACC;
+                    const bool first = i % gs == 0, last = i % gs == gs - 1;
+                    if (first && u > 0) {
+                        if constexpr (PAIR) mbar_wait_cluster(&bar_tempty[a], (u - 1) & 1);
+                        else mbar_wait(&bar_tempty[a], (u - 1) & 1);
+                    }
+                    mbar_wait(&bar_full[s], n & 1);
+                    if constexpr (PAIR) mbar_wait_cluster(&bar_pfull[s], n & 1);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t st_addr = smem0 + s * STAGE;
+                        const uint64_t da = umma_desc(st_addr, 128u, 1024u), db = umma_desc(st_addr + A_BYTES, 128u, 1024u);
+#pragma unroll
+                        for (uint32_t kk = 0; kk < GK / 32; ++kk) {     // 32 K = two core matrices = 256 bytes further on
+                            if constexpr (PAIR) tc_mma_f8_duo(tmem_base + a * TN, da + kk * (256u >> 4), db + kk * (256u >> 4), idesc, (first && kk == 0) ? 0u : 1u);
+                            else tc_mma_f8(tmem_base + a * TN, da + kk * (256u >> 4), db + kk * (256u >> 4), idesc, (first && kk == 0) ? 0u : 1u);
+                        }
+                        if constexpr (PAIR) {
+                            tc_commit_duo(&bar_empty[s]);
+                            if (last) tc_commit_duo(&bar_tfull[a]);
+                        } else {
+                            tc_commit(&bar_empty[s]);
+                            if (last) tc_commit(&bar_tfull[a]);
+                        }
+                    }
+                    __syncwarp();
+                    if (last) ++gi;
+                }
             }
         }
     } else if (warp >= 4) {
@@ -538,7 +605,10 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
                         // every column of this accumulator is in registers: hand it back before the arithmetic
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&bar_tempty[a]);
+                        if (lane == 0) {
+                            if (PAIR && pair_rank != 0) mbar_arrive_remote(&bar_tempty[a], 0u);       // the leader issues the MMAs
+                            else mbar_arrive(&bar_tempty[a]);
+                        }
                     }
 #pragma unroll
                     for (int i = 0; i < 2; ++i) {
@@ -638,7 +708,8 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
     if constexpr (PAIR) cluster_sync_all();            // nothing of the peer is in flight towards this CTA's shared memory any more
     if (warp == 0) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+        if constexpr (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(Cfg::TMEM_COLS) : "memory");
     }
 }
 
@@ -775,7 +846,7 @@ int launch_gemm(GemmArgs& g, cudaStream_t st) {
 template <int TN_, int EC_, int OUT>
 int launch_gemm_pair(GemmArgs& g, cudaStream_t st) {
     using Cfg = GemmCfg<TN_, EC_>;
-    if (int(g.stages) > Cfg::MAX_STAGES) g.stages = Cfg::MAX_STAGES;
+    if (g_tun.gemm_stages >= 6 || int(g.stages) > Cfg::MAX_STAGES_PAIR) g.stages = Cfg::MAX_STAGES_PAIR;     // default: as deep as fits
     const size_t tiles_n = (g.n_pad + TN_ - 1) / TN_, tiles_m = g.m_pad / TM;
     const size_t pairs = (tiles_m + 1) / 2 * tiles_n;
     if (tiles_m * tiles_n > 0x7fffffffull) return FPQ_ERR_UNSUPPORTED;
@@ -788,7 +859,7 @@ int launch_gemm_pair(GemmArgs& g, cudaStream_t st) {
     cudaGetDevice(&dev);
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(Cfg::THREADS);
-    cfg.dynamicSmemBytes = Cfg::smem_bytes(int(g.stages));
+    cfg.dynamicSmemBytes = Cfg::smem_bytes_pair(int(g.stages));
     cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -798,7 +869,7 @@ int launch_gemm_pair(GemmArgs& g, cudaStream_t st) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     if (!attr_set[dev & 63]) {
-        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::smem_bytes(Cfg::MAX_STAGES))) != cudaSuccess) return finish_launch();
+        if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg::smem_bytes_pair(Cfg::MAX_STAGES_PAIR))) != cudaSuccess) return finish_launch();
         cfg.gridDim = dim3(unsigned(sm_count()) / 2 * 2);
         int n = 0;
         if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) != cudaSuccess || n < 1) { cudaGetLastError(); n = sm_count() / 2 - 4; }

@@ -123,7 +123,7 @@ def bench(dev, shapes):
         flop = 2.0 * m * n * k
         res = {}
         ar, wr = lowbit.pack_codes(x, "e2m1", True), lowbit.pack_codes(wt, "e2m1", True)
-        for tn, ec, st, pair in ((256, 128, 4, 1), (256, 128, 4, 0), (256, 64, 4, 0), (128, 32, 6, 0), (128, 64, 6, 0), (128, 128, 6, 0)):
+        for tn, ec, st, pair in ((256, 128, 6, 1), (256, 128, 4, 0), (256, 64, 4, 0), (128, 32, 6, 0), (128, 64, 6, 0), (128, 128, 6, 0)):
             L.set_tunable("gemm_stages", st)
             L.set_tunable("gemm_tile_n", tn)
             L.set_tunable("gemm_epi_cols", ec)
