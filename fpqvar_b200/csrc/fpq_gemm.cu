@@ -309,17 +309,6 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank)
         "}\n" ::"r"(smem_u32(bar)), "r"(rank)
         : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {      // acquire at cluster scope
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "FPQ_WAITC:\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra FPQ_DONEC;\n"
-        "bra FPQ_WAITC;\n"
-        "FPQ_DONEC:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -530,11 +519,10 @@ __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kern
                     const uint32_t s = it % stages, n = it / stages, a = gi % Cfg::ACC, u = gi / Cfg::ACC;
                     const bool first = i % gs == 0, last = i % gs == gs - 1;
                     if (first && u > 0) {
-                        if constexpr (PAIR) mbar_wait_cluster(&bar_tempty[a], (u - 1) & 1);
-                        else mbar_wait(&bar_tempty[a], (u - 1) & 1);
+                        mbar_wait(&bar_tempty[a], (u - 1) & 1);
                     }
                     mbar_wait(&bar_full[s], n & 1);
-                    if constexpr (PAIR) mbar_wait_cluster(&bar_pfull[s], n & 1);
+                    if constexpr (PAIR) mbar_wait(&bar_pfull[s], n & 1);       // arrived on from the peer CTA (release.cluster)
                     tc_fence_after();
                     if (lane == 0) {
                         const uint32_t st_addr = smem0 + s * STAGE;
