@@ -63,7 +63,7 @@ struct Tunables {
     long long rot_small_max_chunks = 40000;    // rotate launches up to this many 128-chunks take the small-launch kernel (measured: VAR-d30 stage 4, 37 500 chunks, 9.95 vs 11.0 us)
     int smem_kb = 0;                           // shared-memory carveout (KB per SM) every activation kernel asks for; 0 = leave it to the driver
     int gemm_stages = 6;                       // shared-memory ring depth of the low-bit GEMM (2..6 stages of 32 KB, 2..4 of 48 KB with 256-column tiles)
-    int gemm_pair = 0;                         // CTA pairs with cta_group::2 MMAs (default tile shape only): 1 on | 0 off (default: bit-exact but slower so far) | -1 on for >= 4 row tiles
+    int gemm_pair = -1;                        // CTA pairs with cta_group::2 MMAs (default tile shape only): 1 on | 0 off | -1 (default) on for row scales and >= 4 row tiles
     int gemm_tile_n = 256;                     // C tile columns of the low-bit GEMM: 128 | 256
     int gemm_epi_cols = 128;                   // columns per epilogue warp: 32 (128-column tiles only) | 64 | 128; fewer = more epilogue warps per scheduler (measured: no faster)
 };

@@ -24,7 +24,8 @@
 // once per tile.  fp16 C tiles leave through a per-warp staging buffer in shared memory (whole-line stores).
 // Measured (B200, profiles/r2_gemm_codes.txt; the fp16 library GEMM on the fake-quantized tensors: 1.44-1.48 PFLOP/s):
 //   row scales 2.1-2.55 PFLOP/s: the SM's shared-memory pipe (48 KB in + 48 KB out per 128 x 256 slab at 128 B/clk = 768 clk; CTA
-//   pairs sharing B by multicast were no faster, cta_group::2 MMAs -- PAIR below -- are bit-exact but slower so far);
+//   pairs sharing B by multicast were no faster, cta_group::2 MMAs -- PAIR below -- gain 3-4 %: neither the L2 cap nor the
+//   shared-memory pipe alone explains the distance to the 512 clk of MMA per slab);
 //   groups of 128 1.04-1.49 PFLOP/s: the epilogue's 2 flops per element (512 clk of the fp32 pipe per 128 x 256 slab, as long as
 //   the slab's MMAs) and its tensor-memory loads do not fully overlap with a memory-bound main loop; DESIGN.md 3.6 has the
 //   experiments (tcgen05.ld alone: ~1 KB/clk per SM, tools/tmem_ldbench.cu; epilogue compiled out; per-tile overhead).
@@ -299,13 +300,15 @@ __device__ __forceinline__ void tc_commit_duo(uint64_t* bar) {          // arriv
                  "h"(uint16_t(3))
                  : "memory");
 }
-// arrive on the barrier at this offset in CTA `rank` of the cluster
+// arrive on the barrier at this offset in CTA `rank` of the cluster.  Default semantics (release at CTA scope), as CUTLASS's
+// ClusterBarrier does: `.release.cluster` compiles to a cluster-wide fence (ERRBAR) in front of every arrive, and the forwarding
+// warp then hands over one stage per fence latency (~1400 clk: the whole kernel ran at that pace, profiles/r2_gemm_codes.txt)
 __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t rank) {
     asm volatile(
         "{\n"
         ".reg .b32 ra;\n"
         "mapa.shared::cluster.u32 ra, %0, %1;\n"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n"
         "}\n" ::"r"(smem_u32(bar)), "r"(rank)
         : "memory");
 }
@@ -405,7 +408,8 @@ struct GemmCfg {
 // 256 x TN x 32 MMA per K step that reads both CTAs' shared memory, each CTA's tensor memory receives its 128 rows.  Per slab an SM
 // takes 32 KB in and 32 KB out of shared memory instead of 48 + 48: the pipe that bounds the single-CTA kernel.  The peer's MMA warp
 // forwards "my stage is full" to the leader; the epilogue warps of both CTAs hand accumulators back to the leader.
-// Measured: bit-exact, 0.65x of the single-CTA kernel whatever the ring depth (profiles/r2_gemm_codes.txt); off by default.
+// Measured (profiles/r2_gemm_codes.txt): bit-exact; row scales 2.42 / 2.63 PFLOP/s against 2.36 / 2.52 for single CTAs, groups of 128
+// 1.31 / 1.44 against 1.40 / 1.52 -- so pairs are the default for row scales only.
 template <int TN_, int EC_, int OUT, bool PAIR = false>
 __global__ void __launch_bounds__(GemmCfg<TN_, EC_>::THREADS, 1) gemm_codes_kernel(const GemmArgs g) {
     using Cfg = GemmCfg<TN_, EC_>;
@@ -879,7 +883,8 @@ int launch_gemm_tn(GemmArgs& g, cudaStream_t st) {
         return launch_gemm<128, 128, OUT>(g, st);
     }
     if (ec == 64) return launch_gemm<256, 64, OUT>(g, st);
-    const bool pair = g_tun.gemm_pair == 1 || (g_tun.gemm_pair < 0 && g.m_pad / TM >= 4);
+    // default (-1): CTA pairs where they were measured faster -- row scales (+3-4 %), not groups of 128 (-6 %)
+    const bool pair = g_tun.gemm_pair == 1 || (g_tun.gemm_pair < 0 && g.group_slabs != 1 && g.slabs > 1 && g.m_pad / TM >= 4);
     return pair ? launch_gemm_pair<256, 128, OUT>(g, st) : launch_gemm<256, 128, OUT>(g, st);
 }
 

@@ -297,8 +297,8 @@ FPQ_API int fpq_nibbles_to_codes(const uint8_t *nibbles, size_t n_codes, int for
  * (2.0-2.5 PFLOP/s; the fp16 library GEMM on the fake-quantized tensors runs at 1.4-1.5).
  * Tunables: "gemm_tile_n" (128 | 256, default 256), "gemm_epi_cols" (columns per epilogue warp: 32 | 64 | 128, default 128),
  * "gemm_stages" (2..6, default 6; as many as fit: 3 with 256-column tiles and the fp16 staging buffer), "gemm_pair" (1: clusters
- * of two CTAs with cta_group::2 MMAs, each holding half of the B tile; 0 = default: the pair path is bit-exact but slower so far;
- * -1: on for >= 4 row tiles).  Results never depend on them.
+ * of two CTAs with cta_group::2 MMAs, each holding half of the B tile; 0: single CTAs; -1 = default: pairs for row scales and >= 4
+ * row tiles, where they measured 3-4 % faster).  Results never depend on them.
  */
 FPQ_API int fpq_gemm_codes(const uint8_t *a_codes, const float *a_scales, size_t m, const uint8_t *b_codes,
                    const float *b_scales, size_t n, size_t k, size_t scale_group, const float *bias, int out_dtype,

@@ -103,7 +103,7 @@ def test_gemm_codes_bit_exact_against_the_fixed_order_oracle(m, n, k, tile_n, ep
         L.set_tunable("gemm_stages", 6)
         L.set_tunable("gemm_tile_n", 256)
         L.set_tunable("gemm_epi_cols", 128)
-        L.set_tunable("gemm_pair", 0)
+        L.set_tunable("gemm_pair", -1)
     assert np.array_equal(bits(c32), bits(LB.gemm_codes(qa, sa, qw, sw, bias)))
     assert np.array_equal(bits(c16), bits(LB.gemm_codes(qa, sa, qw, sw).astype(np.float16)))
 
@@ -126,7 +126,7 @@ def test_gemm_codes_many_tiles_per_cta():
         finally:
             L.set_tunable("gemm_tile_n", 256)
             L.set_tunable("gemm_epi_cols", 128)
-            L.set_tunable("gemm_pair", 0)
+            L.set_tunable("gemm_pair", -1)
         assert np.array_equal(bits(c), bits(want))
         assert np.array_equal(bits(c16), bits(want.astype(np.float16)))
 
@@ -181,7 +181,7 @@ def test_fused_output_level_loss(ref_dtype, per_row):
             got_w = lowbit.linear_codes_sse(a, ww, ref, bias, None, rw).item()
         finally:
             L.set_tunable("gemm_tile_n", 256)
-            L.set_tunable("gemm_pair", 0)
+            L.set_tunable("gemm_pair", -1)
         assert abs(got - want) <= 2e-6 * want          # fp32 squares along a row piece, then float64
         want_w = (((ref.double() - y.double()) ** 2).sum(1) * rw).sum().item()
         assert abs(got_w - want_w) <= 2e-6 * want_w

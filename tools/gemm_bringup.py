@@ -134,7 +134,7 @@ def bench(dev, shapes):
         L.set_tunable("gemm_stages", 6)
         L.set_tunable("gemm_tile_n", 256)
         L.set_tunable("gemm_epi_cols", 128)
-        L.set_tunable("gemm_pair", 0)
+        L.set_tunable("gemm_pair", -1)
         res["sse g128"] = timeit(lambda: lowbit.linear_codes_sse(a, w, out))
         t_packrow = timeit(lambda: lowbit.pack_codes(x, "e2m1", True))
         t_pack = timeit(lambda: lowbit.pack_codes(x, "e2m1"))
@@ -166,7 +166,7 @@ if __name__ == "__main__":
         ok2 = check_gemm(dev) and ok2
     L.set_tunable("gemm_tile_n", 256)
     L.set_tunable("gemm_epi_cols", 128)
-    L.set_tunable("gemm_pair", 0)
+    L.set_tunable("gemm_pair", -1)
     print(f"parity ladder took {time.time() - t0:.1f} s")
     if ok2 or "--bench" in sys.argv:
         shapes = [("d30 mat_qkv stage 9", 25600, 5760, 1920), ("d30 fc1 stage 9", 25600, 7680, 1920), ("d30 proj stage 9", 25600, 1920, 1920),

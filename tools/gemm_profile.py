@@ -1,5 +1,5 @@
 """Six launches of the low-bit GEMM at the largest VAR-d30 mat_qkv shape (warm-up three, then three to capture with
-ncu -k regex:gemm_codes -s 3 -c 3): groups of 128 with 128- and 256-column tiles, row scales with 256-column tiles."""
+ncu -k regex:gemm_codes -s 3 -c 3): groups of 128, row scales, row scales with CTA pairs (all 256-column tiles)."""
 import os
 import sys
 
@@ -17,12 +17,13 @@ a, ww = lowbit.pack_codes(x, "e2m1"), lowbit.pack_codes(w, "e2m1")
 ar, wr = lowbit.pack_codes(x, "e2m1", True), lowbit.pack_codes(w, "e2m1", True)
 out = torch.empty(m, n, device=dev, dtype=torch.float16)
 for _ in range(2):
-    L.set_tunable("gemm_tile_n", 128)
-    L.set_tunable("gemm_stages", 6)
-    lowbit.linear_codes(a, ww, None, torch.float16, out)
     L.set_tunable("gemm_tile_n", 256)
-    L.set_tunable("gemm_stages", 4)
-    lowbit.linear_codes(a, ww, None, torch.float16, out)
-    lowbit.linear_codes(ar, wr, None, torch.float16, out)
+    L.set_tunable("gemm_stages", 6)
+    L.set_tunable("gemm_pair", 0)
+    lowbit.linear_codes(a, ww, None, torch.float16, out)          # groups of 128, single CTAs
+    lowbit.linear_codes(ar, wr, None, torch.float16, out)         # row scales, single CTAs
+    L.set_tunable("gemm_pair", 1)
+    lowbit.linear_codes(ar, wr, None, torch.float16, out)         # row scales, CTA pairs (cta_group::2)
+    L.set_tunable("gemm_pair", -1)
     torch.cuda.synchronize()
 print("ok")
