@@ -24,8 +24,8 @@
 // once per tile.  fp16 C tiles leave through a per-warp staging buffer in shared memory (whole-line stores).
 // Measured (B200, profiles/r2_gemm_codes.txt; the fp16 library GEMM on the fake-quantized tensors: 1.44-1.48 PFLOP/s):
 //   row scales 2.1-2.55 PFLOP/s: the SM's shared-memory pipe (48 KB in + 48 KB out per 128 x 256 slab at 128 B/clk = 768 clk; CTA
-//   pairs sharing B by multicast were no faster, cta_group::2 MMAs -- PAIR below -- gain 3-4 %: neither the L2 cap nor the
-//   shared-memory pipe alone explains the distance to the 512 clk of MMA per slab);
+//   pairs sharing B by multicast were no faster, cta_group::2 MMAs -- PAIR below -- gain 3-4 %; the operand layout feeds the MMAs at
+//   full rate (tools/umma_bench.cu): what is left is bytes in flight over the stage-recycle latency, ~2400 clk under a loaded L2);
 //   groups of 128 1.04-1.49 PFLOP/s: the epilogue's 2 flops per element (512 clk of the fp32 pipe per 128 x 256 slab, as long as
 //   the slab's MMAs) and its tensor-memory loads do not fully overlap with a memory-bound main loop; DESIGN.md 3.6 has the
 //   experiments (tcgen05.ld alone: ~1 KB/clk per SM, tools/tmem_ldbench.cu; epilogue compiled out; per-tile overhead).
