@@ -294,7 +294,7 @@ FPQ_API int fpq_nibbles_to_codes(const uint8_t *nibbles, size_t n_codes, int for
  * c: [m, ldc] row-major, FPQ_F16 | FPQ_F32, 16-byte aligned, n % 8 == 0, ldc % 8 == 0; bias: fp32 [n] or NULL.
  * Persistent kernel, one CTA per SM, 128 x 256 (or 128 x 128) tiles of C, ~205 KB of shared memory.  With groups of 128 every
  * accumulator is handed to the epilogue warps once per 128 K (1.0-1.45 PFLOP/s on a B200); with row scales once per tile
- * (2.0-2.5 PFLOP/s; the fp16 library GEMM on the fake-quantized tensors runs at 1.4-1.5).
+ * (2.1-2.6 PFLOP/s; the fp16 library GEMM on the fake-quantized tensors runs at 1.4-1.5).
  * Tunables: "gemm_tile_n" (128 | 256, default 256), "gemm_epi_cols" (columns per epilogue warp: 32 | 64 | 128, default 128),
  * "gemm_stages" (2..6, default 6; as many as fit: 3 with 256-column tiles and the fp16 staging buffer), "gemm_pair" (1: clusters
  * of two CTAs with cta_group::2 MMAs, each holding half of the B tile; 0: single CTAs; -1 = default: pairs for row scales and >= 4
