@@ -158,6 +158,28 @@ def test_row_scaled_codes_and_gemm(fmt_a, fmt_w, dtype):
         assert np.all(np.abs(c.astype(np.float64) - want) <= 2.0 ** -20 * mag)
 
 
+@pytest.mark.parametrize("pair", [-1, 0, 1])
+def test_row_scaled_gemm_default_pairing(pair):
+    """Row scales with enough row tiles for the default (gemm_pair = -1) to launch CTA pairs with cta_group::2 MMAs, an odd number of
+    row tiles (phantom second tile in the last pair) and a half tile column: bit-exact (e2m1: the sums are exact), whatever the pairing."""
+    rng = np.random.default_rng(17)
+    m, n, k = 128 * 7 - 3, 256 * 2 + 128, 2304
+    x = rng.standard_normal((m, k)).astype(np.float16)
+    w = (rng.standard_normal((n, k)) * 0.05).astype(np.float32)
+    bias = rng.standard_normal(n).astype(np.float32)
+    a = lowbit.pack_codes(torch.from_numpy(x).to(dev()), "e2m1", per_row=True)
+    ww = lowbit.pack_codes(torch.from_numpy(w).to(dev()), "e2m1", per_row=True)
+    (qa, sa), (qw, sw) = LB.quantize_codes(x, "e2m1", None), LB.quantize_codes(w, "e2m1", None)
+    L.set_tunable("gemm_pair", pair)
+    try:
+        c32 = lowbit.linear_codes(a, ww, torch.from_numpy(bias).to(dev()), torch.float32).cpu().numpy()
+        c16 = lowbit.linear_codes(a, ww, None, torch.float16).cpu().numpy()
+    finally:
+        L.set_tunable("gemm_pair", -1)
+    assert np.array_equal(bits(c32), bits(LB.gemm_codes(qa, sa, qw, sw, bias)))
+    assert np.array_equal(bits(c16), bits(LB.gemm_codes(qa, sa, qw, sw).astype(np.float16)))
+
+
 @pytest.mark.parametrize("ref_dtype", [torch.float32, torch.float16])
 @pytest.mark.parametrize("per_row", [False, True])
 def test_fused_output_level_loss(ref_dtype, per_row):
