@@ -40,9 +40,25 @@ class PackedCodes:
     def rows_pad(self) -> int:
         return rows_padded(self.rows)
 
+    def check(self, what: str) -> "PackedCodes":
+        """The kernels index these buffers from rows / k / scale_group alone: refuse anything that does not match."""
+        k, sg = self.k, self.scale_group
+        if k <= 0 or k % GROUP != 0 or sg not in (GROUP, k) or self.rows < 0:
+            raise L.FpqError(f"{what}: inconsistent PackedCodes (rows {self.rows}, k {k}, scale_group {sg})")
+        for t, dt, n, name in ((self.codes, torch.uint8, self.rows_pad * k, "codes"),
+                               (self.scales, torch.float32, (k // sg) * self.rows_pad, "scales")):
+            if not isinstance(t, torch.Tensor) or not t.is_cuda or t.dtype != dt or t.numel() != n or not t.is_contiguous():
+                raise L.FpqError(f"{what}: `{name}` must be a contiguous CUDA {dt} tensor of {n} elements")
+        if self.codes.device != self.scales.device:
+            raise L.FpqError(f"{what}: codes and scales live on different devices")
+        return self
+
     def dequantize(self, dtype=torch.float16) -> torch.Tensor:
         """The fake-quantized tensor these codes stand for ([rows, k]); bit-identical to ops.fake_quant of the packed input
         when `dtype` is the input's dtype."""
+        self.check("dequantize")
+        if dtype not in _DT:
+            raise L.FpqError(f"dequantize: dtype {dtype} is not supported (float16 / float32 only)")
         out = torch.empty((self.rows, self.k), dtype=dtype, device=self.codes.device)
         with _on_device(self.codes) as dev:
             L.check(L.lib().fpq_unpack_codes(self.codes.data_ptr(), self.scales.data_ptr(), self.rows, self.k, self.scale_group,
@@ -51,6 +67,7 @@ class PackedCodes:
 
     def to_nibbles(self) -> torch.Tensor:
         """4-bit storage (FP4 formats only): uint8 [rows_pad * k / 2]."""
+        self.check("to_nibbles")
         nib = torch.empty(self.codes.numel() // 2, dtype=torch.uint8, device=self.codes.device)
         with _on_device(self.codes) as dev:
             L.check(L.lib().fpq_codes_to_nibbles(self.codes.data_ptr(), self.codes.numel(), L.FMT[self.fmt], nib.data_ptr(),
@@ -60,11 +77,15 @@ class PackedCodes:
     @staticmethod
     def from_nibbles(nib: torch.Tensor, scales: torch.Tensor, rows: int, k: int, fmt: str, scale_group: int = GROUP) -> "PackedCodes":
         _require_cuda(nib, "from_nibbles")
+        if nib.dtype != torch.uint8 or not nib.is_contiguous() or nib.numel() * 2 != rows_padded(rows) * k:
+            raise L.FpqError(f"from_nibbles: expected a contiguous uint8 tensor of {rows_padded(rows) * k // 2} bytes")
+        if fmt not in FP4_FORMATS:
+            raise L.FpqError(f"from_nibbles: {fmt} has no 4-bit form (FP4 formats only)")
         codes = torch.empty(nib.numel() * 2, dtype=torch.uint8, device=nib.device)
         with _on_device(nib) as dev:
             L.check(L.lib().fpq_nibbles_to_codes(nib.data_ptr(), codes.numel(), L.FMT[fmt], codes.data_ptr(), _stream(dev)),
                     f"fpq_nibbles_to_codes({fmt})")
-        return PackedCodes(codes, scales, rows, k, fmt, scale_group)
+        return PackedCodes(codes, scales, rows, k, fmt, scale_group).check("from_nibbles")
 
 
 def pack_codes(x: torch.Tensor, fmt: str, per_row: bool = False) -> PackedCodes:
@@ -96,6 +117,8 @@ def pack_codes(x: torch.Tensor, fmt: str, per_row: bool = False) -> PackedCodes:
 def linear_codes(a: PackedCodes, w: PackedCodes, bias: Optional[torch.Tensor] = None, out_dtype=torch.float16,
                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """F.linear(a, w, bias) for packed operands: [a.rows, w.rows] in `out_dtype`."""
+    a.check("linear_codes(a)")
+    w.check("linear_codes(w)")
     if a.k != w.k:
         raise L.FpqError(f"linear_codes: inner sizes differ ({a.k} vs {w.k})")
     if a.codes.device != w.codes.device:
@@ -116,7 +139,7 @@ def linear_codes(a: PackedCodes, w: PackedCodes, bias: Optional[torch.Tensor] = 
         _require_cuda(bias, "linear_codes(bias)")
         if bias.numel() != n:
             raise L.FpqError(f"linear_codes: bias has {bias.numel()} entries, expected {n}")
-        b = bias.detach().to(torch.float32).contiguous()
+        b = bias.detach().to(device=a.codes.device, dtype=torch.float32).contiguous()
     with _on_device(a.codes) as dev:
         L.check(L.lib().fpq_gemm_codes(a.codes.data_ptr(), a.scales.data_ptr(), m, w.codes.data_ptr(), w.scales.data_ptr(), n, a.k,
                                        a.scale_group, None if b is None else b.data_ptr(), _DT[out_dtype], out.data_ptr(), n,
@@ -130,6 +153,8 @@ def linear_codes_sse(a: PackedCodes, w: PackedCodes, ref: torch.Tensor, bias: Op
     of the format search (search/search_fp4_format.py:472-476, :798-816).  ref: [a.rows, w.rows] float16 / float32, contiguous;
     row_weight: float64 [a.rows] or None (= 1); returns (and accumulates into) a one-element float64 tensor."""
     _require_cuda(ref, "linear_codes_sse(ref)")
+    a.check("linear_codes_sse(a)")
+    w.check("linear_codes_sse(w)")
     m, n = a.rows, w.rows
     if a.k != w.k or (a.scale_group == GROUP) != (w.scale_group == GROUP):
         raise L.FpqError("linear_codes_sse: operands do not match")

@@ -292,3 +292,13 @@ def test_gemm_codes_argument_errors():
         lowbit.pack_codes(torch.randn(8, 128), "e2m1")
     with pytest.raises(ValueError):
         lowbit.pack_codes(torch.randn(8, 128, device=dev()), "fp_e9")
+    # hand-made PackedCodes whose buffers do not match their shape never reach the kernel
+    bad = lowbit.PackedCodes(a.codes[:-128], a.scales, a.rows, a.k, a.fmt)
+    with pytest.raises(L.FpqError):
+        lowbit.linear_codes(bad, a)
+    bad = lowbit.PackedCodes(a.codes, a.scales.double(), a.rows, a.k, a.fmt)
+    with pytest.raises(L.FpqError):
+        bad.dequantize()
+    bad = lowbit.PackedCodes(a.codes.cpu(), a.scales, a.rows, a.k, a.fmt)
+    with pytest.raises(L.FpqError):
+        lowbit.linear_codes(a, bad)
