@@ -33,11 +33,10 @@ class FPQuant(torch.autograd.Function):
 
 def compute_quant_error(x: torch.Tensor, w: torch.Tensor, learnable_s: torch.Tensor, Q: torch.Tensor) -> torch.Tensor:
     """learnable_transformation_mat_qkv_fp4.py:104-138 (`compute_quant_error` == `compute_quant_error_v1`)."""
-    fp_result = torch.matmul(x, w.T)
-    x_2_quant = FPQuant.apply(torch.matmul(x * learnable_s, Q))
-    w_2_quant = FPQuant.apply(torch.matmul(w / learnable_s, Q))
-    quant_result = torch.matmul(x_2_quant, w_2_quant.T)
-    return torch.mean((fp_result - quant_result) ** 2)
+    target = x @ w.T                                                   # the full-precision layer output
+    act_q = FPQuant.apply((x * learnable_s) @ Q)                       # smoothed, rotated, fake-quantized activation
+    wgt_q = FPQuant.apply((w / learnable_s) @ Q)                       # inverse-smoothed, rotated, fake-quantized weight
+    return ((target - act_q @ wgt_q.T) ** 2).mean()
 
 
 compute_quant_error_v1 = compute_quant_error
