@@ -102,6 +102,34 @@ def test_fixed_order_gemm_against_float64(fmt_a, fmt_w):
     assert np.all(np.abs(c - lin) <= 2.0 ** -10 * mag)               # fp16 rounding of q * s on the activation side
 
 
+@pytest.mark.parametrize("fmt", FMTS)
+@pytest.mark.parametrize("dtype", [np.float16, np.float32])
+def test_row_scaled_codes_are_the_per_token_functions(fmt, dtype):
+    """scale_group=None: one scale per row, fp6_quant_*_per_token_cuda / the per_channel weight functions (qu.py:503-534)."""
+    rng = np.random.default_rng(6)
+    x = adversarial(rng, 9, 384, dtype)
+    q, s = LB.quantize_codes(x, fmt, None)
+    assert s.shape == (9, 1)
+    out_dt = np.float16 if fmt in ("e2m3", "e3m2") else dtype
+    want = O.fake_quant(x, fmt, None, "kernel", out_dtype=out_dt)
+    assert np.array_equal(bits(LB.dequantize(q, s, out_dt)), bits(want))
+    codes, scales = LB.pack_codes(x, fmt, None)
+    assert codes.size == 128 * 384 and scales.shape == (1, 128)
+    assert np.array_equal(bits(scales[0, :9]), bits(s[:, 0])) and not scales[0, 9:].any()
+
+
+def test_row_scaled_gemm_oracle_against_float64():
+    rng = np.random.default_rng(8)
+    m, n, k = 17, 24, 640
+    x = rng.standard_normal((m, k)).astype(np.float16)
+    w = (rng.standard_normal((n, k)) * 0.05).astype(np.float32)
+    (qa, sa), (qw, sw) = LB.quantize_codes(x, "e2m1", None), LB.quantize_codes(w, "e2m1", None)
+    c = LB.gemm_codes(qa, sa, qw, sw)
+    ref = LB.linear_f64(qa, sa, qw, sw)
+    # one exact sum, two roundings (P * sa, then * sw): 2^-22 relative
+    assert np.all(np.abs(c - ref) <= 2.0 ** -22 * np.abs(ref) + 1e-30)
+
+
 def test_gemm_oracle_slab_order_matters_only_in_rounding():
     rng = np.random.default_rng(5)
     qa = rng.choice(O.GRIDS["e2m1"], (8, 256)).astype(np.float32)
