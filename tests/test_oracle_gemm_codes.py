@@ -151,3 +151,17 @@ def test_c_abi_exports_the_low_bit_entry_points():
     lib.fpq_codes_rows_padded.restype = ctypes.c_size_t
     lib.fpq_codes_rows_padded.argtypes = [ctypes.c_size_t]
     assert lib.fpq_codes_rows_padded(68000) == 68096 and lib.fpq_codes_rows_padded(128) == 128
+
+
+def test_lowbit_host_layer_has_no_cpu_path():
+    """The product raises on CPU tensors and on malformed PackedCodes before anything reaches the library (no fallback)."""
+    import torch
+    from fpqvar_b200 import _lib as L, lowbit
+    with pytest.raises(L.FpqError):
+        lowbit.pack_codes(torch.randn(8, 128), "e2m1")
+    p = lowbit.PackedCodes(torch.zeros(128 * 128, dtype=torch.uint8), torch.zeros(1, 128), 8, 128, "e2m1")
+    with pytest.raises(L.FpqError):
+        lowbit.linear_codes(p, p)
+    with pytest.raises(L.FpqError):
+        p.dequantize()
+    assert lowbit.rows_padded(1) == 128 and lowbit.rows_padded(129) == 256
